@@ -1,0 +1,218 @@
+/*
+ * contextsv_b200.h -- C ABI of the B200-native alignment-scan hot path.
+ *
+ * This is the only door into the CUDA code: plain pointers and sizes, no C++
+ * or torch types.  ContextSV itself has no FFI for this path;
+ * each entry point therefore cites the reference C++ interface it stands
+ * behind.  File:line citations are relative to the ContextSV source tree.
+ *
+ * Conventions: no exception ever crosses this boundary; every
+ * call returns a csv_status (0 = ok) and leaves a message retrievable with
+ * csv_last_error() (thread-local).  A csv_ctx owns one CUDA stream and its
+ * scratch buffers on one device; it is NOT thread-safe -- create one per host
+ * thread (the reference runs one processChromosome task per ThreadPool
+ * worker, sv_caller.cpp:828-851).  Different contexts never share state.
+ * There is no CPU fallback: without a usable GPU every compute entry point
+ * fails with CSV_ERR_CUDA.
+ */
+#ifndef CONTEXTSV_B200_H
+#define CONTEXTSV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CSV_OK = 0,
+    CSV_ERR_CUDA = 1,       /* CUDA runtime error / no device                      */
+    CSV_ERR_ARG = 2,        /* invalid argument                                    */
+    CSV_ERR_CAPACITY = 3,   /* caller buffer too small (required size is reported) */
+    CSV_ERR_LIMIT = 4,      /* batch exceeds an implementation limit               */
+    CSV_ERR_STATE = 5       /* call out of order (e.g. fetch before run)           */
+} csv_status;
+
+/* ------------------------------------------------------------------ context */
+
+typedef struct csv_ctx csv_ctx;
+
+int  csv_ctx_create(int device, csv_ctx** out);
+void csv_ctx_destroy(csv_ctx* ctx);
+int  csv_ctx_sync(csv_ctx* ctx);                 /* wait for everything enqueued so far  */
+const char* csv_last_error(void);                /* thread-local, never NULL             */
+const char* csv_version(void);
+
+/* Pinned host memory for SoA buffers and results (cudaHostAlloc). */
+void* csv_host_alloc(size_t bytes);
+void  csv_host_free(void* p);
+
+/* Device timing on the context's own stream (CUDA events).  bench.py uses
+ * these because torch.cuda.Event only sees torch's current stream. */
+int csv_timer_begin(csv_ctx* ctx);
+int csv_timer_end(csv_ctx* ctx, float* ms_out);  /* synchronises the end event           */
+/* Kernels launched by this context since creation. */
+uint64_t csv_ctx_launch_count(const csv_ctx* ctx);
+
+/* --------------------------------------------------------------- input SoA */
+
+/* Packed alignment records, BAM file order (coordinate-sorted).  What the host
+ * packer extracts from each bam1_t: core.tid, core.pos, core.flag, core.qual
+ * and the raw CIGAR words of bam_get_cigar() (cnv_caller.cpp:491-503,
+ * sv_caller.cpp:526,542-546).  Caller-owned; pinned memory makes the upload
+ * asynchronous but is not required. */
+typedef struct {
+    uint32_t        n_reads;
+    uint64_t        n_ops;     /* == cig_off[n_reads]; must be < 2^32                 */
+    const int32_t*  tid;       /* [n_reads] contig id, or NULL (all reads on contig 0) */
+    const int32_t*  pos0;      /* [n_reads] 0-based leftmost position                  */
+    const uint16_t* flag;      /* [n_reads] BAM FLAG                                   */
+    const uint8_t*  mapq;      /* [n_reads] MAPQ                                       */
+    const uint64_t* cig_off;   /* [n_reads+1] prefix offsets into cigar[]              */
+    const uint32_t* cigar;     /* [n_ops] len<<4 | op                                  */
+} csv_reads;
+
+/* A slice [beg,end) of one contig's depth map.  Indices are those of the
+ * reference's per-chromosome vector<uint32_t>: index == 1-based coordinate,
+ * slot 0 unused, map_size == chromosome length + 1 (sv_caller.cpp:801,
+ * cnv_caller.cpp:482-487).  A whole contig is {tid, 0, map_size, map_size}.
+ * Regions of one batch must not overlap.  A region also OWNS the reads whose
+ * depth index pos0+1 falls in [beg,end) -- the region with end == map_size
+ * additionally owns reads starting at or beyond map_size -- and only owned
+ * reads emit signatures, so a read is reported exactly once however the
+ * genome is sharded. */
+typedef struct {
+    int32_t  tid;
+    uint32_t beg;
+    uint32_t end;
+    uint32_t map_size;
+} csv_region;
+
+/* ------------------------------------------------------- device-side batch */
+
+/* Reads uploaded once and kept in HBM for every pass over them (the reference
+ * re-reads the BAM three times). */
+typedef struct csv_batch csv_batch;
+
+int  csv_batch_upload(csv_ctx* ctx, const csv_reads* reads, uint32_t n_regions,
+                      const csv_region* regions, csv_batch** out);
+void csv_batch_free(csv_ctx* ctx, csv_batch* b);
+
+typedef struct {
+    uint32_t min_len;      /* signature length threshold; reference: 50 (sv_caller.cpp:566)   */
+    uint8_t  min_mapq;     /* reference: 20 (sv_caller.h:72)                                   */
+    uint8_t  want_depth;   /* run the depth part                                               */
+    uint8_t  want_sigs;    /* run the signature part                                           */
+    uint8_t  reserved;
+} csv_scan_params;
+
+/* One pass of the hot path over a batch, enqueued on the context's stream
+ * (asynchronous, no host round trip inside):
+ *   depth  == CNVCaller::calculateMeanChromosomeCoverage inner loops and
+ *             reductions (cnv_caller.cpp:488-535) for every region;
+ *   sigs   == SVCaller::findCIGARSVs -> processCIGARRecord -> addSVCall
+ *             (sv_caller.cpp:506-661, sv_object.cpp:17-33) for every region.
+ * Results stay on the device until fetched. */
+int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p);
+
+/* Per-region sum of depths and count of non-zero positions
+ * (cnv_caller.cpp:534-535); the caller adds shards of one contig and divides
+ * (cnv_caller.cpp:538).  Arrays have n_regions entries. */
+int csv_depth_stats(csv_ctx* ctx, csv_batch* b, uint64_t* sum_out, uint32_t* nonzero_out);
+/* Depth slice of one region: depth_out[i] == reference map[beg + i]. */
+int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth_out);
+/* Device address of a region's depth slice (for device-side consumers). */
+int csv_depth_device_ptr(csv_ctx* ctx, csv_batch* b, uint32_t region, const uint32_t** dptr_out);
+
+/* Signature records in the exact order of the reference's per-chromosome
+ * vector<SVCall> after all addSVCall() insertions: ascending (start,end),
+ * equal keys in reverse insertion order (sv_object.cpp:31-32). */
+typedef struct {
+    uint32_t* start;       /* SVCall.start                                                      */
+    uint32_t* end;         /* SVCall.end                                                        */
+    uint8_t*  kind;        /* 0 CIGARINS, 1 CIGARDEL, 2 CIGARCLIP (sv_types.h SVDataType)       */
+    uint32_t* read_idx;    /* record index in csv_reads                                         */
+    uint32_t* op_idx;      /* CIGAR op index inside the record                                  */
+    uint32_t* query_pos;   /* reference's query_pos at the op (sv_caller.cpp:547,653-655): where */
+                           /* the 50-base literal ALT starts in the read (sv_caller.cpp:572-591) */
+} csv_sigs;
+
+int csv_sigs_count(csv_ctx* ctx, csv_batch* b, uint64_t* n_out);
+/* region_off_out: [n_regions+1] offsets of each region's run inside the arrays. */
+int csv_sigs_fetch(csv_ctx* ctx, csv_batch* b, csv_sigs* out, uint64_t cap,
+                   uint64_t* n_out, uint64_t* region_off_out);
+
+/* DBSCAN1D::fit (dbscan1d.cpp:8-66) over the batch's sorted signature starts,
+ * one independent fit per (region, SVType) group in vector order -- the
+ * grouping mergeSVs uses (sv_object.cpp:61-83).  labels_out[i] belongs to
+ * signature i of csv_sigs_fetch(); may be NULL to leave labels on the device. */
+int csv_sigs_dbscan1d(csv_ctx* ctx, csv_batch* b, double eps, int min_pts,
+                      int32_t* labels_out, uint64_t cap);
+
+/* ------------------------------------------------ one-shot host-to-host API */
+
+/* CNVCaller::calculateMeanChromosomeCoverage for one region (cnv_caller.h:104). */
+int csv_depth(csv_ctx* ctx, const csv_reads* reads, const csv_region* region,
+              uint32_t* depth_out, uint64_t* sum_out, uint32_t* nonzero_out);
+
+/* SVCaller::findCIGARSVs for one region (sv_caller.h:86). */
+int csv_cigar_scan(csv_ctx* ctx, const csv_reads* reads, const csv_region* region,
+                   uint32_t min_len, uint8_t min_mapq, csv_sigs* out, uint64_t cap, uint64_t* n_out);
+
+/* DBSCAN1D::fit + getClusters (dbscan1d.h:13-17).  labels: cluster id >= 0,
+ * -2 noise, exactly as the reference assigns them.  n_clusters_out may be NULL. */
+int csv_dbscan1d(csv_ctx* ctx, const int32_t* pts, uint64_t n, double eps, int min_pts,
+                 int32_t* labels_out, int32_t* n_clusters_out);
+
+/* Many independent fits in one launch sequence: seg_id[i] < n_seg names the
+ * fit point i belongs to (NULL = one fit); input order inside a fit is the
+ * order of appearance in pts[]. */
+int csv_dbscan1d_seg(csv_ctx* ctx, const int32_t* pts, const uint32_t* seg_id, uint64_t n,
+                     uint32_t n_seg, double eps, int min_pts, int32_t* labels_out,
+                     int32_t* n_clusters_out /* [n_seg] or NULL */);
+
+/* DBSCAN1D::getLargestCluster (dbscan1d.cpp:72-90) on labels from a fit: host-side
+ * helper, no device work.  Returns the number of points written to out. */
+uint64_t csv_largest_cluster(const int32_t* pts, const int32_t* labels, uint64_t n, int32_t* out);
+
+/* Window depth sums for CNVCaller::querySNPRegion (cnv_caller.cpp:76-113):
+ * integer sum and position count of each of the sample_size windows of
+ * [start_pos,end_pos], read from a region's device-resident depth.  The
+ * caller finishes with the same libm log2 as the reference. */
+int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv,
+                    const uint32_t* start_pos, const uint32_t* end_pos, int sample_size,
+                    uint64_t* sum_out /* [n_sv*sample_size] */, uint32_t* count_out);
+
+/* ------------------------------------------------------- synthetic inputs */
+
+/* Seeded generator of coordinate-sorted long-read alignments.
+ * Host-only; lives in libcsvsynth.so, which has no CUDA dependency. */
+typedef struct {
+    uint64_t seed;
+    int32_t  profile;           /* 0 HiFi (normal lengths), 1 ONT (lognormal, read_len_mean = N50) */
+    double   coverage;
+    double   read_len_mean, read_len_sd;
+    double   indel_rate;        /* small indel events per reference base                           */
+    uint32_t indel_len_max;
+    uint64_t n_sv;              /* structural variants over all contigs                            */
+    uint32_t sv_len_max;
+    double   sv_jitter_sd;      /* per-read breakpoint jitter (config 5)                           */
+    double   frac_len50;        /* SVs of length exactly 50                                        */
+    double   frac_softclip, frac_supplementary, frac_secondary, frac_dup, frac_qcfail, frac_lowmapq;
+    int32_t  use_eqx;           /* '=' ops instead of 'M'                                          */
+    int32_t  threads;           /* 0 = all cores                                                   */
+} csv_synth_params;
+
+void     csv_synth_default_params(csv_synth_params* p);
+uint64_t csv_synth_num_reads(const csv_synth_params* p, uint32_t n_contigs, const uint32_t* contig_len);
+int      csv_synth_reads(const csv_synth_params* p, uint32_t n_contigs, const uint32_t* contig_len,
+                         int32_t* tid, int32_t* pos0, uint16_t* flag, uint8_t* mapq,
+                         uint64_t* cig_off /* [n_reads+1] */, uint64_t* n_ops_out);
+int      csv_synth_cigar(const csv_synth_params* p, uint32_t n_contigs, const uint32_t* contig_len,
+                         const uint64_t* cig_off, uint32_t* cigar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
