@@ -19,8 +19,8 @@ LIB_SYNTH = os.path.join(PKG, "libcsvsynth.so")
 
 CUDA_SOURCES = ["capi.cu", "prep.cu", "walk.cu", "depth_tiles.cu", "radix_sort.cu", "sigs.cu", "dbscan1d.cu", "windows.cu"]
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",
 ]
 
 
@@ -81,7 +81,7 @@ def build_cuda(force=False):
             ok = False
     if not ok:
         raise RuntimeError("nvcc failed")
-    _run([nvcc, "-shared", "-o", LIB_CUDA] + objs + ["-lcudart"])
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_CUDA] + objs + ["-lcudart"])
     return LIB_CUDA
 
 

@@ -1,0 +1,82 @@
+// batch.cuh -- device-resident batch of packed reads and the per-pass state.
+#pragma once
+#include "common.cuh"
+
+namespace csv {
+constexpr uint32_t kNone = 0xffffffffu;
+
+// u32 slots of csv_batch::d_scalars
+enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_EV_TOTAL = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_COUNT = 16 };
+
+struct SigRaw {          // emission-order signature records (device)
+    unsigned long long* key_hi;   // owner region << 32 | start
+    unsigned long long* key_lo;   // end << 32 | ~global op index  (ties: reverse insertion order)
+    uint32_t* k;                  // compact (non-empty) read index
+    uint32_t* qpos;
+    uint8_t* kind;                // bit 7: query_pos needs the exact sequential recomputation
+};
+}  // namespace csv
+
+struct csv_batch {
+    uint32_t n_reads = 0;
+    uint64_t n_ops = 0;
+    uint32_t n_regions = 0, n_tids = 0, n_tiles = 0, n_spans = 0;
+    bool has_tid = false, multi_region_tid = false;
+    std::vector<csv_region> regions;          // caller order
+    std::vector<uint32_t> tile_base;          // caller order, n_regions + 1
+    uint64_t ev_cap = 0, sig_cap = 0;
+    uint32_t last_min_len = 50;
+    bool scanned = false, have_depth = false, have_sigs = false, have_labels = false;
+
+    // input SoA (device)
+    csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar;
+    // derived per-read tables
+    csv::DevBuf d_meta;      // uint4 {pos0, tid|kNone, flag | mapq << 16, owner region | kNone} per non-empty read
+    csv::DevBuf d_ne_idx;    // compact index -> record index
+    csv::DevBuf d_headbits;  // one bit per op: op is the first of its record (+ sentinel bit at n_ops)
+    csv::DevBuf d_scalars;   // SC_* counters
+    csv::DevBuf d_regs, d_tids, d_reg_sig_cnt;
+    csv::DevBuf d_reg_tab;   // u32 [tile_base (n_regions + 1) | len (n_regions)], caller order
+    // walk
+    csv::DevBuf d_span_agg, d_span_pre, d_span_status;
+    // depth
+    csv::DevBuf d_tile_cn, d_tile_off, d_tile_net, d_events, d_depth, d_sum, d_nz;
+    // signatures
+    csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_qpos, d_sig_kind, d_sig_payload;
+    csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
+
+    void release() {
+        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_ne_idx, &d_headbits, &d_scalars,
+                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_tile_cn, &d_tile_off,
+                              &d_tile_net, &d_events, &d_depth, &d_sum, &d_nz, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
+                              &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
+                              &d_out_qpos, &d_out_seg, &d_labels};
+        for (auto* b : all) b->release();
+    }
+};
+
+namespace csv {
+// kernels' host launchers (each enqueues on ctx->stream and bumps ctx->launches)
+int launch_prep(csv_ctx* ctx, csv_batch* b);
+int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int mode);
+int launch_tile_scan(csv_ctx* ctx, csv_batch* b);
+int launch_depth_tiles(csv_ctx* ctx, csv_batch* b);
+int launch_sig_finish(csv_ctx* ctx, csv_batch* b);
+int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts);
+int launch_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv, const uint32_t* d_start,
+                       const uint32_t* d_end, int sample_size, unsigned long long* d_sum, uint32_t* d_cnt);
+
+// radix sort of (hi, lo) 128-bit keys with a u32 payload; hi may be null (64-bit keys).
+// n_dev (device u32) optionally overrides n_upper.
+struct SortBufs {
+    unsigned long long *hi, *lo; uint32_t* val;          // input / ping
+    unsigned long long *hi2, *lo2; uint32_t* val2;       // pong
+};
+// digit_mask: bit d set = byte d of the 128-bit key (lo bytes 0-7, hi bytes 8-15) may vary.
+// The sorted data always ends up in bufs.hi / lo / val.
+int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32_t* n_dev, uint32_t digit_mask);
+
+// DBSCAN1D on device-resident points.  d_seg may be null (single fit).
+int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, uint64_t n_upper, const uint32_t* n_dev,
+                    uint32_t n_seg, double eps, int min_pts, int32_t* d_labels, int32_t* d_n_clusters /* [n_seg] or null */);
+}  // namespace csv

@@ -1,0 +1,433 @@
+// capi.cu -- the extern "C" layer (include/contextsv_b200.h): contexts, uploads,
+// the scan pipeline, result fetches and the one-shot host-to-host wrappers.
+#include "batch.cuh"
+
+#include <algorithm>
+#include <memory>
+#include <stdarg.h>
+
+namespace csv {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+}
+
+int next_ticket(csv_ctx* ctx, uint32_t** out)
+{
+    if (ctx->ticket_next >= ctx->ticket_cap) {
+        const uint32_t cap = 16384;
+        CSV_TRY(ctx->tickets.ensure(cap * sizeof(uint32_t)));
+        CSV_CUDA(cudaMemsetAsync(ctx->tickets.p, 0, cap * sizeof(uint32_t), ctx->stream));   // stream-ordered after earlier users
+        ctx->ticket_cap = cap; ctx->ticket_next = 0;
+    }
+    *out = ctx->tickets.as<uint32_t>() + ctx->ticket_next++;
+    return CSV_OK;
+}
+
+int ensure_status(csv_ctx* ctx, size_t words)
+{
+    const size_t bytes = words * sizeof(unsigned long long);
+    if (bytes <= ctx->scan_status.cap) return CSV_OK;
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    CSV_TRY(ctx->scan_status.ensure(bytes));
+    CSV_CUDA(cudaMemsetAsync(ctx->scan_status.p, 0, ctx->scan_status.cap, ctx->stream));    // epoch 0 == never published
+    return CSV_OK;
+}
+
+static int read_scalars(csv_ctx* ctx, csv_batch* b, uint32_t* out /* SC_COUNT */)
+{
+    CSV_CUDA(cudaMemcpyAsync(ctx->pinned_small, b->d_scalars.p, SC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->pinned_small, SC_COUNT * sizeof(uint32_t));
+    return CSV_OK;
+}
+
+static int check_overflow(csv_ctx* ctx, csv_batch* b, uint32_t* sc)
+{
+    CSV_TRY(read_scalars(ctx, b, sc));
+    if (b->have_depth && sc[SC_EV_TOTAL] > b->ev_cap) {
+        set_error("depth: %u difference events exceed the batch capacity %llu (regions split too finely)", sc[SC_EV_TOTAL], (unsigned long long)b->ev_cap);
+        return CSV_ERR_LIMIT;
+    }
+    if (b->have_sigs && sc[SC_N_SIG] > b->sig_cap) {
+        set_error("signatures: %u emitted, batch capacity is %llu", sc[SC_N_SIG], (unsigned long long)b->sig_cap);
+        return CSV_ERR_CAPACITY;
+    }
+    return CSV_OK;
+}
+
+}  // namespace csv
+
+using namespace csv;
+
+extern "C" {
+
+const char* csv_last_error(void) { return g_err.c_str(); }
+const char* csv_version(void) { return "contextsv_b200 0.1 (sm_100a)"; }
+
+int csv_ctx_create(int device, csv_ctx** out)
+{
+    if (!out) { set_error("csv_ctx_create: out is NULL"); return CSV_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { set_error("no CUDA device available (%s): there is no CPU fallback", cudaGetErrorString(e)); return CSV_ERR_CUDA; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return CSV_ERR_ARG; }
+    CSV_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CSV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library only carries sm_100a code", device, prop.major, prop.minor); return CSV_ERR_CUDA; }
+    csv_ctx* ctx = new csv_ctx;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CSV_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CSV_CUDA(cudaEventCreate(&ctx->ev0));
+    CSV_CUDA(cudaEventCreate(&ctx->ev1));
+    CSV_CUDA(cudaHostAlloc(&ctx->pinned_small, 4096, cudaHostAllocDefault));
+    *out = ctx;
+    return CSV_OK;
+}
+
+void csv_ctx_destroy(csv_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->tickets.release(); ctx->scan_status.release();
+    for (auto& b : ctx->sort_tmp) b.release();
+    for (auto& b : ctx->db) b.release();
+    if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int csv_ctx_sync(csv_ctx* ctx)
+{
+    if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CSV_OK;
+}
+
+void* csv_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void csv_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int csv_timer_begin(csv_ctx* ctx)
+{
+    CSV_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return CSV_OK;
+}
+int csv_timer_end(csv_ctx* ctx, float* ms_out)
+{
+    CSV_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    CSV_CUDA(cudaEventSynchronize(ctx->ev1));
+    CSV_CUDA(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    return CSV_OK;
+}
+uint64_t csv_ctx_launch_count(const csv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ------------------------------------------------------------------ batch */
+
+int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const csv_region* regions, csv_batch** out)
+{
+    if (!ctx || !r || !out || !regions || n_regions == 0) { set_error("csv_batch_upload: null argument or no regions"); return CSV_ERR_ARG; }
+    *out = nullptr;
+    if (r->n_reads && (!r->pos0 || !r->flag || !r->mapq || !r->cig_off)) { set_error("csv_batch_upload: missing SoA array"); return CSV_ERR_ARG; }
+    if (r->n_ops && !r->cigar) { set_error("csv_batch_upload: cigar is NULL"); return CSV_ERR_ARG; }
+    if (r->n_reads && r->cig_off[r->n_reads] != r->n_ops) { set_error("csv_batch_upload: cig_off[n_reads] != n_ops"); return CSV_ERR_ARG; }
+    if (r->n_ops >= (1ull << 31)) { set_error("batch of %llu CIGAR ops exceeds the 2^31 per-batch limit: split it", (unsigned long long)r->n_ops); return CSV_ERR_LIMIT; }
+    if (n_regions >= (1u << 30)) { set_error("too many regions"); return CSV_ERR_LIMIT; }
+    CSV_CUDA(cudaSetDevice(ctx->device));
+
+    // ---- region tables
+    int32_t max_tid = -1;
+    for (uint32_t i = 0; i < n_regions; i++) {
+        const csv_region& g = regions[i];
+        if (g.tid < 0 || g.beg >= g.end || g.end > g.map_size) { set_error("region %u: need tid >= 0 and beg < end <= map_size", i); return CSV_ERR_ARG; }
+        max_tid = std::max(max_tid, g.tid);
+    }
+    if (max_tid >= (1 << 24)) { set_error("contig id %d too large", max_tid); return CSV_ERR_LIMIT; }
+    std::vector<uint32_t> order(n_regions);
+    for (uint32_t i = 0; i < n_regions; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return regions[a].tid != regions[b].tid ? regions[a].tid < regions[b].tid : regions[a].beg < regions[b].beg;
+    });
+    std::unique_ptr<csv_batch> b(new csv_batch);
+    b->n_reads = r->n_reads; b->n_ops = r->n_ops; b->n_regions = n_regions; b->n_tids = (uint32_t)max_tid + 1;
+    b->has_tid = r->tid != nullptr;
+    b->regions.assign(regions, regions + n_regions);
+    b->tile_base.resize(n_regions + 1);
+    uint64_t tiles = 0;
+    for (uint32_t i = 0; i < n_regions; i++) { b->tile_base[i] = (uint32_t)tiles; tiles += ((uint64_t)(regions[i].end - regions[i].beg) + kTile - 1) / kTile; }
+    if (tiles >= (1ull << 31)) { set_error("too many depth tiles"); return CSV_ERR_LIMIT; }
+    b->tile_base[n_regions] = (uint32_t)tiles; b->n_tiles = (uint32_t)tiles;
+    std::vector<RegionDev> regs(n_regions);
+    std::vector<TidDev> tids(b->n_tids, TidDev{0, 0, 0, 0});
+    for (uint32_t s = 0; s < n_regions; s++) {
+        const csv_region& g = regions[order[s]];
+        regs[s] = RegionDev{g.beg, g.end, b->tile_base[order[s]], order[s]};
+        TidDev& t = tids[g.tid];
+        if (t.count == 0) { t.first = s; t.map_size = g.map_size; }
+        else {
+            if (t.map_size != g.map_size) { set_error("regions of contig %d disagree on map_size", g.tid); return CSV_ERR_ARG; }
+            if (regs[s - 1].end > g.beg) { set_error("regions of contig %d overlap", g.tid); return CSV_ERR_ARG; }
+            b->multi_region_tid = true;
+        }
+        t.count++;
+    }
+    std::vector<uint32_t> reg_tab(2 * n_regions + 1);
+    for (uint32_t i = 0; i <= n_regions; i++) reg_tab[i] = b->tile_base[i];
+    for (uint32_t i = 0; i < n_regions; i++) reg_tab[n_regions + 1 + i] = regions[i].end - regions[i].beg;
+
+    b->n_spans = (uint32_t)((r->n_ops + kWalkSpan - 1) / kWalkSpan);
+    b->ev_cap = std::min<uint64_t>(2 * (r->n_ops + r->n_reads) * (b->multi_region_tid ? 2 : 1) + 64, 0xfffffff0ull);
+    b->sig_cap = std::max<uint64_t>(16, std::min<uint64_t>(r->n_ops, std::max<uint64_t>(1u << 20, r->n_ops / 16)));
+
+    // ---- allocations
+    const size_t nr = r->n_reads, no = (size_t)r->n_ops, nt = b->n_tiles, sc = (size_t)b->sig_cap;
+    if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16));
+    CSV_TRY(b->d_pos0.ensure(nr * 4 + 16)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16)); CSV_TRY(b->d_mapq.ensure(nr + 16));
+    CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64));
+    CSV_TRY(b->d_meta.ensure(nr * 16 + 16)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16)); CSV_TRY(b->d_headbits.ensure(no / 8 + 64));
+    CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4));
+    CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev))); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev)));
+    CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4));
+    CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16));
+    CSV_TRY(b->d_span_status.ensure((size_t)b->n_spans * 4 + 16));
+    CSV_CUDA(cudaMemsetAsync(b->d_span_status.p, 0, b->d_span_status.cap, ctx->stream));
+    CSV_TRY(b->d_tile_cn.ensure(nt * 8 + 16)); CSV_TRY(b->d_tile_off.ensure(nt * 4 + 16)); CSV_TRY(b->d_tile_net.ensure(nt * 4 + 16));
+    CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 2)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4));
+    CSV_TRY(b->d_sum.ensure(n_regions * 8)); CSV_TRY(b->d_nz.ensure(n_regions * 4));
+    CSV_TRY(b->d_sig_hi.ensure(sc * 8)); CSV_TRY(b->d_sig_lo.ensure(sc * 8)); CSV_TRY(b->d_sig_k.ensure(sc * 4));
+    CSV_TRY(b->d_sig_qpos.ensure(sc * 4)); CSV_TRY(b->d_sig_kind.ensure(sc)); CSV_TRY(b->d_sig_payload.ensure(sc * 4));
+    CSV_TRY(b->d_out_start.ensure(sc * 4)); CSV_TRY(b->d_out_end.ensure(sc * 4)); CSV_TRY(b->d_out_kind.ensure(sc));
+    CSV_TRY(b->d_out_read.ensure(sc * 4)); CSV_TRY(b->d_out_op.ensure(sc * 4)); CSV_TRY(b->d_out_qpos.ensure(sc * 4));
+    CSV_TRY(b->d_out_seg.ensure(sc * 4));
+
+    // ---- uploads (asynchronous when the host buffers are pinned)
+    cudaStream_t st = ctx->stream;
+    if (nr) {
+        if (b->has_tid) CSV_CUDA(cudaMemcpyAsync(b->d_tid.p, r->tid, nr * 4, cudaMemcpyHostToDevice, st));
+        CSV_CUDA(cudaMemcpyAsync(b->d_pos0.p, r->pos0, nr * 4, cudaMemcpyHostToDevice, st));
+        CSV_CUDA(cudaMemcpyAsync(b->d_flag.p, r->flag, nr * 2, cudaMemcpyHostToDevice, st));
+        CSV_CUDA(cudaMemcpyAsync(b->d_mapq.p, r->mapq, nr, cudaMemcpyHostToDevice, st));
+        CSV_CUDA(cudaMemcpyAsync(b->d_cig_off.p, r->cig_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        CSV_CUDA(cudaMemsetAsync(b->d_cig_off.p, 0, 8, st));
+    }
+    if (no) CSV_CUDA(cudaMemcpyAsync(b->d_cigar.p, r->cigar, no * 4, cudaMemcpyHostToDevice, st));
+    // table copies come from temporaries: make them synchronous with respect to the host
+    CSV_CUDA(cudaMemcpyAsync(b->d_regs.p, regs.data(), regs.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
+    CSV_CUDA(cudaMemcpyAsync(b->d_tids.p, tids.data(), tids.size() * sizeof(TidDev), cudaMemcpyHostToDevice, st));
+    CSV_CUDA(cudaMemcpyAsync(b->d_reg_tab.p, reg_tab.data(), reg_tab.size() * 4, cudaMemcpyHostToDevice, st));
+    CSV_CUDA(cudaStreamSynchronize(st));
+    *out = b.release();
+    return CSV_OK;
+}
+
+void csv_batch_free(csv_ctx* ctx, csv_batch* b)
+{
+    if (!b) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    b->release();
+    delete b;
+}
+
+int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
+{
+    if (!ctx || !b || !p) { set_error("csv_scan_run: null argument"); return CSV_ERR_ARG; }
+    if (!p->want_depth && !p->want_sigs) { set_error("csv_scan_run: nothing requested"); return CSV_ERR_ARG; }
+    cudaStream_t st = ctx->stream;
+    b->last_min_len = p->min_len;
+    CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
+    if (p->want_depth) {
+        CSV_CUDA(cudaMemsetAsync(b->d_tile_cn.p, 0, (size_t)b->n_tiles * 8, st));
+        CSV_CUDA(cudaMemsetAsync(b->d_sum.p, 0, b->n_regions * 8, st));
+        CSV_CUDA(cudaMemsetAsync(b->d_nz.p, 0, b->n_regions * 4, st));
+    }
+    CSV_TRY(launch_prep(ctx, b));
+    CSV_TRY(launch_walk(ctx, b, p, 0));
+    if (p->want_depth) {
+        CSV_TRY(launch_tile_scan(ctx, b));
+        CSV_TRY(launch_walk(ctx, b, p, 1));
+        CSV_TRY(launch_depth_tiles(ctx, b));
+    }
+    if (p->want_sigs) CSV_TRY(launch_sig_finish(ctx, b));
+    b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;
+    return CSV_OK;
+}
+
+int csv_depth_stats(csv_ctx* ctx, csv_batch* b, uint64_t* sum_out, uint32_t* nonzero_out)
+{
+    if (!ctx || !b) { set_error("null argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_depth) { set_error("csv_depth_stats: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    uint32_t sc[SC_COUNT];
+    CSV_TRY(check_overflow(ctx, b, sc));
+    if (sum_out) CSV_CUDA(cudaMemcpyAsync(sum_out, b->d_sum.p, b->n_regions * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nonzero_out) CSV_CUDA(cudaMemcpyAsync(nonzero_out, b->d_nz.p, b->n_regions * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CSV_OK;
+}
+
+int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth_out)
+{
+    if (!ctx || !b || !depth_out) { set_error("null argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_depth) { set_error("csv_depth_fetch: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    if (region >= b->n_regions) { set_error("region %u out of range", region); return CSV_ERR_ARG; }
+    const size_t len = b->regions[region].end - b->regions[region].beg;
+    const uint32_t* src = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
+    CSV_CUDA(cudaMemcpyAsync(depth_out, src, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CSV_OK;
+}
+
+int csv_depth_device_ptr(csv_ctx* ctx, csv_batch* b, uint32_t region, const uint32_t** dptr_out)
+{
+    if (!ctx || !b || !dptr_out || region >= b->n_regions) { set_error("bad argument"); return CSV_ERR_ARG; }
+    *dptr_out = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
+    return CSV_OK;
+}
+
+int csv_sigs_count(csv_ctx* ctx, csv_batch* b, uint64_t* n_out)
+{
+    if (!ctx || !b || !n_out) { set_error("null argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_count: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
+    uint32_t sc[SC_COUNT];
+    int s = check_overflow(ctx, b, sc);
+    *n_out = sc[SC_N_SIG];
+    return s;
+}
+
+int csv_sigs_fetch(csv_ctx* ctx, csv_batch* b, csv_sigs* out, uint64_t cap, uint64_t* n_out, uint64_t* region_off_out)
+{
+    if (!ctx || !b || !out || !n_out) { set_error("null argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_fetch: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
+    uint32_t sc[SC_COUNT];
+    CSV_TRY(check_overflow(ctx, b, sc));
+    const uint64_t n = sc[SC_N_SIG];
+    *n_out = n;
+    if (n > cap) { set_error("csv_sigs_fetch: %llu signatures, caller capacity %llu", (unsigned long long)n, (unsigned long long)cap); return CSV_ERR_CAPACITY; }
+    cudaStream_t st = ctx->stream;
+    if (n) {
+        if (out->start) CSV_CUDA(cudaMemcpyAsync(out->start, b->d_out_start.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (out->end) CSV_CUDA(cudaMemcpyAsync(out->end, b->d_out_end.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (out->kind) CSV_CUDA(cudaMemcpyAsync(out->kind, b->d_out_kind.p, n, cudaMemcpyDeviceToHost, st));
+        if (out->read_idx) CSV_CUDA(cudaMemcpyAsync(out->read_idx, b->d_out_read.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (out->op_idx) CSV_CUDA(cudaMemcpyAsync(out->op_idx, b->d_out_op.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (out->query_pos) CSV_CUDA(cudaMemcpyAsync(out->query_pos, b->d_out_qpos.p, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (region_off_out) {
+        std::vector<uint32_t> cnt(b->n_regions);
+        CSV_CUDA(cudaMemcpyAsync(cnt.data(), b->d_reg_sig_cnt.p, b->n_regions * 4, cudaMemcpyDeviceToHost, st));
+        CSV_CUDA(cudaStreamSynchronize(st));
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < b->n_regions; i++) { region_off_out[i] = acc; acc += cnt[i]; }
+        region_off_out[b->n_regions] = acc;
+    }
+    CSV_CUDA(cudaStreamSynchronize(st));
+    return CSV_OK;
+}
+
+int csv_sigs_dbscan1d(csv_ctx* ctx, csv_batch* b, double eps, int min_pts, int32_t* labels_out, uint64_t cap)
+{
+    if (!ctx || !b) { set_error("null argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_dbscan1d: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
+    CSV_TRY(launch_sig_dbscan(ctx, b, eps, min_pts));
+    b->have_labels = true;
+    if (labels_out) {
+        uint32_t sc[SC_COUNT];
+        CSV_TRY(check_overflow(ctx, b, sc));
+        const uint64_t n = sc[SC_N_SIG];
+        if (n > cap) { set_error("csv_sigs_dbscan1d: %llu labels, caller capacity %llu", (unsigned long long)n, (unsigned long long)cap); return CSV_ERR_CAPACITY; }
+        if (n) CSV_CUDA(cudaMemcpyAsync(labels_out, b->d_labels.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return CSV_OK;
+}
+
+/* ------------------------------------------------------- one-shot wrappers */
+
+int csv_depth(csv_ctx* ctx, const csv_reads* reads, const csv_region* region, uint32_t* depth_out, uint64_t* sum_out, uint32_t* nonzero_out)
+{
+    csv_batch* b = nullptr;
+    CSV_TRY(csv_batch_upload(ctx, reads, 1, region, &b));
+    csv_scan_params p = {50, 20, 1, 0, 0};
+    int s = csv_scan_run(ctx, b, &p);
+    if (s == CSV_OK) s = csv_depth_stats(ctx, b, sum_out, nonzero_out);
+    if (s == CSV_OK && depth_out) s = csv_depth_fetch(ctx, b, 0, depth_out);
+    csv_batch_free(ctx, b);
+    return s;
+}
+
+int csv_cigar_scan(csv_ctx* ctx, const csv_reads* reads, const csv_region* region, uint32_t min_len, uint8_t min_mapq,
+                   csv_sigs* out, uint64_t cap, uint64_t* n_out)
+{
+    csv_batch* b = nullptr;
+    CSV_TRY(csv_batch_upload(ctx, reads, 1, region, &b));
+    csv_scan_params p = {min_len, min_mapq, 0, 1, 0};
+    int s = csv_scan_run(ctx, b, &p);
+    if (s == CSV_OK) s = csv_sigs_fetch(ctx, b, out, cap, n_out, nullptr);
+    csv_batch_free(ctx, b);
+    return s;
+}
+
+int csv_dbscan1d_seg(csv_ctx* ctx, const int32_t* pts, const uint32_t* seg_id, uint64_t n, uint32_t n_seg, double eps, int min_pts,
+                     int32_t* labels_out, int32_t* n_clusters_out)
+{
+    if (!ctx || (n && (!pts || !labels_out))) { set_error("csv_dbscan1d: null argument"); return CSV_ERR_ARG; }
+    if (n_seg == 0) n_seg = 1;
+    if (n_clusters_out) for (uint32_t i = 0; i < n_seg; i++) n_clusters_out[i] = 0;
+    if (n == 0) return CSV_OK;
+    if (n >= (1ull << 30)) { set_error("csv_dbscan1d: %llu points exceed the 2^30 limit", (unsigned long long)n); return CSV_ERR_LIMIT; }
+    CSV_CUDA(cudaSetDevice(ctx->device));
+    DevBuf& d_pts = ctx->sort_tmp[4]; DevBuf& d_misc = ctx->sort_tmp[5];
+    CSV_TRY(d_pts.ensure(n * 4));
+    // d_misc: labels | seg | n_clusters
+    const size_t off_seg = n * 4, off_nc = off_seg + (seg_id ? n * 4 : 0);
+    CSV_TRY(d_misc.ensure(off_nc + (size_t)n_seg * 4 + 16));
+    cudaStream_t st = ctx->stream;
+    CSV_CUDA(cudaMemcpyAsync(d_pts.p, pts, n * 4, cudaMemcpyHostToDevice, st));
+    uint32_t* d_seg = nullptr;
+    if (seg_id) { d_seg = (uint32_t*)((char*)d_misc.p + off_seg); CSV_CUDA(cudaMemcpyAsync(d_seg, seg_id, n * 4, cudaMemcpyHostToDevice, st)); }
+    int32_t* d_nc = (int32_t*)((char*)d_misc.p + off_nc);
+    CSV_TRY(dbscan1d_device(ctx, d_pts.as<int32_t>(), d_seg, n, nullptr, n_seg, eps, min_pts, d_misc.as<int32_t>(), d_nc));
+    CSV_CUDA(cudaMemcpyAsync(labels_out, d_misc.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n_clusters_out) CSV_CUDA(cudaMemcpyAsync(n_clusters_out, d_nc, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
+    CSV_CUDA(cudaStreamSynchronize(st));
+    return CSV_OK;
+}
+
+int csv_dbscan1d(csv_ctx* ctx, const int32_t* pts, uint64_t n, double eps, int min_pts, int32_t* labels_out, int32_t* n_clusters_out)
+{
+    return csv_dbscan1d_seg(ctx, pts, nullptr, n, 1, eps, min_pts, labels_out, n_clusters_out);
+}
+
+uint64_t csv_largest_cluster(const int32_t* pts, const int32_t* labels, uint64_t n, int32_t* out)
+{
+    // dbscan1d.cpp:72-90: std::map order = ascending id, strictly-greater keeps the first;
+    // with no id >= 0 the reference returns cluster_map[-1]
+    int32_t max_id = -1;
+    for (uint64_t i = 0; i < n; i++) if (labels[i] > max_id) max_id = labels[i];
+    int32_t best = -1;
+    if (max_id >= 0) {
+        std::vector<uint64_t> cnt((size_t)max_id + 1, 0);
+        for (uint64_t i = 0; i < n; i++) if (labels[i] >= 0) cnt[labels[i]]++;
+        uint64_t best_n = 0;
+        for (int32_t c = 0; c <= max_id; c++) if (cnt[c] > best_n) { best_n = cnt[c]; best = c; }
+    }
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n; i++) if (labels[i] == best) out[m++] = pts[i];
+    return m;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// common.cuh -- shared host/device plumbing of the sm_100a scan path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "contextsv_b200.h"
+
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 1000
+#error "contextsv_b200 kernels are written for sm_100a only"
+#endif
+
+namespace csv {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define CSV_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            csv::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CSV_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+#define CSV_TRY(call)                 \
+    do {                              \
+        int s__ = (call);             \
+        if (s__ != CSV_OK) return s__; \
+    } while (0)
+
+// ------------------------------------------------------ geometry constants
+constexpr int kSMs = 148;                       // B200
+constexpr int kTile = 8192;                     // depth positions per tile (32 KB of int32 in smem)
+constexpr int kTileShift = 13;
+constexpr int kWalkThreads = 256;
+constexpr int kWalkOpsPerThread = 8;
+constexpr int kWalkSpan = kWalkThreads * kWalkOpsPerThread;   // CIGAR ops per span
+constexpr int kIvCap = 2048;                    // staged depth intervals per span window
+
+// BAM constants (SAM spec): which ops consume reference / query
+constexpr uint32_t kRefMask = (1u << 0) | (1u << 2) | (1u << 3) | (1u << 7) | (1u << 8);   // M D N = X
+constexpr uint32_t kQryMask = (1u << 0) | (1u << 1) | (1u << 4) | (1u << 7) | (1u << 8);   // M I S = X
+constexpr uint32_t kGapMask = (1u << 2) | (1u << 3);                                        // D N
+constexpr uint32_t kSigMask = (1u << 1) | (1u << 2) | (1u << 4);                            // I D S
+constexpr uint32_t kDepthSkipFlags = 0x4 | 0x100 | 0x200 | 0x400;          // cnv_caller.cpp:491-495
+constexpr uint32_t kSigSkipFlags = 0x4 | 0x100 | 0x200 | 0x400 | 0x800;    // sv_caller.cpp:526
+
+// ------------------------------------------------------------ device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CSV_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CSV_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return CSV_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// Region tables (device copies live in the batch)
+struct RegionDev {       // sorted by (tid, beg)
+    uint32_t beg, end;   // end already clipped to map_size
+    uint32_t tile_base;  // first global tile of the region
+    uint32_t orig;       // caller's region index
+};
+struct TidDev { uint32_t first, count, map_size, pad; };
+
+// Look-back scan state of the walk: (heads, ref, qry); segmented on heads > 0
+struct WalkAgg { uint32_t heads, ref, qry, pad; };
+
+}  // namespace csv
+
+// ------------------------------------------------------------------ context
+struct csv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    uint32_t epoch = 1;                 // look-back epoch, bumped per chained launch
+    csv::DevBuf tickets;                // zeroed u32 counters, one per chained launch
+    uint32_t ticket_next = 0, ticket_cap = 0;
+    csv::DevBuf scan_status;            // u64 status words for chained scans / radix passes
+    csv::DevBuf sort_tmp[6];            // radix sort ping-pong buffers + histograms
+    csv::DevBuf db[16];                 // DBSCAN scratch
+    void* pinned_small = nullptr;       // 4 KB pinned staging for tiny D2H reads
+    int sm_count = csv::kSMs;
+};
+
+namespace csv {
+// Returns a device pointer to a zeroed u32 ticket counter (stream-ordered).
+int next_ticket(csv_ctx* ctx, uint32_t** out);
+inline uint32_t next_epoch(csv_ctx* ctx) { ctx->epoch++; if (ctx->epoch >= 0x3fffffffu) ctx->epoch = 1; return ctx->epoch; }
+int ensure_status(csv_ctx* ctx, size_t words);   // u64 words; never needs clearing (epoch-tagged)
+}
+
+// ------------------------------------------------------------- device utils
+#ifdef __CUDACC__
+namespace csv {
+
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_cs_v4(void* p, uint4 v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane_id() >= (uint32_t)d) v += t; }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// CTA-wide exclusive sum of one u32 per thread (blockDim multiple of 32, <= 1024).
+// smem: at least 33 u32.  Returns exclusive prefix; *total receives the CTA sum.
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* smem, uint32_t* total)
+{
+    uint32_t incl = warp_incl_scan_u32(v);
+    uint32_t w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane_id() == 31) smem[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane_id() < nw ? smem[lane_id()] : 0;
+        uint32_t xi = warp_incl_scan_u32(x);
+        smem[lane_id()] = xi - x;
+        if (lane_id() == 31) smem[32] = xi;
+    }
+    __syncthreads();
+    uint32_t base = smem[w];
+    *total = smem[32];
+    return base + incl - v;
+}
+
+}  // namespace csv
+#endif

@@ -1,0 +1,125 @@
+// sigs.cu -- order the emitted signatures exactly like the reference's
+// vector<SVCall> (addSVCall, sv_object.cpp:22-33: ascending (start,end), equal
+// keys in reverse insertion order) and materialise the output SoA.
+//
+// The walk appends signatures in arbitrary order; the 128-bit key
+//   hi = owner region << 32 | start      lo = end << 32 | ~(global op index)
+// is unique, so one stable radix sort gives a deterministic total order:
+// insertion order in the reference is (record order, op order) == ascending
+// global op index, hence ~index sorts equal (start,end) in reverse insertion order.
+#include "batch.cuh"
+#include "scan.cuh"
+
+namespace csv {
+
+__global__ void k_sig_clamp(uint32_t* scalars, uint32_t cap)
+{
+    const uint32_t n = scalars[SC_N_SIG];
+    scalars[SC_N_SIG_EFF] = n < cap ? n : cap;
+}
+
+__global__ void k_sig_iota(uint32_t* val, const uint32_t* scalars)
+{
+    const uint32_t n = scalars[SC_N_SIG_EFF];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) val[i] = i;
+}
+
+struct GatherParams {
+    const unsigned long long *hi, *lo;
+    const uint32_t* val;
+    const uint32_t *raw_k, *raw_qpos;
+    const uint8_t* raw_kind;
+    const uint32_t* ne_idx;
+    const unsigned long long* cig_off;
+    const uint32_t* cigar;
+    const uint4* meta;
+    const TidDev* tids;
+    const uint32_t* scalars;
+    uint32_t cap, min_len;
+    uint32_t *o_start, *o_end, *o_read, *o_op, *o_qpos, *o_seg;
+    uint8_t* o_kind;
+};
+
+__global__ void k_sig_gather(const GatherParams P)
+{
+    const uint32_t n = P.scalars[SC_N_SIG_EFF];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long hi = P.hi[i], lo = P.lo[i];
+        const uint32_t slot = P.val[i];
+        const uint32_t g = 0xffffffffu - (uint32_t)lo;
+        const uint32_t k = P.raw_k[slot];
+        const uint32_t read = P.ne_idx[k];
+        const unsigned long long c0 = P.cig_off[read];
+        const uint8_t kr = P.raw_kind[slot];
+        uint32_t qpos = P.raw_qpos[slot];
+        if (kr & 0x80u) {
+            // exact sequential restatement (sv_caller.cpp:563-655) for the rare records that reach or
+            // pass the end of their contig: a soft clip there skips the query advance (:602-604)
+            const uint4 m = P.meta[k];
+            const uint32_t map_size = P.tids[m.y].map_size;
+            uint32_t pos = m.x, q = 0;
+            for (unsigned long long o = c0; o < (unsigned long long)g; o++) {
+                const uint32_t w = P.cigar[o], op = w & 15u, len = w >> 4;
+                if (len >= P.min_len && op == 4u && (uint32_t)(pos + 1u) >= map_size) continue;
+                if ((kRefMask >> op) & 1u) pos += len;
+                if ((kQryMask >> op) & 1u) q += len;
+            }
+            qpos = q;
+        }
+        const uint32_t kind = kr & 0x7fu;
+        const uint32_t region = (uint32_t)(hi >> 32);
+        P.o_start[i] = (uint32_t)hi;
+        P.o_end[i] = (uint32_t)(lo >> 32);
+        P.o_kind[i] = (uint8_t)kind;
+        P.o_read[i] = read;
+        P.o_op[i] = (uint32_t)((unsigned long long)g - c0);
+        P.o_qpos[i] = qpos;
+        P.o_seg[i] = region * 2u + (kind == 1u ? 0u : 1u);   // group = (region, SVType): DEL | INS
+    }
+}
+
+int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
+{
+    const uint32_t cap = (uint32_t)b->sig_cap;
+    uint32_t* scalars = b->d_scalars.as<uint32_t>();
+    uint32_t grid = ctx->sm_count * 4;
+    k_sig_clamp<<<1, 1, 0, ctx->stream>>>(scalars, cap);
+    k_sig_iota<<<grid, 256, 0, ctx->stream>>>(b->d_sig_payload.as<uint32_t>(), scalars);
+    ctx->launches += 2;
+    // alternates for the sort live in the output buffers' neighbours (ctx scratch)
+    CSV_TRY(ctx->sort_tmp[1].ensure((size_t)cap * 8));
+    CSV_TRY(ctx->sort_tmp[2].ensure((size_t)cap * 8));
+    CSV_TRY(ctx->sort_tmp[3].ensure((size_t)cap * 4));
+    SortBufs sb;
+    sb.hi = b->d_sig_hi.as<unsigned long long>(); sb.lo = b->d_sig_lo.as<unsigned long long>(); sb.val = b->d_sig_payload.as<uint32_t>();
+    sb.hi2 = ctx->sort_tmp[1].as<unsigned long long>(); sb.lo2 = ctx->sort_tmp[2].as<unsigned long long>(); sb.val2 = ctx->sort_tmp[3].as<uint32_t>();
+    // bytes that can vary: ~op index (as many bytes as n_ops needs), end, start, owner region
+    uint32_t mask = 0;
+    for (int d = 0; d < 4; d++) if (d == 0 || (b->n_ops >> (8 * d))) mask |= 1u << d;
+    mask |= 0xf0u | 0xf00u;
+    for (int d = 0; d < 4; d++) if (d == 0 ? b->n_regions > 1 : (b->n_regions >> (8 * d))) mask |= 1u << (12 + d);
+    // n_dev is clamped inside the kernels through cap: pass the upper bound and the device count
+    CSV_TRY(radix_sort_pairs(ctx, sb, cap, scalars + SC_N_SIG_EFF, mask));
+    GatherParams P;
+    P.hi = sb.hi; P.lo = sb.lo; P.val = sb.val;
+    P.raw_k = b->d_sig_k.as<uint32_t>(); P.raw_qpos = b->d_sig_qpos.as<uint32_t>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
+    P.ne_idx = b->d_ne_idx.as<uint32_t>(); P.cig_off = b->d_cig_off.as<unsigned long long>(); P.cigar = b->d_cigar.as<uint32_t>();
+    P.meta = b->d_meta.as<uint4>(); P.tids = b->d_tids.as<TidDev>(); P.scalars = scalars; P.cap = cap;
+    P.o_start = b->d_out_start.as<uint32_t>(); P.o_end = b->d_out_end.as<uint32_t>(); P.o_read = b->d_out_read.as<uint32_t>();
+    P.o_op = b->d_out_op.as<uint32_t>(); P.o_qpos = b->d_out_qpos.as<uint32_t>(); P.o_seg = b->d_out_seg.as<uint32_t>();
+    P.o_kind = b->d_out_kind.as<uint8_t>();
+    P.min_len = b->last_min_len;
+    k_sig_gather<<<grid, 256, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
+int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts)
+{
+    CSV_TRY(b->d_labels.ensure((size_t)b->sig_cap * 4 + 16));
+    return dbscan1d_device(ctx, b->d_out_start.as<int32_t>(), b->d_out_seg.as<uint32_t>(), b->sig_cap,
+                           b->d_scalars.as<uint32_t>() + SC_N_SIG_EFF, b->n_regions * 2, eps, min_pts, b->d_labels.as<int32_t>(), nullptr);
+}
+
+}  // namespace csv

@@ -1,0 +1,243 @@
+"""GPU: the CUDA path, called through the C ABI, against the committed golden vectors (reference's
+own outputs) and against the oracle on seeded inputs.  Bit-exact for every integer output."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from contextsv_b200 import api
+from contextsv_b200._capi import CsvReads, CsvRegion, CsvSigs, check, lib, ptr, reads_struct
+
+pytestmark = pytest.mark.gpu
+
+
+def run_batch(ctx, r, regions, **kw):
+    b = api.Batch(ctx, r, regions)
+    b.scan(**kw)
+    return b
+
+
+def check_contigs(ctx, oracle, r, clen, seq=None):
+    regions = api.whole_contig_regions(clen)
+    b = run_batch(ctx, r, regions)
+    sums, nzs = b.depth_stats()
+    sg = b.sigs()
+    for tid in range(len(clen)):
+        d, s, nz = oracle.depth(r, tid, clen[tid] + 1)
+        got = b.depth(tid)
+        assert np.array_equal(got, d), "depth tid %d: first diff at %s" % (tid, np.nonzero(got != d)[0][:5])
+        assert int(sums[tid]) == s and int(nzs[tid]) == nz
+        o = oracle.cigar_scan(r, tid, clen[tid] + 1)
+        lo, hi = int(sg["region_off"][tid]), int(sg["region_off"][tid + 1])
+        assert hi - lo == len(o), "tid %d: %d signatures, oracle %d" % (tid, hi - lo, len(o))
+        for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+            assert np.array_equal(sg[f][lo:hi], o[f]), "signature field %s tid %d" % (f, tid)
+    b.free()
+
+
+def test_golden_dbscan1d(ctx):
+    for i, pts, eps, mp, labels, largest in util.golden_db_cases():
+        db = api.DBSCAN1D(eps, mp, ctx)
+        db.fit(pts)
+        assert np.array_equal(db.getClusters(), labels), "case %d eps=%g minPts=%d" % (i, eps, mp)
+        assert np.array_equal(db.getLargestCluster(pts), largest), "largest cluster case %d" % i
+
+
+def test_golden_depth_and_signatures(ctx):
+    for i, r, clen, seq4, seq_off in util.golden_cg_cases():
+        regions = api.whole_contig_regions(clen)
+        b = run_batch(ctx, r, regions)
+        sums, nzs = b.depth_stats()
+        sg = b.sigs()
+        for tid in range(len(clen)):
+            ans = util.golden_cg_answer(i, tid)
+            assert np.array_equal(b.depth(tid), ans["depth"]), "depth case %d tid %d" % (i, tid)
+            assert int(sums[tid]) == ans["sum"] and int(nzs[tid]) == ans["nonzero"]
+            mean = float(sums[tid]) / float(nzs[tid]) if nzs[tid] else 0.0
+            assert mean == ans["mean"]
+            lo, hi = int(sg["region_off"][tid]), int(sg["region_off"][tid + 1])
+            assert np.array_equal(sg["start"][lo:hi], ans["start"]) and np.array_equal(sg["end"][lo:hi], ans["end"]), "case %d tid %d" % (i, tid)
+            assert np.array_equal(sg["kind"][lo:hi], ans["kind"])
+            alts = [util.oracle_alt(seq4, seq_off, {k: sg[k][j] for k in ("start", "end", "kind", "read_idx", "query_pos")}) for j in range(lo, hi)]
+            assert alts == ans["alt"], "ALT allele case %d tid %d" % (i, tid)
+            if "l2" in ans:
+                a, e, ss = ans["l2par"]
+                su, cn = b.window_sums(tid, [a], [e], ss)
+                lg = api.CNVCaller.log2_from_sums(su[0], cn[0], ans["mean"])
+                # golden is in the reference's hash order keyed by window centre: compare as multisets per centre
+                step = float(np.uint32(e - a + 1)) / float(ss)
+                cent = np.array([(int(np.uint32(a + k * step)) + int(np.uint32(a + (k + 1) * step))) // 2 for k in range(ss)], np.uint64)
+                o = np.argsort(ans["l2pos"], kind="stable"); oo = np.argsort(cent, kind="stable")
+                assert np.array_equal(cent[oo], ans["l2pos"][o].astype(np.uint64))
+                ref = ans["l2"][o]; got = lg[oo]
+                assert np.all(np.abs(got - ref) <= 1e-6 * np.maximum(np.abs(ref), 1e-3)), "log2 ratio beyond 1e-6 relative"
+        b.free()
+
+
+def test_random_adversarial_cigars(ctx, oracle):
+    rng = np.random.default_rng(11)
+    for it in range(30):
+        clen = [int(rng.choice([300, 2500, 12000, 70000])) for _ in range(int(rng.integers(1, 4)))]
+        r = util.random_cigar_reads(rng, int(rng.integers(0, 400)), clen, n_tids=len(clen), weird=bool(it % 2),
+                                    max_ops=int(rng.choice([3, 12, 40])))
+        check_contigs(ctx, oracle, r, clen)
+
+
+def test_long_reads_spanning_many_spans(ctx, oracle):
+    """ONT-like records: thousands of ops per record, so records straddle many 2048-op spans."""
+    r = util.synth_reads([3_000_000], seed=21, profile=1, coverage=6.0, read_len_mean=50000, indel_rate=0.1, indel_len_max=4, n_sv=60)
+    assert (np.diff(r["cig_off"]).max()) > 5000
+    check_contigs(ctx, oracle, r, [3_000_000])
+
+
+def test_synthetic_hifi_multi_contig(ctx, oracle):
+    clen = [1_500_000, 700_000, 50_000]
+    r = util.synth_reads(clen, seed=5, n_sv=300, coverage=30.0, frac_len50=0.1)
+    check_contigs(ctx, oracle, r, clen)
+
+
+def test_empty_and_degenerate_inputs(ctx, oracle):
+    from oracle.oracle_py import make_reads
+    # no reads at all
+    r = make_reads([], [])
+    check_contigs(ctx, oracle, r, [1000])
+    # only empty CIGARs, and empty ones between real ones
+    r = make_reads([5, 7, 9, 9, 30], [[], [(10, 0)], [], [], [(60, 1), (5, 0)]])
+    check_contigs(ctx, oracle, r, [100])
+    # one op exactly at the end of the contig; soft clip beyond the end (sv_caller.cpp:602-604)
+    r = make_reads([90, 95], [[(10, 0), (60, 4), (50, 1)], [(5, 0), (50, 4), (50, 1), (50, 2)]])
+    check_contigs(ctx, oracle, r, [100])
+    # contig exactly one tile and one tile + 1
+    for L in (8191, 8192, 8193):
+        r = util.synth_reads([L], seed=L, coverage=40.0, read_len_mean=900, read_len_sd=100, n_sv=3)
+        check_contigs(ctx, oracle, r, [L])
+
+
+def test_one_shot_entry_points(ctx, oracle):
+    clen = [60_000]
+    r = util.synth_reads(clen, seed=9, n_sv=30, coverage=20.0)
+    rs, keep = reads_struct(r)
+    reg = CsvRegion(0, 0, clen[0] + 1, clen[0] + 1)
+    depth = np.zeros(clen[0] + 1, np.uint32); s = C.c_uint64(0); nz = C.c_uint32(0)
+    check(lib().csv_depth(ctx.h, C.byref(rs), C.byref(reg), ptr(depth), C.byref(s), C.byref(nz)))
+    d, s0, nz0 = oracle.depth(r, 0, clen[0] + 1)
+    assert np.array_equal(depth, d) and s.value == s0 and nz.value == nz0
+    o = oracle.cigar_scan(r, 0, clen[0] + 1)
+    cap = len(o) + 8
+    arr = {k: np.zeros(cap, np.uint8 if k == "kind" else np.uint32) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
+    st = CsvSigs(*[ptr(arr[k]) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")])
+    n = C.c_uint64(0)
+    check(lib().csv_cigar_scan(ctx.h, C.byref(rs), C.byref(reg), 50, 20, C.byref(st), cap, C.byref(n)))
+    assert n.value == len(o)
+    for k in arr:
+        assert np.array_equal(arr[k][: len(o)], o[k])
+    # too small a caller buffer is reported, not overrun
+    rc = lib().csv_cigar_scan(ctx.h, C.byref(rs), C.byref(reg), 50, 20, C.byref(st), 1, C.byref(n))
+    assert rc == 3 and n.value == len(o)
+
+
+def test_region_sharding_with_halo_reads(ctx, oracle):
+    """shards of one contig give disjoint depth slices whose concatenation is the whole map,
+    stats add up, and every signature is emitted by exactly one shard."""
+    L = 400_000
+    r = util.synth_reads([L], seed=13, n_sv=120, coverage=25.0)
+    d, s, nz = oracle.depth(r, 0, L + 1)
+    o = oracle.cigar_scan(r, 0, L + 1)
+    cuts = [0, 100_003, 100_004, 250_000, L + 1]
+    regions = [(0, cuts[i], cuts[i + 1], L + 1) for i in range(len(cuts) - 1)]
+    b = run_batch(ctx, r, regions)
+    got = np.concatenate([b.depth(i) for i in range(len(regions))])
+    assert np.array_equal(got, d)
+    sums, nzs = b.depth_stats()
+    assert int(sums.sum()) == s and int(nzs.sum()) == nz
+    sg = b.sigs()
+    assert len(sg["start"]) == len(o)
+    # host merge with the addSVCall comparator: (start, end, reverse insertion order)
+    order = np.lexsort((-(sg["read_idx"].astype(np.int64) * (1 << 20) + sg["op_idx"]), sg["end"], sg["start"]))
+    for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+        assert np.array_equal(sg[f][order], o[f])
+    # ownership: region of a signature == region containing pos0 + 1 of its read
+    for i in range(len(regions)):
+        lo, hi = int(sg["region_off"][i]), int(sg["region_off"][i + 1])
+        idx = r["pos0"][sg["read_idx"][lo:hi]].astype(np.int64) + 1
+        assert np.all((idx >= cuts[i]) & (idx < cuts[i + 1]))
+    b.free()
+    # regions in scrambled caller order
+    perm = [2, 0, 3, 1]
+    b = run_batch(ctx, r, [regions[p] for p in perm])
+    for j, p in enumerate(perm):
+        assert np.array_equal(b.depth(j), d[cuts[p]:cuts[p + 1]])
+    b.free()
+
+
+def test_dbscan1d_fuzz_and_large(ctx, oracle):
+    rng = np.random.default_rng(3)
+    for it in range(200):
+        n = int(rng.integers(0, 300))
+        span = int(rng.choice([5, 30, 200, 5000, 2_000_000_000]))
+        pts = rng.integers(-span, span, n).astype(np.int32)
+        eps = float(rng.choice([-1, 0, 0.5, 1, 2, 3.7, 10, 50, 100, 1e12]))
+        mp = int(rng.choice([-1, 0, 1, 2, 3, 5, 8]))
+        db = api.DBSCAN1D(eps, mp, ctx); db.fit(pts)
+        assert np.array_equal(db.getClusters(), oracle.dbscan1d(pts, eps, mp)), (pts.tolist(), eps, mp)
+    # sizes the O(N^2) reference cannot reach: checked against the closed-form oracle
+    for n, eps, mp in ((20_000, 100, 5), (300_000, 10, 3), (1_000_000, 50, 5)):
+        centers = rng.integers(0, 46_000_000, n // 25)
+        pts = (rng.choice(centers, n) + np.rint(rng.normal(0, 10, n)).astype(np.int64)).astype(np.int32)
+        db = api.DBSCAN1D(eps, mp, ctx); db.fit(pts)
+        want = oracle.dbscan1d(pts, eps, mp, fast=True) if n > 20_000 else oracle.dbscan1d(pts, eps, mp)
+        assert np.array_equal(db.getClusters(), want)
+
+
+def test_dbscan1d_segments(ctx, oracle):
+    rng = np.random.default_rng(4)
+    n, n_seg = 5000, 7
+    seg = rng.integers(0, n_seg, n).astype(np.uint32)
+    pts = (rng.integers(0, 40, n) * 500 + rng.integers(-20, 20, n)).astype(np.int32)
+    lab, nc = api.dbscan1d_segments(pts, seg, n_seg, 15.0, 4, ctx)
+    for sgm in range(n_seg):
+        m = seg == sgm
+        want = oracle.dbscan1d(pts[m], 15.0, 4)
+        assert np.array_equal(lab[m], want)
+        assert nc[sgm] == (want.max() + 1 if len(want) and want.max() >= 0 else 0)
+
+
+def test_signature_clustering_on_device(ctx, oracle):
+    clen = [900_000, 300_000]
+    r = util.synth_reads(clen, seed=17, n_sv=250, coverage=30.0, sv_jitter_sd=10.0)
+    b = run_batch(ctx, r, api.whole_contig_regions(clen))
+    sg = b.sigs()
+    lab = b.sigs_dbscan1d(100.0, 5)
+    for tid in range(len(clen)):
+        lo, hi = int(sg["region_off"][tid]), int(sg["region_off"][tid + 1])
+        for is_del in (True, False):
+            m = np.zeros(len(lab), bool); m[lo:hi] = True
+            m &= (sg["kind"] == 1) if is_del else (sg["kind"] != 1)
+            want = oracle.dbscan1d(sg["start"][m].astype(np.int32), 100.0, 5, fast=True)
+            assert np.array_equal(lab[m], want)
+    b.free()
+
+
+def test_mirror_classes(ctx, oracle):
+    """The reference-shaped host interface (CNVCaller / SVCaller mirrors in contextsv_b200.api)."""
+    clen = [80_000, 20_000]
+    r = util.synth_reads(clen, seed=23, n_sv=40, coverage=15.0, frac_len50=0.3)
+    rng = np.random.default_rng(23)
+    seq4, seq_off = util.random_seq4(rng, r)
+    aln = api.Alignments(r, ["chr21", "chrM"], clen, seq4, seq_off)
+    depth_map = {"chr21": np.zeros(clen[0] + 1, np.uint32), "chrM": np.zeros(5, np.uint32)}   # chrM: wrong size -> resized
+    mean_map = {}
+    errors = []
+    api.CNVCaller(ctx).calculateMeanChromosomeCoverage(["chr21", "chrM", "chrNope"], depth_map, mean_map, aln, 1, errors.append)
+    for tid, chrom in enumerate(["chr21", "chrM"]):
+        d, s, nz = oracle.depth(r, tid, clen[tid] + 1)
+        assert np.array_equal(depth_map[chrom], d)
+        assert mean_map[chrom] == oracle.mean_cov(s, nz)
+    assert len(errors) == 2 and "chrNope" in errors[0] and "mismatch" in errors[1]
+    calls = []
+    api.SVCaller(ctx).findCIGARSVs(aln, "chr21", calls, depth_map["chr21"])
+    o = oracle.cigar_scan(r, 0, clen[0] + 1)
+    assert [(c.start, c.end) for c in calls] == [(int(x["start"]), int(x["end"])) for x in o]
+    assert [c.alt_allele for c in calls] == [util.oracle_alt(seq4, seq_off, x) for x in o]
+    assert any(len(c.alt_allele) == 50 for c in calls)

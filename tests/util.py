@@ -1,0 +1,126 @@
+"""Shared helpers of the test-suite: input builders and oracle-side conveniences."""
+import numpy as np
+
+from contextsv_b200 import synth
+from oracle.oracle_py import make_reads, norm_reads
+
+M, I, D, N, S, H, P, EQ, X, B = range(10)
+
+
+def synth_reads(contig_len, **kw):
+    return synth.generate(contig_len, **kw)
+
+
+def random_cigar_reads(rng, n_reads, contig_len, max_ops=12, ops=(M, I, D, N, S, H, P, EQ, X), big_p=0.25, n_tids=1,
+                       weird=False):
+    """Adversarial records: arbitrary op alphabets, many ops >= 50, empty CIGARs, zero-length ops,
+    reads running off the contig end, all flag/MAPQ combinations.  Sorted by (tid, pos0)."""
+    tid = np.sort(rng.integers(0, n_tids, n_reads)).astype(np.int32)
+    pos0 = np.zeros(n_reads, np.int64)
+    for t in range(n_tids):
+        m = tid == t
+        pos0[m] = np.sort(rng.integers(0, contig_len[t] + (60 if weird else 0), int(m.sum())))
+    if weird and n_reads > 3:
+        first = np.nonzero(tid == 0)[0]
+        if len(first):
+            pos0[first[0]] = -1          # (uint32)(-1) + 1 == 0: depth index 0, sv pos wraps (cnv_caller.cpp:499)
+    cigars = []
+    for i in range(n_reads):
+        k = int(rng.integers(0, max_ops + 1))
+        c = []
+        for _ in range(k):
+            op = int(rng.choice(ops))
+            u = rng.random()
+            if u < big_p:
+                ln = int(rng.choice([49, 50, 51, 60, 100, 500]))
+            elif u < big_p + 0.05:
+                ln = 0
+            else:
+                ln = int(rng.integers(1, 40))
+            c.append((ln, op))
+        cigars.append(c)
+    flag = rng.choice([0, 16, 4, 0x100, 0x200, 0x400, 0x800, 0x810, 0], n_reads, p=[.4, .3, .03, .03, .03, .03, .06, .06, .06]).astype(np.uint16)
+    mapq = rng.choice([0, 19, 20, 21, 60], n_reads).astype(np.uint8)
+    r = make_reads(pos0.astype(np.int32), cigars, tid=tid if n_tids > 1 else None, flag=flag, mapq=mapq)
+    return r
+
+
+def random_seq4(rng, reads):
+    """4-bit packed bases per record (BAM encoding); includes IUPAC codes to exercise the ->N mapping."""
+    r = norm_reads(reads)
+    n = int(r["n_reads"])
+    qlen = np.zeros(n, np.int64)
+    cig = r["cigar"]; off = r["cig_off"]
+    qmask = (1 << 0) | (1 << 1) | (1 << 4) | (1 << 7) | (1 << 8)
+    for i in range(n):
+        c = cig[int(off[i]):int(off[i + 1])]
+        qlen[i] = int(((c >> 4) * ((qmask >> (c & 15)) & 1)).sum())
+    nbytes = (qlen + 1) // 2
+    seq_off = np.zeros(n, np.uint64)
+    seq_off[1:] = np.cumsum(nbytes)[:-1]
+    total = int(nbytes.sum())
+    codes = rng.choice(np.arange(16, dtype=np.uint8), size=2 * total + 2, p=[.01] + [.20, .20, .01, .20, .01, .01, .01, .20, .01, .01, .01, .01, .01, .01, .09])
+    seq4 = ((codes[0::2][:total] << 4) | codes[1::2][:total]).astype(np.uint8)
+    return np.ascontiguousarray(seq4), seq_off
+
+
+def oracle_alt(seq4, seq_off, sig):
+    """ALT allele the reference builds for a signature (sv_caller.cpp:572-591)."""
+    NT16 = "=ACMGRSVTWYHKDBN"
+    if sig["kind"] == 1:
+        return "<DEL>"
+    ln = int(sig["end"]) - int(sig["start"]) + 1
+    if ln > 50:
+        return "<INS>"
+    out = []
+    base = int(seq_off[int(sig["read_idx"])])
+    for j in range(ln):
+        q = int(sig["query_pos"]) + j
+        b = int(seq4[base + (q >> 1)])
+        ch = NT16[(b >> ((~q & 1) << 2)) & 0xF]
+        out.append("N" if ch in "RYKMSWBDHV" else ch)
+    return "".join(out)
+
+
+# ------------------------------------------------------------------ golden vectors
+
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+_golden = None
+
+
+def golden():
+    global _golden
+    if _golden is None:
+        _golden = np.load(GOLDEN)
+    return _golden
+
+
+def golden_db_cases():
+    g = golden()
+    for i in range(int(g["n_db"][0])):
+        eps, mp = g["db%d_par" % i]
+        yield i, g["db%d_pts" % i], float(eps), int(mp), g["db%d_labels" % i], g["db%d_largest" % i]
+
+
+def golden_cg_cases():
+    g = golden()
+    for i in range(int(g["n_cg"][0])):
+        p = "cg%d" % i
+        tid = g[p + "_tid"]
+        r = norm_reads({"n_reads": len(g[p + "_pos0"]), "tid": tid if len(tid) else None, "pos0": g[p + "_pos0"], "flag": g[p + "_flag"],
+                        "mapq": g[p + "_mapq"], "cig_off": g[p + "_cig_off"], "cigar": g[p + "_cigar"]})
+        yield i, r, [int(x) for x in g[p + "_clen"]], g[p + "_seq4"], g[p + "_seq_off"]
+
+
+def golden_cg_answer(i, tid):
+    g = golden()
+    q = "cg%d_t%d" % (i, tid)
+    ev = g[q + "_evidence"]
+    kind = np.where(ev == 1, 0, np.where(ev == 2, 1, 2)).astype(np.uint8)   # bitset<10>: bit0 CIGARINS, bit1 CIGARDEL, bit2 CIGARCLIP
+    ans = {"depth": g[q + "_depth"], "sum": int(g[q + "_stats"][0]), "nonzero": int(g[q + "_stats"][1]), "mean": float(g[q + "_mean"][0]),
+           "start": g[q + "_start"], "end": g[q + "_end"], "kind": kind, "svtype": g[q + "_svtype"], "alt": [str(a) for a in g[q + "_alt"]]}
+    if q + "_l2" in g.files:
+        ans["l2par"] = [int(x) for x in g[q + "_l2par"]]; ans["l2pos"] = g[q + "_l2pos"]; ans["l2"] = g[q + "_l2"]
+    return ans
