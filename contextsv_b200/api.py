@@ -59,6 +59,17 @@ class Context:
         check(lib().csv_timer_end(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def profile_enable(self, on=True):
+        check(lib().csv_profile_enable(self.h, int(on)))
+
+    def profile_read(self, reset=True):
+        """{stage: (total_ms, calls)} accumulated while profiling was enabled."""
+        names = (C.c_char_p * 16)(); ms = (C.c_double * 16)(); calls = (C.c_uint32 * 16)()
+        n = lib().csv_profile_read(self.h, 16, names, ms, calls, int(reset))
+        if n < 0:
+            check(-n)
+        return {names[i].decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
+
     @property
     def launches(self):
         return int(lib().csv_ctx_launch_count(self.h))

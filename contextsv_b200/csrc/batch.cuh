@@ -45,13 +45,13 @@ struct csv_batch {
     csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_qpos, d_sig_kind, d_sig_payload;
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
 
-    void release() {
+    void release(csv::DevPool* pool = nullptr) {
         csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_ne_idx, &d_headbits, &d_scalars,
                               &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_tile_cn, &d_tile_off,
                               &d_tile_net, &d_events, &d_depth, &d_sum, &d_nz, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
-        for (auto* b : all) b->release();
+        for (auto* b : all) b->release(pool);
     }
 };
 

@@ -39,6 +39,22 @@ int ensure_status(csv_ctx* ctx, size_t words)
     return CSV_OK;
 }
 
+static cudaEvent_t get_event(csv_ctx* ctx)
+{
+    if (!ctx->spare_events.empty()) { cudaEvent_t e = ctx->spare_events.back(); ctx->spare_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+StageTimer::StageTimer(csv_ctx* c, int s) : ctx(c), stage(s)
+{
+    if (!ctx->profile) return;
+    cudaEvent_t e0 = get_event(ctx); e1 = get_event(ctx);
+    cudaEventRecord(e0, ctx->stream);
+    ctx->stage_events[stage].emplace_back(e0, e1);
+}
+StageTimer::~StageTimer() { if (e1) cudaEventRecord(e1, ctx->stream); }
+
 static int read_scalars(csv_ctx* ctx, csv_batch* b, uint32_t* out /* SC_COUNT */)
 {
     CSV_CUDA(cudaMemcpyAsync(ctx->pinned_small, b->d_scalars.p, SC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -98,6 +114,9 @@ void csv_ctx_destroy(csv_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->pool.trim();
+    for (auto& v : ctx->stage_events) for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto e : ctx->spare_events) cudaEventDestroy(e);
     ctx->tickets.release(); ctx->scan_status.release();
     for (auto& b : ctx->sort_tmp) b.release();
     for (auto& b : ctx->db) b.release();
@@ -135,6 +154,35 @@ int csv_timer_end(csv_ctx* ctx, float* ms_out)
     return CSV_OK;
 }
 uint64_t csv_ctx_launch_count(const csv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int csv_profile_enable(csv_ctx* ctx, int on)
+{
+    if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
+    ctx->profile = on != 0;
+    return CSV_OK;
+}
+
+int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, double* ms_out, uint32_t* calls_out, int reset)
+{
+    static const char* kNames[ST_COUNT] = {"prep", "walk_count", "tile_scan", "walk_scatter", "depth_tiles", "sig_sort", "dbscan1d"};
+    if (!ctx) { set_error("null context"); return -CSV_ERR_ARG; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("csv_profile_read: stream synchronisation failed"); return -CSV_ERR_CUDA; }
+    for (int s = 0; s < ST_COUNT; s++) {
+        for (auto& e : ctx->stage_events[s]) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) { ctx->stage_ms[s] += ms; ctx->stage_calls[s]++; }
+            ctx->spare_events.push_back(e.first); ctx->spare_events.push_back(e.second);
+        }
+        ctx->stage_events[s].clear();
+    }
+    for (int s = 0; s < ST_COUNT && s < max_stages; s++) {
+        if (names_out) names_out[s] = kNames[s];
+        if (ms_out) ms_out[s] = ctx->stage_ms[s];
+        if (calls_out) calls_out[s] = ctx->stage_calls[s];
+    }
+    if (reset) for (int s = 0; s < ST_COUNT; s++) { ctx->stage_ms[s] = 0; ctx->stage_calls[s] = 0; }
+    return ST_COUNT;
+}
 
 /* ------------------------------------------------------------------ batch */
 
@@ -195,24 +243,24 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
 
     // ---- allocations
     const size_t nr = r->n_reads, no = (size_t)r->n_ops, nt = b->n_tiles, sc = (size_t)b->sig_cap;
-    if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16));
-    CSV_TRY(b->d_pos0.ensure(nr * 4 + 16)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16)); CSV_TRY(b->d_mapq.ensure(nr + 16));
-    CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64));
-    CSV_TRY(b->d_meta.ensure(nr * 16 + 16)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16)); CSV_TRY(b->d_headbits.ensure(no / 8 + 64));
-    CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4));
-    CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev))); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev)));
-    CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4));
-    CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16));
-    CSV_TRY(b->d_span_status.ensure((size_t)b->n_spans * 4 + 16));
+    if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16, &ctx->pool));
+    CSV_TRY(b->d_pos0.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16, &ctx->pool)); CSV_TRY(b->d_mapq.ensure(nr + 16, &ctx->pool));
+    CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8, &ctx->pool)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64, &ctx->pool));
+    CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 64, &ctx->pool));
+    CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4, &ctx->pool));
+    CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev), &ctx->pool)); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev), &ctx->pool));
+    CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4, &ctx->pool)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4, &ctx->pool));
+    CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
+    CSV_TRY(b->d_span_status.ensure((size_t)b->n_spans * 4 + 16, &ctx->pool));
     CSV_CUDA(cudaMemsetAsync(b->d_span_status.p, 0, b->d_span_status.cap, ctx->stream));
-    CSV_TRY(b->d_tile_cn.ensure(nt * 8 + 16)); CSV_TRY(b->d_tile_off.ensure(nt * 4 + 16)); CSV_TRY(b->d_tile_net.ensure(nt * 4 + 16));
-    CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 2)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4));
-    CSV_TRY(b->d_sum.ensure(n_regions * 8)); CSV_TRY(b->d_nz.ensure(n_regions * 4));
-    CSV_TRY(b->d_sig_hi.ensure(sc * 8)); CSV_TRY(b->d_sig_lo.ensure(sc * 8)); CSV_TRY(b->d_sig_k.ensure(sc * 4));
-    CSV_TRY(b->d_sig_qpos.ensure(sc * 4)); CSV_TRY(b->d_sig_kind.ensure(sc)); CSV_TRY(b->d_sig_payload.ensure(sc * 4));
-    CSV_TRY(b->d_out_start.ensure(sc * 4)); CSV_TRY(b->d_out_end.ensure(sc * 4)); CSV_TRY(b->d_out_kind.ensure(sc));
-    CSV_TRY(b->d_out_read.ensure(sc * 4)); CSV_TRY(b->d_out_op.ensure(sc * 4)); CSV_TRY(b->d_out_qpos.ensure(sc * 4));
-    CSV_TRY(b->d_out_seg.ensure(sc * 4));
+    CSV_TRY(b->d_tile_cn.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_off.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_net.ensure(nt * 4 + 16, &ctx->pool));
+    CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 2, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
+    CSV_TRY(b->d_sum.ensure(n_regions * 8, &ctx->pool)); CSV_TRY(b->d_nz.ensure(n_regions * 4, &ctx->pool));
+    CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_sig_qpos.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_out_start.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_end.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_kind.ensure(sc, &ctx->pool));
+    CSV_TRY(b->d_out_read.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_op.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_qpos.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_out_seg.ensure(sc * 4, &ctx->pool));
 
     // ---- uploads (asynchronous when the host buffers are pinned)
     cudaStream_t st = ctx->stream;
@@ -239,7 +287,7 @@ void csv_batch_free(csv_ctx* ctx, csv_batch* b)
 {
     if (!b) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    b->release();
+    b->release(ctx ? &ctx->pool : nullptr);
     delete b;
 }
 
@@ -255,14 +303,14 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         CSV_CUDA(cudaMemsetAsync(b->d_sum.p, 0, b->n_regions * 8, st));
         CSV_CUDA(cudaMemsetAsync(b->d_nz.p, 0, b->n_regions * 4, st));
     }
-    CSV_TRY(launch_prep(ctx, b));
-    CSV_TRY(launch_walk(ctx, b, p, 0));
+    { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b)); }
+    { StageTimer t(ctx, ST_WALK_COUNT); CSV_TRY(launch_walk(ctx, b, p, 0)); }
     if (p->want_depth) {
-        CSV_TRY(launch_tile_scan(ctx, b));
-        CSV_TRY(launch_walk(ctx, b, p, 1));
-        CSV_TRY(launch_depth_tiles(ctx, b));
+        { StageTimer t(ctx, ST_TILE_SCAN); CSV_TRY(launch_tile_scan(ctx, b)); }
+        { StageTimer t(ctx, ST_WALK_SCATTER); CSV_TRY(launch_walk(ctx, b, p, 1)); }
+        { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b)); }
     }
-    if (p->want_sigs) CSV_TRY(launch_sig_finish(ctx, b));
+    if (p->want_sigs) { StageTimer t(ctx, ST_SIG_SORT); CSV_TRY(launch_sig_finish(ctx, b)); }
     b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;
     return CSV_OK;
 }
@@ -342,7 +390,7 @@ int csv_sigs_dbscan1d(csv_ctx* ctx, csv_batch* b, double eps, int min_pts, int32
 {
     if (!ctx || !b) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_dbscan1d: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
-    CSV_TRY(launch_sig_dbscan(ctx, b, eps, min_pts));
+    { StageTimer t(ctx, ST_DBSCAN); CSV_TRY(launch_sig_dbscan(ctx, b, eps, min_pts)); }
     b->have_labels = true;
     if (labels_out) {
         uint32_t sc[SC_COUNT];

@@ -50,20 +50,49 @@ constexpr uint32_t kDepthSkipFlags = 0x4 | 0x100 | 0x200 | 0x400;          // cn
 constexpr uint32_t kSigSkipFlags = 0x4 | 0x100 | 0x200 | 0x400 | 0x800;    // sv_caller.cpp:526
 
 // ------------------------------------------------------------ device buffer
+// Freed batch buffers are parked in a per-context pool so that the next upload of
+// a similar batch does not pay cudaMalloc/cudaFree (both synchronise the device).
+struct DevPool {
+    std::vector<std::pair<void*, size_t>> free_list;
+    void* take(size_t bytes) {
+        int best = -1;
+        for (int i = 0; i < (int)free_list.size(); i++)
+            if (free_list[i].second >= bytes && free_list[i].second <= 2 * bytes + (1u << 20) &&
+                (best < 0 || free_list[i].second < free_list[best].second)) best = i;
+        if (best < 0) return nullptr;
+        void* p = free_list[best].first;
+        last_cap = free_list[best].second;
+        free_list.erase(free_list.begin() + best);
+        return p;
+    }
+    size_t last_cap = 0;
+    void give(void* p, size_t cap) { free_list.emplace_back(p, cap); }
+    void trim() { for (auto& e : free_list) cudaFree(e.first); free_list.clear(); }
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
-    int ensure(size_t bytes) {
+    int ensure(size_t bytes, DevPool* pool = nullptr) {
         if (bytes <= cap) return CSV_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        release(pool);
+        if (pool) { p = pool->take(bytes); if (p) { cap = pool->last_cap; return CSV_OK; } }
         size_t want = bytes + bytes / 8 + 256;
-        CSV_CUDA(cudaMalloc(&p, want));
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && pool) { cudaGetLastError(); pool->trim(); e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) { p = nullptr; csv::set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return CSV_ERR_CUDA; }
         cap = want;
         return CSV_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release(DevPool* pool = nullptr) {
+        if (p) { if (pool) pool->give(p, cap); else cudaFree(p); }
+        p = nullptr; cap = 0;
+    }
     template <class T> T* as() const { return (T*)p; }
 };
+
+// Per-stage device timing (CUDA events on the context's stream), for bench.py's roofline.
+enum Stage { ST_PREP = 0, ST_WALK_COUNT, ST_TILE_SCAN, ST_WALK_SCATTER, ST_DEPTH_TILES, ST_SIG_SORT, ST_DBSCAN, ST_COUNT };
 
 // Region tables (device copies live in the batch)
 struct RegionDev {       // sorted by (tid, beg)
@@ -92,6 +121,12 @@ struct csv_ctx {
     csv::DevBuf db[16];                 // DBSCAN scratch
     void* pinned_small = nullptr;       // 4 KB pinned staging for tiny D2H reads
     int sm_count = csv::kSMs;
+    csv::DevPool pool;                  // parked batch buffers
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events[csv::ST_COUNT];
+    std::vector<cudaEvent_t> spare_events;
+    double stage_ms[csv::ST_COUNT] = {0};
+    uint32_t stage_calls[csv::ST_COUNT] = {0};
 };
 
 namespace csv {
@@ -99,6 +134,12 @@ namespace csv {
 int next_ticket(csv_ctx* ctx, uint32_t** out);
 inline uint32_t next_epoch(csv_ctx* ctx) { ctx->epoch++; if (ctx->epoch >= 0x3fffffffu) ctx->epoch = 1; return ctx->epoch; }
 int ensure_status(csv_ctx* ctx, size_t words);   // u64 words; never needs clearing (epoch-tagged)
+// RAII stage timer: records an event pair around a pipeline stage when profiling is on.
+struct StageTimer {
+    csv_ctx* ctx; int stage; cudaEvent_t e1 = nullptr;
+    StageTimer(csv_ctx* c, int s);
+    ~StageTimer();
+};
 }
 
 // ------------------------------------------------------------- device utils

@@ -1,0 +1,99 @@
+"""Host-side region planner and result merging for multi-GPU runs.
+
+The path shards by chromosome/region with no exchange step: every rank scans the reads that overlap
+its regions (its own reads plus the halo reads that start before a region and reach into it), depth
+slices are disjoint and simply concatenated, per-region (sum, nonzero) add up, and the signatures of
+each read come from the one region that owns it.  The reference only shards by whole chromosome
+(sv_caller.cpp:847-851).
+"""
+import numpy as np
+
+GRCH38 = [
+    ("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555), ("chr5", 181538259),
+    ("chr6", 170805979), ("chr7", 159345973), ("chr8", 145138636), ("chr9", 138394717), ("chr10", 133797422),
+    ("chr11", 135086622), ("chr12", 133275309), ("chr13", 114364328), ("chr14", 107043718), ("chr15", 101991189),
+    ("chr16", 90338345), ("chr17", 83257441), ("chr18", 80373285), ("chr19", 58617616), ("chr20", 64444167),
+    ("chr21", 46709983), ("chr22", 50818468), ("chrX", 156040895), ("chrY", 57227415),
+]
+
+
+def plan_regions(contig_len, n_shards):
+    """Cuts the concatenated depth-map index space (sum of L+1) into n_shards contiguous pieces of
+    (almost) equal length.  Returns a list (one entry per shard) of lists of (tid, beg, end, map_size)."""
+    sizes = [int(l) + 1 for l in contig_len]
+    total = sum(sizes)
+    bounds = [(total * k) // n_shards for k in range(n_shards + 1)]
+    shards = [[] for _ in range(n_shards)]
+    base = 0
+    for tid, size in enumerate(sizes):
+        for k in range(n_shards):
+            lo, hi = max(bounds[k], base), min(bounds[k + 1], base + size)
+            if lo < hi:
+                shards[k].append((tid, lo - base, hi - base, size))
+        base += size
+    return shards
+
+
+REF_MASK = (1 << 0) | (1 << 2) | (1 << 3) | (1 << 7) | (1 << 8)
+
+
+def ref_end(reads):
+    """pos0 + 1 + reference length of every record (depth-map index one past the last covered base)."""
+    n = int(reads["n_reads"])
+    cig = np.asarray(reads["cigar"]); off = np.asarray(reads["cig_off"]).astype(np.int64)
+    rl = (cig >> 4).astype(np.int64) * ((REF_MASK >> (cig & 15)) & 1)
+    csum = np.concatenate([[0], np.cumsum(rl)])
+    return np.asarray(reads["pos0"]).astype(np.int64) + 1 + (csum[off[1:n + 1]] - csum[off[:n]])
+
+
+def select_reads(reads, regions, ends=None):
+    """Contiguous slice of the (tid, pos0)-sorted records that contains every record overlapping or owned
+    by `regions` (a shard's region list, in genome order).  Views, no copy of the CIGAR words."""
+    n = int(reads["n_reads"])
+    if n == 0 or not regions:
+        return dict(reads), 0
+    tid = np.zeros(n, np.int64) if reads.get("tid") is None else np.asarray(reads["tid"]).astype(np.int64)
+    idx = np.asarray(reads["pos0"]).astype(np.int64) + 1
+    ends = ref_end(reads) if ends is None else ends
+    t0, b0, _, _ = regions[0]
+    t1, _, e1, m1 = regions[-1]
+    key = tid * (1 << 33) + idx
+    i_own = int(np.searchsorted(key, t0 * (1 << 33) + b0, side="left"))
+    # halo: records of contig t0 that start before b0 and reach past it
+    lo_t = int(np.searchsorted(key, t0 * (1 << 33), side="left"))
+    halo = np.nonzero(ends[lo_t:i_own] > b0)[0]
+    i0 = lo_t + int(halo[0]) if len(halo) else i_own
+    if e1 == m1:
+        i1 = int(np.searchsorted(key, (t1 + 1) * (1 << 33), side="left"))     # last region also owns records beyond the contig end
+    else:
+        i1 = int(np.searchsorted(key, t1 * (1 << 33) + e1, side="left"))
+    i1 = max(i1, i0)
+    off = np.asarray(reads["cig_off"])
+    o0, o1 = int(off[i0]), int(off[i1])
+    sub = {
+        "n_reads": i1 - i0, "n_ops": o1 - o0,
+        "tid": None if reads.get("tid") is None else reads["tid"][i0:i1],
+        "pos0": reads["pos0"][i0:i1], "flag": reads["flag"][i0:i1], "mapq": reads["mapq"][i0:i1],
+        "cig_off": (off[i0:i1 + 1] - np.uint64(o0)).astype(np.uint64), "cigar": reads["cigar"][o0:o1],
+    }
+    return sub, i0
+
+
+def merge_signatures(parts):
+    """parts: list of (sigs dict from Batch.sigs(), regions, read index offset) per shard, in genome order.
+    Returns one dict per contig id in the reference's vector order (start, end, reverse insertion order)."""
+    per_tid = {}
+    for sg, regions, base in parts:
+        for r, (tid, _, _, _) in enumerate(regions):
+            lo, hi = int(sg["region_off"][r]), int(sg["region_off"][r + 1])
+            d = per_tid.setdefault(tid, {k: [] for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")})
+            for k in d:
+                v = sg[k][lo:hi]
+                d[k].append(v.astype(np.int64) + base if k == "read_idx" else v)
+    out = {}
+    for tid, d in per_tid.items():
+        m = {k: np.concatenate(v) if v else np.zeros(0) for k, v in d.items()}
+        seq = m["read_idx"].astype(np.int64) * (1 << 31) + m["op_idx"].astype(np.int64)
+        order = np.lexsort((-seq, m["end"], m["start"]))
+        out[tid] = {k: v[order] for k, v in m.items()}
+    return out

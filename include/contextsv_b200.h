@@ -54,6 +54,13 @@ int csv_timer_begin(csv_ctx* ctx);
 int csv_timer_end(csv_ctx* ctx, float* ms_out);  /* synchronises the end event           */
 /* Kernels launched by this context since creation. */
 uint64_t csv_ctx_launch_count(const csv_ctx* ctx);
+/* Per-stage device time of the scan pipeline (event pairs around each stage while
+ * enabled).  csv_profile_read synchronises, fills up to max_stages entries
+ * (stage name, accumulated ms, number of timed calls) and returns the number of
+ * stages, or a negative csv_status. */
+int csv_profile_enable(csv_ctx* ctx, int on);
+int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, double* ms_out,
+                     uint32_t* calls_out, int reset);
 
 /* --------------------------------------------------------------- input SoA */
 

@@ -18,6 +18,7 @@
 #include "htslib_shim/shim_mem.h"
 
 #include <atomic>
+#include <mutex>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -28,20 +29,30 @@ namespace {
 std::atomic<uint64_t> g_counter{0};
 std::string unique_name() { return "h" + std::to_string(g_counter++); }
 
-/* the reference chats on stdout/stderr for every call; keep test logs readable */
+/* the reference chats on stdout/stderr for every call; keep test logs readable.
+ * Process-wide fd redirection, reference-counted so concurrent harness calls
+ * (bench.py runs one contig per thread) nest correctly. */
+std::mutex g_quiet_mu;
+int g_quiet_depth = 0, g_saved_out = -1, g_saved_err = -1;
 struct Quiet {
-    int so, se;
-    explicit Quiet(bool on) : so(-1), se(-1) {
+    bool on;
+    explicit Quiet(bool o) : on(o) {
         if (!on) return;
-        fflush(stdout); fflush(stderr);
-        so = dup(1); se = dup(2);
-        int nul = open("/dev/null", O_WRONLY);
-        dup2(nul, 1); dup2(nul, 2); close(nul);
+        std::lock_guard<std::mutex> lk(g_quiet_mu);
+        if (g_quiet_depth++ == 0) {
+            fflush(stdout); fflush(stderr);
+            g_saved_out = dup(1); g_saved_err = dup(2);
+            int nul = open("/dev/null", O_WRONLY);
+            dup2(nul, 1); dup2(nul, 2); close(nul);
+        }
     }
     ~Quiet() {
-        if (so < 0) return;
-        fflush(stdout); fflush(stderr);
-        dup2(so, 1); dup2(se, 2); close(so); close(se);
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_quiet_mu);
+        if (--g_quiet_depth == 0) {
+            fflush(stdout); fflush(stderr);
+            dup2(g_saved_out, 1); dup2(g_saved_err, 2); close(g_saved_out); close(g_saved_err);
+        }
     }
 };
 int g_quiet = 1;
