@@ -5,7 +5,7 @@
   python bench.py --impl reference ...     the reference's own CPU code (oracle/_ref) on the host cores
 
 One "step" = one pass of the hot path over one batch: prep + CIGAR walk (signatures, depth events) +
-tile scan + event scatter + depth tiles + signature sort + DBSCAN1D over the signature starts.
+tile event ranges + depth tiles + signature sort + DBSCAN1D over the signature starts.
   value  : device-resident inputs, CUDA-event time on the library's own stream, max over ranks
   e2e    : same work through the host-facing C-ABI calls with HOST buffers: H2D of the packed SoA and
            D2H of depth maps, signatures and labels inside the timed region (wall clock, max over ranks)
@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -71,7 +71,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -83,7 +89,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for row in self.rows:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.11]
+        if not inside and self.rows:          # timed region shorter than the sampling period: nearest sample
+            inside = [min(self.rows, key=lambda x: abs(x[0] - t1))[1]]
+        for row in inside:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 8:
                 continue
@@ -245,20 +255,25 @@ def main_ours(args):
         batch.scan(want_depth=True, want_sigs=True)
         batch.sigs_dbscan1d(DB_EPS, DB_MIN_PTS, fetch=False)
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init) can stall kernel launches for
+    # hundreds of milliseconds; only samples taken inside the timed region are reported
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(1.0)
     for _ in range(args.warmup):
         step_resident()
     ctx.sync()
     n_sig = batch.sigs_count()
     ctx.profile_read(reset=True)
     ctx.profile_enable(True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launches
     ctx.timer_begin()
     for _ in range(args.steps):
         step_resident()
     ms = ctx.timer_end()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop()
     launches = ctx.launches - launches0
@@ -303,17 +318,20 @@ def main_ours(args):
         return len(lab), sg, sums, nzs
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nl, sg, sums, nzs = step_e2e()
-    ctx.sync()
-    dt = time.perf_counter() - t0
-    barrier()
-    dt_max = max_over_ranks(dt)
-    e2e_value = total_reads * e2e_steps / dt_max
+    if args.skip_e2e:        # profiling runs only (ncu): never used for a reported number
+        e2e_steps, dt_max, e2e_value = 0, 0.0, None
+    else:
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nl, sg, sums, nzs = step_e2e()
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt_max = max_over_ranks(dt)
+        e2e_value = total_reads * e2e_steps / dt_max
     h2d = 15 * n_reads + 8 + 4 * n_ops
     d2h = 4 * depth_words + 21 * n_sig + 4 * n_sig + 12 * len(regions)
 
@@ -340,7 +358,7 @@ def main_ours(args):
                        "host_generation_s": round(t_gen, 2)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * dt_max / e2e_steps},
+                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1)},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -360,6 +378,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018 + 2)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3        # timing rule: at least 3 warm-up steps

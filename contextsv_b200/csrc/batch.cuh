@@ -6,7 +6,7 @@ namespace csv {
 constexpr uint32_t kNone = 0xffffffffu;
 
 // u32 slots of csv_batch::d_scalars
-enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_EV_TOTAL = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_COUNT = 16 };
+enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_COUNT = 16 };
 
 struct SigRaw {          // emission-order signature records (device)
     unsigned long long* key_hi;   // owner region << 32 | start
@@ -31,7 +31,7 @@ struct csv_batch {
     // input SoA (device)
     csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar;
     // derived per-read tables
-    csv::DevBuf d_meta;      // uint4 {pos0, tid|kNone, flag | mapq << 16, owner region | kNone} per non-empty read
+    csv::DevBuf d_meta;      // uint4 {pos0, tid, flag | mapq << 16 | ignored << 31, owner region | kNone} per non-empty read
     csv::DevBuf d_ne_idx;    // compact index -> record index
     csv::DevBuf d_headbits;  // one bit per op: op is the first of its record (+ sentinel bit at n_ops)
     csv::DevBuf d_scalars;   // SC_* counters
@@ -40,15 +40,17 @@ struct csv_batch {
     // walk
     csv::DevBuf d_span_agg, d_span_pre, d_span_status;
     // depth
-    csv::DevBuf d_tile_cn, d_tile_off, d_tile_net, d_events, d_depth, d_sum, d_nz;
+    csv::DevBuf d_events;    // uint32 depth-map indices, sign = slot parity
+    csv::DevBuf d_ev_start, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
+    csv::DevBuf d_depth, d_sum, d_nz, d_tile_desc, d_tile_ev, d_tile_sum, d_tile_nz;
     // signatures
     csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_qpos, d_sig_kind, d_sig_payload;
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
 
     void release(csv::DevPool* pool = nullptr) {
         csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_ne_idx, &d_headbits, &d_scalars,
-                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_tile_cn, &d_tile_off,
-                              &d_tile_net, &d_events, &d_depth, &d_sum, &d_nz, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
+                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status,
+                              &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
         for (auto* b : all) b->release(pool);
@@ -58,8 +60,8 @@ struct csv_batch {
 namespace csv {
 // kernels' host launchers (each enqueues on ctx->stream and bumps ctx->launches)
 int launch_prep(csv_ctx* ctx, csv_batch* b);
-int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int mode);
-int launch_tile_scan(csv_ctx* ctx, csv_batch* b);
+int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p);
+int launch_tile_ranges(csv_ctx* ctx, csv_batch* b);
 int launch_depth_tiles(csv_ctx* ctx, csv_batch* b);
 int launch_sig_finish(csv_ctx* ctx, csv_batch* b);
 int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts);

@@ -66,9 +66,9 @@ static int read_scalars(csv_ctx* ctx, csv_batch* b, uint32_t* out /* SC_COUNT */
 static int check_overflow(csv_ctx* ctx, csv_batch* b, uint32_t* sc)
 {
     CSV_TRY(read_scalars(ctx, b, sc));
-    if (b->have_depth && sc[SC_EV_TOTAL] > b->ev_cap) {
-        set_error("depth: %u difference events exceed the batch capacity %llu (regions split too finely)", sc[SC_EV_TOTAL], (unsigned long long)b->ev_cap);
-        return CSV_ERR_LIMIT;
+    if (b->have_depth && sc[SC_UNSORTED]) {
+        set_error("records are not sorted by (contig, position): the depth path needs coordinate-sorted input, like the indexed BAM the reference requires");
+        return CSV_ERR_ARG;
     }
     if (b->have_sigs && sc[SC_N_SIG] > b->sig_cap) {
         set_error("signatures: %u emitted, batch capacity is %llu", sc[SC_N_SIG], (unsigned long long)b->sig_cap);
@@ -164,7 +164,7 @@ int csv_profile_enable(csv_ctx* ctx, int on)
 
 int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, double* ms_out, uint32_t* calls_out, int reset)
 {
-    static const char* kNames[ST_COUNT] = {"prep", "walk_count", "tile_scan", "walk_scatter", "depth_tiles", "sig_sort", "dbscan1d"};
+    static const char* kNames[ST_COUNT] = {"prep", "walk", "tile_ranges", "depth_tiles", "sig_sort", "dbscan1d"};
     if (!ctx) { set_error("null context"); return -CSV_ERR_ARG; }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("csv_profile_read: stream synchronisation failed"); return -CSV_ERR_CUDA; }
     for (int s = 0; s < ST_COUNT; s++) {
@@ -202,6 +202,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     for (uint32_t i = 0; i < n_regions; i++) {
         const csv_region& g = regions[i];
         if (g.tid < 0 || g.beg >= g.end || g.end > g.map_size) { set_error("region %u: need tid >= 0 and beg < end <= map_size", i); return CSV_ERR_ARG; }
+        if (g.map_size > 0x80000000u) { set_error("region %u: map_size beyond 2^31 (BAM positions are int32)", i); return CSV_ERR_LIMIT; }
         max_tid = std::max(max_tid, g.tid);
     }
     if (max_tid >= (1 << 24)) { set_error("contig id %d too large", max_tid); return CSV_ERR_LIMIT; }
@@ -238,7 +239,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     for (uint32_t i = 0; i < n_regions; i++) reg_tab[n_regions + 1 + i] = regions[i].end - regions[i].beg;
 
     b->n_spans = (uint32_t)((r->n_ops + kWalkSpan - 1) / kWalkSpan);
-    b->ev_cap = std::min<uint64_t>(2 * (r->n_ops + r->n_reads) * (b->multi_region_tid ? 2 : 1) + 64, 0xfffffff0ull);
+    b->ev_cap = 2 * (r->n_ops + (uint64_t)r->n_reads) + 2;      // exact bound: 2 per record + 2 per D/N op
     b->sig_cap = std::max<uint64_t>(16, std::min<uint64_t>(r->n_ops, std::max<uint64_t>(1u << 20, r->n_ops / 16)));
 
     // ---- allocations
@@ -253,8 +254,11 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
     CSV_TRY(b->d_span_status.ensure((size_t)b->n_spans * 4 + 16, &ctx->pool));
     CSV_CUDA(cudaMemsetAsync(b->d_span_status.p, 0, b->d_span_status.cap, ctx->stream));
-    CSV_TRY(b->d_tile_cn.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_off.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_net.ensure(nt * 4 + 16, &ctx->pool));
-    CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 2, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
+    CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
+    CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
+    CSV_TRY(b->d_pmax.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_pmax_part.ensure((nr / 2048 + 2) * 8, &ctx->pool));
+    CSV_TRY(b->d_tile_desc.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_ev.ensure(nt * 8 + 16, &ctx->pool));
+    CSV_TRY(b->d_tile_sum.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_nz.ensure(nt * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_sum.ensure(n_regions * 8, &ctx->pool)); CSV_TRY(b->d_nz.ensure(n_regions * 4, &ctx->pool));
     CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));
     CSV_TRY(b->d_sig_qpos.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
@@ -278,6 +282,15 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_CUDA(cudaMemcpyAsync(b->d_regs.p, regs.data(), regs.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemcpyAsync(b->d_tids.p, tids.data(), tids.size() * sizeof(TidDev), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemcpyAsync(b->d_reg_tab.p, reg_tab.data(), reg_tab.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<uint4> tile_desc(nt);
+    for (uint32_t i = 0; i < n_regions; i++) {
+        const uint32_t len = regions[i].end - regions[i].beg;
+        for (uint32_t t = b->tile_base[i]; t < b->tile_base[i + 1]; t++) {
+            const uint32_t p0 = (t - b->tile_base[i]) * (uint32_t)kTile;
+            tile_desc[t] = make_uint4(i, len - p0 < (uint32_t)kTile ? len - p0 : (uint32_t)kTile, regions[i].beg + p0, (uint32_t)regions[i].tid);
+        }
+    }
+    if (nt) CSV_CUDA(cudaMemcpyAsync(b->d_tile_desc.p, tile_desc.data(), nt * sizeof(uint4), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaStreamSynchronize(st));
     *out = b.release();
     return CSV_OK;
@@ -298,16 +311,11 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     cudaStream_t st = ctx->stream;
     b->last_min_len = p->min_len;
     CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
-    if (p->want_depth) {
-        CSV_CUDA(cudaMemsetAsync(b->d_tile_cn.p, 0, (size_t)b->n_tiles * 8, st));
-        CSV_CUDA(cudaMemsetAsync(b->d_sum.p, 0, b->n_regions * 8, st));
-        CSV_CUDA(cudaMemsetAsync(b->d_nz.p, 0, b->n_regions * 4, st));
-    }
+    if (p->want_depth) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));
     { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b)); }
-    { StageTimer t(ctx, ST_WALK_COUNT); CSV_TRY(launch_walk(ctx, b, p, 0)); }
+    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p)); }
     if (p->want_depth) {
-        { StageTimer t(ctx, ST_TILE_SCAN); CSV_TRY(launch_tile_scan(ctx, b)); }
-        { StageTimer t(ctx, ST_WALK_SCATTER); CSV_TRY(launch_walk(ctx, b, p, 1)); }
+        { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b)); }
         { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b)); }
     }
     if (p->want_sigs) { StageTimer t(ctx, ST_SIG_SORT); CSV_TRY(launch_sig_finish(ctx, b)); }

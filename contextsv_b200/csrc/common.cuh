@@ -39,7 +39,6 @@ constexpr int kTileShift = 13;
 constexpr int kWalkThreads = 256;
 constexpr int kWalkOpsPerThread = 8;
 constexpr int kWalkSpan = kWalkThreads * kWalkOpsPerThread;   // CIGAR ops per span
-constexpr int kIvCap = 2048;                    // staged depth intervals per span window
 
 // BAM constants (SAM spec): which ops consume reference / query
 constexpr uint32_t kRefMask = (1u << 0) | (1u << 2) | (1u << 3) | (1u << 7) | (1u << 8);   // M D N = X
@@ -92,7 +91,7 @@ struct DevBuf {
 };
 
 // Per-stage device timing (CUDA events on the context's stream), for bench.py's roofline.
-enum Stage { ST_PREP = 0, ST_WALK_COUNT, ST_TILE_SCAN, ST_WALK_SCATTER, ST_DEPTH_TILES, ST_SIG_SORT, ST_DBSCAN, ST_COUNT };
+enum Stage { ST_PREP = 0, ST_WALK, ST_TILE_RANGES, ST_DEPTH_TILES, ST_SIG_SORT, ST_DBSCAN, ST_COUNT };
 
 // Region tables (device copies live in the batch)
 struct RegionDev {       // sorted by (tid, beg)
@@ -102,8 +101,9 @@ struct RegionDev {       // sorted by (tid, beg)
 };
 struct TidDev { uint32_t first, count, map_size, pad; };
 
-// Look-back scan state of the walk: (heads, ref, qry); segmented on heads > 0
-struct WalkAgg { uint32_t heads, ref, qry, pad; };
+// Look-back scan state of the walk: record heads and depth events are plain sums,
+// (ref, qry) consumption is segmented: it restarts at every record head.
+struct WalkAgg { uint32_t heads, ref, qry, ev; };
 
 }  // namespace csv
 

@@ -1,83 +1,224 @@
-// depth_tiles.cu -- per-base read depth from binned difference events
-// (cnv_caller.cpp:507-519 and the two reductions at :534-535).
+// depth_tiles.cu -- per-base read depth (cnv_caller.cpp:507-519) and the two
+// reductions that follow it (:534-535), from the walk's op-ordered event list.
 //
-// The depth map of every region is cut into tiles of kTile positions.  One CTA
-// owns one tile: it zeroes a kTile-int difference array in shared memory,
-// applies the tile's +-1 events with shared-memory atomics, prefix-sums it
-// (carry-in = net sign of all events in earlier tiles of the region) and
-// writes every depth word exactly once with 128-bit streaming stores, while
-// accumulating sum(depth) and count(depth > 0) for the region.
+// The depth map of every region is cut into tiles of kTile positions.
+//
+// launch_tile_ranges: records are coordinate-sorted, so the records that can
+//   touch a tile [T0,T1) of contig c are a contiguous run [r_lo, r_hi):
+//     r_hi = first record with (tid, pos0+1) >= (c, T1)
+//     r_lo = first record whose running maximum of (tid, ref_end) exceeds (c, T0)
+//   (a u64 prefix-max over records, then two binary searches per tile).  Their
+//   events are one contiguous slice of the event array.
+//
+// k_depth_tiles: one CTA owns one tile.  It zeroes a kTile-int difference array
+//   in shared memory and streams the slice: an event left of the tile adds its
+//   sign to the tile's carry-in (depth at T0), an event inside goes into the
+//   difference array with a shared-memory atomic, the rest is skipped.  Sign =
+//   parity of the event slot.  No inter-tile dependency, no global atomics.
+//   Then prefix sum + carry, every depth word is written exactly once with
+//   128-bit streaming stores, and sum(depth) / count(depth > 0) are reduced per
+//   tile and summed per region by k_region_stats.
 #include "batch.cuh"
 #include "scan.cuh"
 
 namespace csv {
 
-int launch_tile_scan(csv_ctx* ctx, csv_batch* b)
+// ------------------------------------------------------- prefix max over records
+constexpr int kPmThreads = 256, kPmItems = 8, kPmTile = kPmThreads * kPmItems;
+
+__device__ __forceinline__ unsigned long long pm_value(const uint4* meta, const uint32_t* ref_end, uint32_t k)
 {
-    const unsigned long long* cn = b->d_tile_cn.as<unsigned long long>();
-    uint32_t* off = b->d_tile_off.as<uint32_t>();
-    uint32_t* net = b->d_tile_net.as<uint32_t>();
-    // event slot bases: exclusive sum of the per-tile counts (low halves)
-    CSV_TRY(chained_scan(ctx,
-                         [=] __device__(uint64_t i) -> uint32_t { return (uint32_t)cn[i]; },
-                         [=] __device__(uint64_t i, uint32_t ex, uint32_t) { off[i] = ex; },
-                         b->n_tiles, nullptr, b->d_scalars.as<uint32_t>() + SC_EV_TOTAL));
-    // carry-in: exclusive sum of the per-tile net signs (high halves), modulo 2^32
-    CSV_TRY(chained_scan(ctx,
-                         [=] __device__(uint64_t i) -> uint32_t { return (uint32_t)(cn[i] >> 32); },
-                         [=] __device__(uint64_t i, uint32_t ex, uint32_t) { net[i] = ex; },
-                         b->n_tiles, nullptr, nullptr));
+    return ((unsigned long long)meta[k].y << 32) | ref_end[k];
+}
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+__global__ void __launch_bounds__(kPmThreads) k_pm_partials(const uint4* __restrict__ meta, const uint32_t* __restrict__ ref_end,
+                                                            const uint32_t* scalars, unsigned long long* part)
+{
+    __shared__ unsigned long long s[kPmThreads / 32];
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
+        unsigned long long v = 0;
+        for (int j = 0; j < kPmItems; j++) {
+            const uint64_t k = (uint64_t)t * kPmTile + j * kPmThreads + threadIdx.x;
+            if (k < n) v = umax64(v, pm_value(meta, ref_end, (uint32_t)k));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = umax64(v, __shfl_xor_sync(0xffffffffu, v, d));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long r = s[0];
+            for (int i = 1; i < kPmThreads / 32; i++) r = umax64(r, s[i]);
+            part[t] = r;
+        }
+    }
+}
+
+// single CTA: part[t] <- max of part[0..t-1] (exclusive), in place
+__global__ void __launch_bounds__(1024) k_pm_scan_partials(const uint32_t* scalars, unsigned long long* part)
+{
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    const uint32_t n_part = (uint32_t)(((uint64_t)n + kPmTile - 1) / kPmTile);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_part; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < n_part ? part[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc = umax64(inc, t); }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (uint32_t w = 0; w < warp; w++) pre = umax64(pre, s_w[w]);
+        unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        if (i < n_part) part[i] = umax64(pre, excl);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = umax64(pre, inc);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kPmThreads) k_pm_final(const uint4* __restrict__ meta, const uint32_t* __restrict__ ref_end,
+                                                         uint32_t* scalars, const unsigned long long* __restrict__ part,
+                                                         unsigned long long* pmax)
+{
+    __shared__ unsigned long long s_w[kPmThreads / 32];
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
+        // blocked arrangement: thread owns kPmItems consecutive records
+        const uint64_t k0 = (uint64_t)t * kPmTile + (uint64_t)threadIdx.x * kPmItems;
+        unsigned long long v[kPmItems], run = 0;
+#pragma unroll
+        for (int j = 0; j < kPmItems; j++) {
+            v[j] = (k0 + j < n) ? pm_value(meta, ref_end, (uint32_t)(k0 + j)) : 0ull;
+            // coordinate order check rides along: (tid, pos0 + 1) must not decrease
+            if (k0 + j < n && k0 + j > 0) {
+                const uint4 a = meta[k0 + j - 1], b = meta[k0 + j];
+                const unsigned long long ka = ((unsigned long long)a.y << 32) | (uint32_t)(a.x + 1u), kb = ((unsigned long long)b.y << 32) | (uint32_t)(b.x + 1u);
+                if (ka > kb) scalars[SC_UNSORTED] = 1;
+            }
+            run = umax64(run, v[j]);
+        }
+        unsigned long long inc = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc = umax64(inc, x); }
+        __syncthreads();
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = part[t];
+        for (uint32_t w = 0; w < warp; w++) pre = umax64(pre, s_w[w]);
+        unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        pre = umax64(pre, excl);
+#pragma unroll
+        for (int j = 0; j < kPmItems; j++) { pre = umax64(pre, v[j]); if (k0 + j < n) pmax[k0 + j] = pre; }
+    }
+}
+
+// ------------------------------------------------------------ tile -> event slice
+__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_tiles, const uint4* __restrict__ meta,
+                              const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
+                              const uint32_t* scalars, uint2* tile_ev)
+{
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        const uint4 d = tile_desc[t];            // {region, positions, T0, tid}
+        const unsigned long long key_hi = ((unsigned long long)d.w << 32) | (unsigned long long)(d.z + d.y);   // (tid, T1)
+        const unsigned long long key_lo = ((unsigned long long)d.w << 32) | (unsigned long long)d.z;           // (tid, T0)
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {                        // r_hi: first record with (tid, pos0 + 1) >= (tid, T1)
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint4 m = meta[mid];
+            const unsigned long long km = ((unsigned long long)m.y << 32) | (uint32_t)(m.x + 1u);
+            if (km < key_hi) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t r_hi = lo;
+        lo = 0; hi = r_hi;
+        while (lo < hi) {                        // r_lo: first record with running max (tid, ref_end) > (tid, T0)
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pmax[mid] <= key_lo) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t r_lo = lo;
+        tile_ev[t] = r_lo < r_hi ? make_uint2(ev_start[r_lo], ev_start[r_hi]) : make_uint2(0u, 0u);
+    }
+}
+
+int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
+{
+    if (b->n_tiles == 0) return CSV_OK;
+    const uint4* meta = b->d_meta.as<uint4>();
+    const uint32_t* ref_end = b->d_ref_end.as<uint32_t>();
+    uint32_t* scalars = b->d_scalars.as<uint32_t>();
+    unsigned long long* part = b->d_pmax_part.as<unsigned long long>();
+    unsigned long long* pmax = b->d_pmax.as<unsigned long long>();
+    const uint32_t n_part = (uint32_t)(((uint64_t)b->n_reads + kPmTile - 1) / kPmTile);
+    if (n_part) {
+        const uint32_t grid = n_part < (uint32_t)ctx->sm_count * 8 ? n_part : (uint32_t)ctx->sm_count * 8;
+        k_pm_partials<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, part);
+        k_pm_scan_partials<<<1, 1024, 0, ctx->stream>>>(scalars, part);
+        k_pm_final<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, part, pmax);
+        ctx->launches += 3;
+    }
+    const uint32_t grid_t = (b->n_tiles + 255) / 256;
+    k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), b->n_tiles, meta, pmax, b->d_ev_start.as<uint32_t>(),
+                                                  scalars, b->d_tile_ev.as<uint2>());
+    ctx->launches++;
+    CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
 
+// --------------------------------------------------------------------- tile kernel
 constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kWarpChunk = kTile / kTileWarps;     // positions per warp
 constexpr int kRows = kWarpChunk / 128;            // 128 positions (one int4 per lane) per row
 
 struct TileParams {
-    const uint32_t* reg_tile_base;   // caller order, n_regions + 1
-    const uint32_t* reg_len;         // caller order: end - beg
-    uint32_t n_regions;
-    const uint32_t* tile_end;        // after the scatter walk: end of each tile's event run
-    const uint32_t* tile_net;
-    const uint16_t* events;
+    const uint4* tile_desc;          // static per tile: {region, positions in tile, T0, tid}
+    const uint2* tile_ev;            // event slice [x, y)
+    const uint32_t* events;
     uint32_t ev_cap;
     uint32_t* depth;                 // n_tiles * kTile words
-    unsigned long long* reg_sum;
-    uint32_t* reg_nz;
+    unsigned long long* tile_sum;    // per-tile partial reductions (no contended atomics)
+    uint32_t* tile_nz;
     uint32_t n_tiles;
 };
 
-__global__ void __launch_bounds__(kTileThreads) k_depth_tiles(const TileParams P)
+__global__ void __launch_bounds__(kTileThreads, 6) k_depth_tiles(const TileParams P)
 {
     __shared__ __align__(16) int s_diff[kTile];
     __shared__ int s_wtot[kTileWarps];
-    __shared__ uint32_t s_reg;
+    __shared__ int s_wcarry[kTileWarps];
+    __shared__ unsigned long long s_wsum[kTileWarps];
+    __shared__ uint32_t s_wnz[kTileWarps];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        // region of this tile: last r with reg_tile_base[r] <= t
-        if (tid == 0) {
-            uint32_t lo = 0, hi = P.n_regions;
-            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (P.reg_tile_base[mid] <= t) lo = mid; else hi = mid; }
-            s_reg = lo;
-        }
+        const uint4 desc = __ldg(P.tile_desc + t);
+        const uint2 er = __ldg(P.tile_ev + t);
+        const uint32_t n_here = desc.y, T0 = desc.z, T1 = desc.z + desc.y;
+        const uint32_t e1 = er.y < P.ev_cap ? er.y : P.ev_cap;
         int4* z = reinterpret_cast<int4*>(s_diff);
 #pragma unroll
         for (int i = 0; i < kTile / 4 / kTileThreads; i++) z[tid + i * kTileThreads] = make_int4(0, 0, 0, 0);
         __syncthreads();
-        const uint32_t r = s_reg;
-        const uint32_t tb = P.reg_tile_base[r];
-        const uint32_t p0 = (t - tb) << kTileShift;                  // first position of the tile inside the region
-        const uint32_t reg_len = P.reg_len[r];
-        const uint32_t n_here = reg_len - p0 < (uint32_t)kTile ? reg_len - p0 : (uint32_t)kTile;
-        uint32_t e0 = t ? P.tile_end[t - 1] : 0u, e1 = P.tile_end[t];
-        if (e1 > P.ev_cap) e1 = P.ev_cap;
-        for (uint32_t e = e0 + tid; e < e1; e += kTileThreads) {
-            const uint32_t ev = P.events[e];
-            atomicAdd(&s_diff[ev & 0x7fffu], (ev & 0x8000u) ? -1 : 1);
+        int mycarry = 0;
+        for (uint32_t e = er.x + tid; e < e1; e += kTileThreads) {
+            const uint32_t p = __ldg(P.events + e);
+            const int sgn = (e & 1u) ? -1 : 1;
+            if (p < T0) mycarry += sgn;
+            else if (p < T1) atomicAdd(&s_diff[p - T0], sgn);
         }
+        mycarry = (int)warp_sum_u32((uint32_t)mycarry);
+        if (lane == 0) s_wcarry[warp] = mycarry;
         __syncthreads();
         // pass A: per-warp totals
         const int4* row = reinterpret_cast<const int4*>(s_diff + warp * kWarpChunk);
@@ -87,7 +228,9 @@ __global__ void __launch_bounds__(kTileThreads) k_depth_tiles(const TileParams P
         tot = (int)warp_sum_u32((uint32_t)tot);
         if (lane == 0) s_wtot[warp] = tot;
         __syncthreads();
-        int carry = (int)(P.tile_net[t] - P.tile_net[tb]);
+        int carry = 0;
+#pragma unroll
+        for (int i = 0; i < kTileWarps; i++) carry += s_wcarry[i];
         for (uint32_t i = 0; i < warp; i++) carry += s_wtot[i];
         // pass B: scan rows, write, reduce
         unsigned long long sum = 0; uint32_t nz = 0;
@@ -115,29 +258,52 @@ __global__ void __launch_bounds__(kTileThreads) k_depth_tiles(const TileParams P
             }
         }
         sum = warp_sum_u64(sum); nz = warp_sum_u32(nz);
-        if (lane == 0 && (sum | nz)) { atomicAdd(&P.reg_sum[r], sum); atomicAdd(&P.reg_nz[r], nz); }
+        if (lane == 0) { s_wsum[warp] = sum; s_wnz[warp] = nz; }
         __syncthreads();
+        if (tid == 0) {
+            unsigned long long ts = 0; uint32_t tn = 0;
+#pragma unroll
+            for (int i = 0; i < kTileWarps; i++) { ts += s_wsum[i]; tn += s_wnz[i]; }
+            P.tile_sum[t] = ts; P.tile_nz[t] = tn;
+        }
+    }
+}
+
+// one CTA per region: sum the per-tile partials (cnv_caller.cpp:534-535)
+__global__ void __launch_bounds__(256) k_region_stats(const uint32_t* __restrict__ reg_tile_base, const unsigned long long* __restrict__ tile_sum,
+                                                       const uint32_t* __restrict__ tile_nz, unsigned long long* reg_sum, uint32_t* reg_nz)
+{
+    __shared__ unsigned long long s_s[8];
+    __shared__ uint32_t s_n[8];
+    const uint32_t r = blockIdx.x, t0 = reg_tile_base[r], t1 = reg_tile_base[r + 1];
+    unsigned long long s = 0; uint32_t n = 0;
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) { s += tile_sum[t]; n += tile_nz[t]; }
+    s = warp_sum_u64(s); n = warp_sum_u32(n);
+    if ((threadIdx.x & 31) == 0) { s_s[threadIdx.x >> 5] = s; s_n[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { s += s_s[i]; n += s_n[i]; }
+        reg_sum[r] = s; reg_nz[r] = n;
     }
 }
 
 int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
 {
     TileParams P;
-    P.reg_tile_base = b->d_reg_tab.as<uint32_t>();
-    P.reg_len = b->d_reg_tab.as<uint32_t>() + b->n_regions + 1;
-    P.n_regions = b->n_regions;
-    P.tile_end = b->d_tile_off.as<uint32_t>();
-    P.tile_net = b->d_tile_net.as<uint32_t>();
-    P.events = b->d_events.as<uint16_t>();
+    P.tile_desc = b->d_tile_desc.as<uint4>();
+    P.tile_ev = b->d_tile_ev.as<uint2>();
+    P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.depth = b->d_depth.as<uint32_t>();
-    P.reg_sum = b->d_sum.as<unsigned long long>();
-    P.reg_nz = b->d_nz.as<uint32_t>();
+    P.tile_sum = b->d_tile_sum.as<unsigned long long>();
+    P.tile_nz = b->d_tile_nz.as<uint32_t>();
     P.n_tiles = b->n_tiles;
     if (b->n_tiles == 0) return CSV_OK;
-    uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 24 ? b->n_tiles : (uint32_t)ctx->sm_count * 24;
+    uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 28 ? b->n_tiles : (uint32_t)ctx->sm_count * 28;
     k_depth_tiles<<<grid, kTileThreads, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    k_region_stats<<<b->n_regions, 256, 0, ctx->stream>>>(b->d_reg_tab.as<uint32_t>(), P.tile_sum, P.tile_nz,
+                                                          b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());
+    ctx->launches += 2;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }

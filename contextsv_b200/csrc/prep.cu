@@ -49,9 +49,10 @@ int launch_prep(csv_ctx* ctx, csv_batch* b)
         int32_t t = tid ? tid[i] : 0;
         uint4 m;
         m.x = (uint32_t)pos0[i];
+        m.y = (uint32_t)t;                                   // raw contig id: (tid, pos0 + 1) is the sort key of the batch
         m.z = (uint32_t)flag[i] | ((uint32_t)mapq[i] << 16);
-        if (t < 0 || (uint32_t)t >= n_tids || tids[t].count == 0) { m.y = kNone; m.w = kNone; }
-        else { m.y = (uint32_t)t; m.w = find_owner(tids[t], regs, m.x + 1u); }
+        if (t < 0 || (uint32_t)t >= n_tids || tids[t].count == 0) { m.z |= 0x80000000u; m.w = kNone; }   // contig not requested
+        else m.w = find_owner(tids[t], regs, m.x + 1u);
         meta[k] = m;
         ne_idx[k] = (uint32_t)i;
     };

@@ -8,17 +8,19 @@
 //      say where records start;
 //   2. a segmented scan (reset at record heads) of (reference, query)
 //      consumption runs thread -> warp -> CTA -> chained look-back across spans;
-//      a plain sum of head bits rides along and yields the record index;
-//   3. every op now knows its reference position and query offset:
-//        - I/D/S ops >= min_len become signatures (mode COUNT only);
-//        - D/N ops and record ends become depth intervals: coverage of a record
-//          is +1 over its reference span and -1 over every D/N gap, which is
-//          exactly the set of bases its M/=/X ops touch;
-//   4. the intervals are staged in shared memory, clipped against the regions
-//      of their contig and turned into (tile, offset, sign) difference events.
-//      Mode COUNT only counts events per tile (one 64-bit atomic per warp and
-//      tile: low half count, high half net sign); mode SCATTER, run after the
-//      per-tile offsets are known, writes the 16-bit events into per-tile bins.
+//      plain sums of head bits (-> record index) and of depth-event counts
+//      (-> event slot) ride along;
+//   3. every op now knows its reference position, query offset and event slot:
+//        - I/D/S ops >= min_len become signatures;
+//        - depth events are written in op order: a record contributes +1 at its
+//          first index, -1/+1 around every D/N gap, -1 one past its last base --
+//          exactly the bases its M/=/X ops cover (cnv_caller.cpp:507-519).
+//          Every record writes an EVEN number of events that alternate +,-,+,-...
+//          so the sign of an event is the parity of its slot: the event list is
+//          a plain array of uint32 depth-map indices (kNone = clipped/filtered),
+//          grouped by record, hence sorted by contig and (nearly) by position.
+// Per record the walk also leaves ev_start[k] (first event slot) and
+// ref_end[k] (one past the last covered index, 0 if filtered) for the tile kernel.
 #include "batch.cuh"
 #include "scan.cuh"
 
@@ -30,17 +32,16 @@ struct WalkParams {
     const uint8_t* headbits;
     const uint4* meta;
     const TidDev* tids;
-    const RegionDev* regs;
     WalkAgg* span_agg;
     WalkAgg* span_pre;
     uint32_t* span_status;
     uint32_t* ticket;
     uint32_t epoch;
     uint32_t n_spans;
-    unsigned long long* tile_cn;
-    uint32_t* tile_off;
-    uint16_t* events;
+    uint32_t* events;
     uint32_t ev_cap;
+    uint32_t* ev_start;     // [n_nonempty + 1]
+    uint32_t* ref_end;      // [n_nonempty]
     uint32_t min_len, min_mapq;
     uint32_t* scalars;
     SigRaw sig;
@@ -55,7 +56,7 @@ __device__ __forceinline__ WalkAgg combine(const WalkAgg a, const WalkAgg b)
     r.heads = a.heads + b.heads;
     r.ref = b.heads ? b.ref : a.ref + b.ref;
     r.qry = b.heads ? b.qry : a.qry + b.qry;
-    r.pad = 0;
+    r.ev = a.ev + b.ev;
     return r;
 }
 
@@ -65,14 +66,13 @@ __device__ __forceinline__ WalkAgg shfl_agg(const WalkAgg v, int src)
     r.heads = __shfl_sync(0xffffffffu, v.heads, src);
     r.ref = __shfl_sync(0xffffffffu, v.ref, src);
     r.qry = __shfl_sync(0xffffffffu, v.qry, src);
-    r.pad = 0;
+    r.ev = __shfl_sync(0xffffffffu, v.ev, src);
     return r;
 }
 
-// Chained look-back over spans for the 3-word segmented state.  Payloads live
-// in span_agg / span_pre; span_status carries (epoch << 2 | flag) and is
-// published after a __threadfence().  Called by warp 0; returns the exclusive
-// state of span s on every lane.
+// Chained look-back over spans for the 4-word state.  Payloads live in span_agg /
+// span_pre; span_status carries (epoch << 2 | flag) and is published after a
+// __threadfence().  Called by warp 0; returns the exclusive state of span s.
 __device__ __forceinline__ WalkAgg walk_lookback(const WalkParams& P, uint32_t s, const WalkAgg total)
 {
     const uint32_t lane = lane_id();
@@ -97,7 +97,6 @@ __device__ __forceinline__ WalkAgg walk_lookback(const WalkParams& P, uint32_t s
         if (idx >= 0) v = (flag == kFlagPrefix) ? P.span_pre[idx] : P.span_agg[idx];
         uint32_t pm = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
         int last = pm ? (__ffs(pm) - 1) : 31;     // farthest lane that contributes
-        // fold near -> far: acc = v[last] (+) ... (+) v[0] (+) previous excl
         WalkAgg acc = shfl_agg(v, last);
         for (int i = last - 1; i >= 0; i--) acc = combine(acc, shfl_agg(v, i));
         excl = have ? combine(acc, excl) : acc;
@@ -109,14 +108,11 @@ __device__ __forceinline__ WalkAgg walk_lookback(const WalkParams& P, uint32_t s
     return excl;
 }
 
-template <int MODE>   // 0 = COUNT (+ signatures, publishes span prefixes), 1 = SCATTER
 __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
 {
     __shared__ WalkAgg s_warp[kWalkThreads / 32];
     __shared__ WalkAgg s_excl;
-    __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_span;
-    __shared__ uint32_t iv_a[kIvCap], iv_b[kIvCap], iv_m[kIvCap];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
@@ -140,9 +136,8 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
         if (g0 < P.n_ops) hb = (uint32_t)P.headbits[g0 >> 3] | ((uint32_t)P.headbits[(g0 >> 3) + 1] << 8);
         const uint32_t n_valid = g0 >= P.n_ops ? 0u : (P.n_ops - g0 < kWalkOpsPerThread ? P.n_ops - g0 : kWalkOpsPerThread);
 
-        // ---- 2a. thread aggregate + upper bound of staged intervals
+        // ---- 2a. thread aggregate
         WalkAgg a = {0, 0, 0, 0};
-        uint32_t ivcnt = 0;
 #pragma unroll
         for (int j = 0; j < kWalkOpsPerThread; j++) {
             if ((uint32_t)j < n_valid) {
@@ -150,8 +145,7 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
                 if ((hb >> j) & 1u) { a.heads++; a.ref = 0; a.qry = 0; }
                 a.ref += ((kRefMask >> op) & 1u) ? len : 0u;
                 a.qry += ((kQryMask >> op) & 1u) ? len : 0u;
-                ivcnt += (((kGapMask >> op) & 1u) && len) ? 1u : 0u;
-                ivcnt += (hb >> (j + 1)) & 1u;
+                a.ev += ((hb >> j) & 1u) + ((hb >> (j + 1)) & 1u) + ((((kGapMask >> op) & 1u) && len) ? 2u : 0u);
             }
         }
         // ---- 2b. warp segmented inclusive scan
@@ -162,14 +156,14 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
             t.heads = __shfl_up_sync(0xffffffffu, inc.heads, d);
             t.ref = __shfl_up_sync(0xffffffffu, inc.ref, d);
             t.qry = __shfl_up_sync(0xffffffffu, inc.qry, d);
-            t.pad = 0;
+            t.ev = __shfl_up_sync(0xffffffffu, inc.ev, d);
             if (lane >= (uint32_t)d) inc = combine(t, inc);
         }
         WalkAgg lane_excl;
         lane_excl.heads = __shfl_up_sync(0xffffffffu, inc.heads, 1);
         lane_excl.ref = __shfl_up_sync(0xffffffffu, inc.ref, 1);
         lane_excl.qry = __shfl_up_sync(0xffffffffu, inc.qry, 1);
-        lane_excl.pad = 0;
+        lane_excl.ev = __shfl_up_sync(0xffffffffu, inc.ev, 1);
         if (lane == 0) lane_excl = WalkAgg{0, 0, 0, 0};
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
@@ -177,149 +171,87 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
         WalkAgg wpre = {0, 0, 0, 0};
         for (uint32_t i = 0; i < warp; i++) wpre = combine(wpre, s_warp[i]);
         if (warp == 0) {
-            WalkAgg ex;
-            if (MODE == 0) {
-                WalkAgg total = s_warp[0];
+            WalkAgg total = s_warp[0];
 #pragma unroll
-                for (int i = 1; i < kWalkThreads / 32; i++) total = combine(total, s_warp[i]);
-                ex = walk_lookback(P, span, total);
-            } else {
-                ex = span ? P.span_pre[span - 1] : WalkAgg{0, 0, 0, 0};
-            }
+            for (int i = 1; i < kWalkThreads / 32; i++) total = combine(total, s_warp[i]);
+            const WalkAgg ex = walk_lookback(P, span, total);
             if (lane == 0) s_excl = ex;
         }
-        uint32_t iv_total;
-        const uint32_t iv_excl = P.want_depth ? block_excl_scan_u32(ivcnt, s_scan, &iv_total) : 0u;
-        if (!P.want_depth) { iv_total = 0; __syncthreads(); }
+        __syncthreads();
         const WalkAgg T = combine(s_excl, combine(wpre, lane_excl));
 
-        // ---- 3/4. replay with full prefixes; windows of kIvCap staged intervals
-        for (uint32_t wbase = 0; wbase == 0 || wbase < iv_total; wbase += kIvCap) {
-            uint32_t Hc = T.heads, Rc = T.ref, Qc = T.qry, slot = iv_excl;
-            uint32_t kcur = kNone;
-            uint4 m = make_uint4(0, kNone, 0, kNone);
-            TidDev td = {0, 0, 0, 0};
+        // ---- 3. replay with full prefixes
+        uint32_t Hc = T.heads, Rc = T.ref, Qc = T.qry, slot = T.ev;
+        uint32_t kcur = kNone;
+        uint4 m = make_uint4(0, 0, 0x80000000u, kNone);
+        uint32_t map_size = 0;
+        bool dok = false, sok = false;
 #pragma unroll
-            for (int j = 0; j < kWalkOpsPerThread; j++) {
-                if ((uint32_t)j >= n_valid) break;
-                const uint32_t op = w[j] & 15u, len = w[j] >> 4;
-                if ((hb >> j) & 1u) { Hc++; Rc = 0; Qc = 0; }
-                const uint32_t k = Hc - 1u;
-                if (k != kcur) {
-                    kcur = k; m = __ldg(P.meta + k);
-                    if (m.y != kNone) td = P.tids[m.y];
-                }
-                const bool ignored = (m.y == kNone);
-                const uint32_t rl = ((kRefMask >> op) & 1u) ? len : 0u;
-                const uint32_t pos = m.x + Rc;   // 0-based position at this op, uint32 like the reference's `pos`
+        for (int j = 0; j < kWalkOpsPerThread; j++) {
+            if ((uint32_t)j >= n_valid) break;
+            const uint32_t op = w[j] & 15u, len = w[j] >> 4;
+            const bool head = (hb >> j) & 1u, tail = (hb >> (j + 1)) & 1u;
+            if (head) { Hc++; Rc = 0; Qc = 0; }
+            const uint32_t k = Hc - 1u;
+            if (k != kcur) {
+                kcur = k; m = __ldg(P.meta + k);
+                const bool ignored = m.z >> 31;
+                map_size = ignored ? 0u : P.tids[m.y].map_size;
+                const uint32_t flags = m.z & 0xffffu, mq = (m.z >> 16) & 0xffu;
+                dok = !ignored && !(flags & kDepthSkipFlags);
+                sok = !ignored && !(flags & kSigSkipFlags) && mq >= P.min_mapq && m.w != kNone;
+            }
+            const uint32_t rl = ((kRefMask >> op) & 1u) ? len : 0u;
+            const uint32_t pos = m.x + Rc;   // 0-based position at this op, uint32 like the reference's `pos`
 
-                if (MODE == 0 && wbase == 0 && P.want_sigs && !ignored && len >= P.min_len && ((kSigMask >> op) & 1u)) {
-                    const uint32_t flags = m.z & 0xffffu, mq = m.z >> 16;
-                    const bool ok = !(flags & kSigSkipFlags) && mq >= P.min_mapq && m.w != kNone;
-                    const bool beyond = (pos + 1u) >= td.map_size;
-                    if (ok && !(op == 4 && beyond)) {                               // sv_caller.cpp:602-604
-                        const uint32_t start = pos + 1u, end = start + len - 1u;
-                        if (start <= end) {                                         // sv_object.cpp:25-28
-                            const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
-                            if (sl < P.sig_cap) {
-                                P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
-                                P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
-                                P.sig.k[sl] = k;
-                                P.sig.qpos[sl] = Qc;
-                                const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
-                                P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
-                                atomicAdd(&P.reg_sig_cnt[m.w], 1u);
-                            }
+            if (P.want_sigs && sok && len >= P.min_len && ((kSigMask >> op) & 1u)) {
+                const bool beyond = (pos + 1u) >= map_size;
+                if (!(op == 4 && beyond)) {                                     // sv_caller.cpp:602-604
+                    const uint32_t start = pos + 1u, end = start + len - 1u;
+                    if (start <= end) {                                         // sv_object.cpp:25-28
+                        const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
+                        if (sl < P.sig_cap) {
+                            P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
+                            P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
+                            P.sig.k[sl] = k;
+                            P.sig.qpos[sl] = Qc;
+                            const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
+                            P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
+                            atomicAdd(&P.reg_sig_cnt[m.w], 1u);
                         }
                     }
-                }
-                if (P.want_depth) {
-                    const bool dok = !ignored && !((m.z & 0xffffu) & kDepthSkipFlags);
-                    if (((kGapMask >> op) & 1u) && len) {
-                        const uint32_t sidx = slot++ - wbase;
-                        if (sidx < (uint32_t)kIvCap) {
-                            unsigned long long ia = (unsigned long long)(uint32_t)(pos + 1u), ib = ia + len;
-                            if (ib > td.map_size) ib = td.map_size;
-                            const bool valid = dok && ia < ib;
-                            iv_a[sidx] = (uint32_t)ia; iv_b[sidx] = (uint32_t)ib;
-                            iv_m[sidx] = valid ? (m.y | 0x80000000u) : kNone;       // gap: weight -1
-                        }
-                    }
-                    if ((hb >> (j + 1)) & 1u) {                                     // last op of the record
-                        const uint32_t sidx = slot++ - wbase;
-                        if (sidx < (uint32_t)kIvCap) {
-                            unsigned long long ia = (unsigned long long)(uint32_t)(m.x + 1u), ib = ia + (unsigned long long)Rc + rl;
-                            if (ib > td.map_size) ib = td.map_size;
-                            const bool valid = dok && ia < ib;
-                            iv_a[sidx] = (uint32_t)ia; iv_b[sidx] = (uint32_t)ib;
-                            iv_m[sidx] = valid ? m.y : kNone;                       // record span: weight +1
-                        }
-                    }
-                }
-                Rc += rl;
-                Qc += ((kQryMask >> op) & 1u) ? len : 0u;
-            }
-            if (!P.want_depth) break;
-            __syncthreads();
-            // ---- drain the staged window: intervals -> tile events
-            const uint32_t cnt = iv_total - wbase < (uint32_t)kIvCap ? iv_total - wbase : (uint32_t)kIvCap;
-            for (uint32_t i0 = warp * 32; i0 < cnt; i0 += kWalkThreads) {
-                const uint32_t i = i0 + lane;
-                uint32_t mm = i < cnt ? iv_m[i] : kNone;
-                const bool valid = mm != kNone;
-                const uint32_t ia = valid ? iv_a[i] : 0u, ib = valid ? iv_b[i] : 0u;
-                const bool neg = valid && (mm >> 31);
-                uint32_t r = 0, rend = 0;
-                if (valid) {
-                    const TidDev t2 = P.tids[mm & 0x7fffffffu];
-                    r = t2.first; rend = t2.first + t2.count;
-                    while (r < rend && P.regs[r].end <= ia) r++;
-                }
-                for (;;) {
-                    RegionDev rg = {0, 0, 0, 0};
-                    bool has = false;
-                    if (r < rend) { rg = P.regs[r]; has = rg.beg < ib; }
-                    if (!__any_sync(0xffffffffu, has)) break;
-                    // clipped interval [x0, x1) inside region rg
-                    const uint32_t x0 = ia > rg.beg ? ia : rg.beg;
-                    const uint32_t x1 = ib < rg.end ? ib : rg.end;
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        // e == 0: +w at x0 ; e == 1: -w at x1 (dropped when x1 is the region end)
-                        const bool ev = has && (e == 0 || x1 < rg.end);
-                        const uint32_t x = (e == 0 ? x0 : x1) - rg.beg;
-                        const uint32_t tile = rg.tile_base + (x >> kTileShift);
-                        const bool minus = (e == 0) ? neg : !neg;
-                        const uint32_t active = __ballot_sync(0xffffffffu, ev);
-                        if (ev) {
-                            const uint32_t peers = __match_any_sync(active, tile);
-                            const uint32_t leader = __ffs(peers) - 1;
-                            const uint32_t n = __popc(peers);
-                            if (MODE == 0) {
-                                const uint32_t minus_mask = __ballot_sync(active, minus);
-                                const int nneg = __popc(peers & minus_mask);
-                                if (lane == leader) {
-                                    const long long net = (long long)((int)n - 2 * nneg);
-                                    atomicAdd(&P.tile_cn[tile], (unsigned long long)(net * 4294967296ll + (long long)n));
-                                }
-                            } else {
-                                uint32_t base = 0;
-                                if (lane == leader) base = atomicAdd(&P.tile_off[tile], n);
-                                base = __shfl_sync(peers, base, leader);
-                                const uint32_t sl = base + __popc(peers & lanemask_lt());
-                                if (sl < P.ev_cap) P.events[sl] = (uint16_t)((x & (kTile - 1)) | (minus ? 0x8000u : 0u));
-                            }
-                        }
-                    }
-                    if (has) r++;
                 }
             }
-            __syncthreads();
+            if (P.want_depth) {
+                const uint32_t a0 = m.x + 1u;                                   // (uint32)pos + 1, cnv_caller.cpp:499
+                const bool live = dok && a0 < map_size;
+                if (head) {
+                    if (slot < P.ev_cap) P.events[slot] = live ? a0 : kNone;
+                    slot++;
+                }
+                if (((kGapMask >> op) & 1u) && len) {
+                    const unsigned long long ia = (unsigned long long)(uint32_t)(pos + 1u), ib = ia + len;
+                    if (slot + 1 < P.ev_cap) {
+                        P.events[slot] = (live && ia < map_size) ? (uint32_t)ia : kNone;
+                        P.events[slot + 1] = (live && ib < map_size) ? (uint32_t)ib : kNone;
+                    }
+                    slot += 2;
+                }
+                if (tail) {
+                    const unsigned long long ie = (unsigned long long)a0 + Rc + rl;
+                    if (slot < P.ev_cap) P.events[slot] = (live && ie < map_size) ? (uint32_t)ie : kNone;
+                    slot++;
+                    P.ev_start[k + 1] = slot;
+                    P.ref_end[k] = live ? (uint32_t)(ie < map_size ? ie : map_size) : 0u;
+                }
+            }
+            Rc += rl;
+            Qc += ((kQryMask >> op) & 1u) ? len : 0u;
         }
     }
 }
 
-int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int mode)
+int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
 {
     if (b->n_ops == 0) return CSV_OK;
     WalkParams P;
@@ -328,17 +260,16 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int mode)
     P.headbits = b->d_headbits.as<uint8_t>();
     P.meta = b->d_meta.as<uint4>();
     P.tids = b->d_tids.as<TidDev>();
-    P.regs = b->d_regs.as<RegionDev>();
     P.span_agg = b->d_span_agg.as<WalkAgg>();
     P.span_pre = b->d_span_pre.as<WalkAgg>();
     P.span_status = b->d_span_status.as<uint32_t>();
     CSV_TRY(next_ticket(ctx, &P.ticket));
-    if (mode == 0) P.epoch = next_epoch(ctx); else P.epoch = ctx->epoch;
+    P.epoch = next_epoch(ctx);
     P.n_spans = b->n_spans;
-    P.tile_cn = b->d_tile_cn.as<unsigned long long>();
-    P.tile_off = b->d_tile_off.as<uint32_t>();
-    P.events = b->d_events.as<uint16_t>();
+    P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
+    P.ev_start = b->d_ev_start.as<uint32_t>();
+    P.ref_end = b->d_ref_end.as<uint32_t>();
     P.min_len = p->min_len; P.min_mapq = p->min_mapq;
     P.scalars = b->d_scalars.as<uint32_t>();
     P.sig.key_hi = b->d_sig_hi.as<unsigned long long>();
@@ -350,8 +281,7 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int mode)
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
     P.want_depth = p->want_depth; P.want_sigs = p->want_sigs;
     uint32_t grid = b->n_spans < (uint32_t)ctx->sm_count * 4 ? b->n_spans : (uint32_t)ctx->sm_count * 4;
-    if (mode == 0) k_walk<0><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
-    else k_walk<1><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
+    k_walk<<<grid, kWalkThreads, 0, ctx->stream>>>(P);
     ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
