@@ -36,6 +36,8 @@ DB_EPS, DB_MIN_PTS = 100.0, 5        # the reference's own DBSCAN1D parameters (
 def workload_contigs(name):
     if name == "wgs30x":
         return [l for _, l in shard.GRCH38], 25000
+    if name == "chr1_5":
+        return [l for _, l in shard.GRCH38[:5]], 8500
     if name == "chr21":
         return [46709983], 400
     if name == "small":
@@ -45,6 +47,7 @@ def workload_contigs(name):
 
 def workload_name(name):
     return {"wgs30x": "synthetic whole-genome 30x HiFi GRCh38-shaped (24 contigs, 15 kb reads, 25k SVs) [BASELINE configs[1]]",
+            "chr1_5": "synthetic 30x HiFi chr1-chr5 (1.06 Gb; profiling workload)",
             "chr21": "synthetic 30x HiFi chr21 [BASELINE configs[0]]",
             "small": "synthetic 30x HiFi, 2 contigs of 5+3 Mb (debug)"}[name]
 
@@ -373,7 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr21", "small"])
+    ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr1_5", "chr21", "small"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--seed", type=int, default=20261018 + 2)
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -31,7 +31,8 @@ struct csv_batch {
     // input SoA (device)
     csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar;
     // derived per-read tables
-    csv::DevBuf d_meta;      // uint4 {pos0, tid, flag | mapq << 16 | ignored << 31, owner region | kNone} per non-empty read
+    csv::DevBuf d_meta;      // uint4 {pos0, map_size | 0 (contig not requested), flag | mapq << 16, owner region | kNone} per non-empty read
+    csv::DevBuf d_key;       // u64 (tid << 32 | pos0 + 1) per non-empty read: the batch's sort key
     csv::DevBuf d_ne_idx;    // compact index -> record index
     csv::DevBuf d_headbits;  // one bit per op: op is the first of its record (+ sentinel bit at n_ops)
     csv::DevBuf d_scalars;   // SC_* counters
@@ -48,7 +49,7 @@ struct csv_batch {
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
 
     void release(csv::DevPool* pool = nullptr) {
-        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_ne_idx, &d_headbits, &d_scalars,
+        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
                               &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status,
                               &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,

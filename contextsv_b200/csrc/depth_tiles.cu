@@ -26,13 +26,13 @@ namespace csv {
 // ------------------------------------------------------- prefix max over records
 constexpr int kPmThreads = 256, kPmItems = 8, kPmTile = kPmThreads * kPmItems;
 
-__device__ __forceinline__ unsigned long long pm_value(const uint4* meta, const uint32_t* ref_end, uint32_t k)
+__device__ __forceinline__ unsigned long long pm_value(const unsigned long long* key, const uint32_t* ref_end, uint32_t k)
 {
-    return ((unsigned long long)meta[k].y << 32) | ref_end[k];
+    return (key[k] & 0xffffffff00000000ull) | ref_end[k];
 }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-__global__ void __launch_bounds__(kPmThreads) k_pm_partials(const uint4* __restrict__ meta, const uint32_t* __restrict__ ref_end,
+__global__ void __launch_bounds__(kPmThreads) k_pm_partials(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
                                                             const uint32_t* scalars, unsigned long long* part)
 {
     __shared__ unsigned long long s[kPmThreads / 32];
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024) k_pm_scan_partials(const uint32_t* scala
     }
 }
 
-__global__ void __launch_bounds__(kPmThreads) k_pm_final(const uint4* __restrict__ meta, const uint32_t* __restrict__ ref_end,
+__global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
                                                          uint32_t* scalars, const unsigned long long* __restrict__ part,
                                                          unsigned long long* pmax)
 {
@@ -101,9 +101,7 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const uint4* __restrict
             v[j] = (k0 + j < n) ? pm_value(meta, ref_end, (uint32_t)(k0 + j)) : 0ull;
             // coordinate order check rides along: (tid, pos0 + 1) must not decrease
             if (k0 + j < n && k0 + j > 0) {
-                const uint4 a = meta[k0 + j - 1], b = meta[k0 + j];
-                const unsigned long long ka = ((unsigned long long)a.y << 32) | (uint32_t)(a.x + 1u), kb = ((unsigned long long)b.y << 32) | (uint32_t)(b.x + 1u);
-                if (ka > kb) scalars[SC_UNSORTED] = 1;
+                if (meta[k0 + j - 1] > meta[k0 + j]) scalars[SC_UNSORTED] = 1;
             }
             run = umax64(run, v[j]);
         }
@@ -124,7 +122,7 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const uint4* __restrict
 }
 
 // ------------------------------------------------------------ tile -> event slice
-__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_tiles, const uint4* __restrict__ meta,
+__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_tiles, const unsigned long long* __restrict__ key,
                               const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
                               const uint32_t* scalars, uint2* tile_ev)
 {
@@ -136,9 +134,7 @@ __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_ti
         uint32_t lo = 0, hi = n;
         while (lo < hi) {                        // r_hi: first record with (tid, pos0 + 1) >= (tid, T1)
             const uint32_t mid = (lo + hi) >> 1;
-            const uint4 m = meta[mid];
-            const unsigned long long km = ((unsigned long long)m.y << 32) | (uint32_t)(m.x + 1u);
-            if (km < key_hi) lo = mid + 1; else hi = mid;
+            if (key[mid] < key_hi) lo = mid + 1; else hi = mid;
         }
         const uint32_t r_hi = lo;
         lo = 0; hi = r_hi;
@@ -154,7 +150,7 @@ __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_ti
 int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
 {
     if (b->n_tiles == 0) return CSV_OK;
-    const uint4* meta = b->d_meta.as<uint4>();
+    const unsigned long long* meta = b->d_key.as<unsigned long long>();
     const uint32_t* ref_end = b->d_ref_end.as<uint32_t>();
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
     unsigned long long* part = b->d_pmax_part.as<unsigned long long>();
@@ -178,8 +174,9 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
 // --------------------------------------------------------------------- tile kernel
 constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kWarpChunk = kTile / kTileWarps;     // positions per warp
-constexpr int kRows = kWarpChunk / 128;            // 128 positions (one int4 per lane) per row
+constexpr int kPerThread = kTile / kTileThreads;   // 32 consecutive positions per thread
+constexpr int kPad = kPerThread + 4;               // padded row: 16-byte aligned, conflict-free 128-bit access
+static_assert(kPerThread == 32, "layout below assumes 32 positions per thread");
 
 struct TileParams {
     const uint4* tile_desc;          // static per tile: {region, positions in tile, T0, tid}
@@ -192,80 +189,108 @@ struct TileParams {
     uint32_t n_tiles;
 };
 
-__global__ void __launch_bounds__(kTileThreads, 6) k_depth_tiles(const TileParams P)
+// shared-memory index of tile position q: thread-major rows of 32 positions, padded to 36 words
+__device__ __forceinline__ uint32_t tile_slot(uint32_t q) { return (q >> 5) * kPad + (q & 31u); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(kTileThreads, 5) k_depth_tiles(const TileParams P)
 {
-    __shared__ __align__(16) int s_diff[kTile];
-    __shared__ int s_wtot[kTileWarps];
+    __shared__ __align__(16) int s_diff[kTileThreads * kPad];
+    __shared__ uint32_t s_scan[40];
     __shared__ int s_wcarry[kTileWarps];
-    __shared__ unsigned long long s_wsum[kTileWarps];
-    __shared__ uint32_t s_wnz[kTileWarps];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        const uint4 desc = __ldg(P.tile_desc + t);
-        const uint2 er = __ldg(P.tile_ev + t);
+    for (uint32_t i = tid; i < kTileThreads * kPad / 4; i += kTileThreads) reinterpret_cast<int4*>(s_diff)[i] = make_int4(0, 0, 0, 0);
+    uint32_t t = blockIdx.x;
+    uint4 desc = make_uint4(0, 0, 0, 0);
+    uint2 er = make_uint2(0, 0);
+    if (t < P.n_tiles) { desc = __ldg(P.tile_desc + t); er = __ldg(P.tile_ev + t); }
+    __syncthreads();
+
+    while (t < P.n_tiles) {
+        // descriptor of the NEXT tile of this CTA: loaded now, used one iteration later
+        const uint32_t tn = t + gridDim.x;
+        uint4 desc_n = make_uint4(0, 0, 0, 0);
+        uint2 er_n = make_uint2(0, 0);
+        if (tn < P.n_tiles) { desc_n = __ldg(P.tile_desc + tn); er_n = __ldg(P.tile_ev + tn); }
+
         const uint32_t n_here = desc.y, T0 = desc.z, T1 = desc.z + desc.y;
         const uint32_t e1 = er.y < P.ev_cap ? er.y : P.ev_cap;
-        int4* z = reinterpret_cast<int4*>(s_diff);
-#pragma unroll
-        for (int i = 0; i < kTile / 4 / kTileThreads; i++) z[tid + i * kTileThreads] = make_int4(0, 0, 0, 0);
-        __syncthreads();
+        // ---- events of the records that overlap the tile (s_diff is all zero here)
+        // All loads of a batch are issued before the first shared-memory atomic, so a tile pays
+        // one memory round trip per 2048 events instead of one per 256.
         int mycarry = 0;
-        for (uint32_t e = er.x + tid; e < e1; e += kTileThreads) {
-            const uint32_t p = __ldg(P.events + e);
-            const int sgn = (e & 1u) ? -1 : 1;
-            if (p < T0) mycarry += sgn;
-            else if (p < T1) atomicAdd(&s_diff[p - T0], sgn);
+        const int sgn = 1 - 2 * (int)((er.x + tid) & 1u);          // slot parity; the stride (256) is even
+        for (uint32_t base = er.x + tid; base < e1; base += kTileThreads * 8u) {
+            uint32_t p[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const uint32_t e = base + u * kTileThreads; p[u] = e < e1 ? __ldg(P.events + e) : kNone; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (p[u] < T0) mycarry += sgn;
+                else if (p[u] < T1) atomicAdd(&s_diff[tile_slot(p[u] - T0)], sgn);
+            }
         }
         mycarry = (int)warp_sum_u32((uint32_t)mycarry);
         if (lane == 0) s_wcarry[warp] = mycarry;
         __syncthreads();
-        // pass A: per-warp totals
-        const int4* row = reinterpret_cast<const int4*>(s_diff + warp * kWarpChunk);
+        // ---- thread-sequential prefix over 32 consecutive positions
+        int v[kPerThread];
+        int4* mine = reinterpret_cast<int4*>(s_diff + tid * kPad);
         int tot = 0;
 #pragma unroll
-        for (int i = 0; i < kRows; i++) { int4 v = row[i * 32 + lane]; tot += v.x + v.y + v.z + v.w; }
-        tot = (int)warp_sum_u32((uint32_t)tot);
-        if (lane == 0) s_wtot[warp] = tot;
+        for (int i = 0; i < kPerThread / 4; i++) {
+            const int4 x = mine[i];
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+            tot += (x.x + x.y) + (x.z + x.w);
+        }
+        uint32_t dummy;
+        const uint32_t ex = block_excl_scan_u32((uint32_t)tot, s_scan, &dummy);
+        int carry_in = 0;
+#pragma unroll
+        for (int i = 0; i < kTileWarps; i++) carry_in += s_wcarry[i];
+        int run = carry_in + (int)ex;
+        // no depth in the tile exceeds carry_in + #events: 32 of them fit a 32-bit sum unless that bound is absurd
+        const bool wide = (unsigned long long)(uint32_t)carry_in + (e1 - er.x) >= (1ull << 26);
+        const uint32_t q0 = tid * kPerThread;
+        const uint32_t cnt = q0 >= n_here ? 0u : (n_here - q0 < (uint32_t)kPerThread ? n_here - q0 : (uint32_t)kPerThread);
+        uint32_t sum32 = 0, mn = 0xffffffffu, nz;
+#pragma unroll
+        for (int i = 0; i < kPerThread; i++) { run += v[i]; v[i] = run; sum32 += (uint32_t)run; mn = min(mn, (uint32_t)run); }
+        unsigned long long sum = sum32;
+        nz = cnt;
+        if (cnt != (uint32_t)kPerThread || mn == 0u || wide) {            // rare: ragged tile end, zero depth, absurd depth
+            sum = 0; nz = 0;
+#pragma unroll
+            for (int i = 0; i < kPerThread; i++) if ((uint32_t)i < cnt) { sum += (uint32_t)v[i]; nz += v[i] != 0; }
+        }
+#pragma unroll
+        for (int i = 0; i < kPerThread / 4; i++) mine[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        sum = warp_sum_u64(sum); nz = warp_sum_u32(nz);
+        if (lane == 0 && (sum | nz)) { atomicAdd(&P.tile_sum[t], sum); atomicAdd(&P.tile_nz[t], nz); }
+        // pull the next tile's event slice towards L2 while this tile is written out
+        if (tn < P.n_tiles) {
+            const uint32_t pe = er_n.y < P.ev_cap ? er_n.y : P.ev_cap;
+            for (uint32_t a = er_n.x + tid * 32u; a < pe; a += kTileThreads * 32u) prefetch_l2(P.events + a);
+        }
         __syncthreads();
-        int carry = 0;
+        // ---- coalesced copy-out: each warp streams 8 rows of 128 positions, zeroing behind itself
+        uint32_t* out = P.depth + (size_t)t * kTile;
 #pragma unroll
-        for (int i = 0; i < kTileWarps; i++) carry += s_wcarry[i];
-        for (uint32_t i = 0; i < warp; i++) carry += s_wtot[i];
-        // pass B: scan rows, write, reduce
-        unsigned long long sum = 0; uint32_t nz = 0;
-        uint32_t* out = P.depth + (size_t)t * kTile + warp * kWarpChunk;
-        const uint32_t wbase = warp * kWarpChunk;
-#pragma unroll
-        for (int i = 0; i < kRows; i++) {
-            int4 v = row[i * 32 + lane];
-            v.y += v.x; v.z += v.y; v.w += v.z;
-            int incl = (int)warp_incl_scan_u32((uint32_t)v.w);
-            int base = carry + incl - v.w;
-            v.x += base; v.y += base; v.z += base; v.w += base;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t pos = wbase + i * 128 + lane * 4;
-            if (pos + 4 <= n_here) {
-                st_cs_v4(out + i * 128 + lane * 4, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
-                sum += (unsigned long long)(uint32_t)v.x + (uint32_t)v.y + (uint32_t)v.z + (uint32_t)v.w;
-                nz += (v.x > 0) + (v.y > 0) + (v.z > 0) + (v.w > 0);
-            } else if (pos < n_here) {
-                const int vv[4] = {v.x, v.y, v.z, v.w};
-                for (uint32_t q = 0; q < 4 && pos + q < n_here; q++) {
-                    out[i * 128 + lane * 4 + q] = (uint32_t)vv[q];
-                    sum += (uint32_t)vv[q]; nz += vv[q] > 0;
-                }
+        for (int i = 0; i < kTile / 128 / kTileWarps; i++) {
+            const uint32_t q = (warp * (kTile / 128 / kTileWarps) + i) * 128u + lane * 4u;
+            int4* sp = reinterpret_cast<int4*>(s_diff + tile_slot(q));
+            const int4 x = *sp;
+            *sp = make_int4(0, 0, 0, 0);
+            if (q + 4 <= n_here) st_cs_v4(out + q, make_uint4((uint32_t)x.x, (uint32_t)x.y, (uint32_t)x.z, (uint32_t)x.w));
+            else if (q < n_here) {
+                const int xx[4] = {x.x, x.y, x.z, x.w};
+                for (uint32_t k = 0; k < 4 && q + k < n_here; k++) out[q + k] = (uint32_t)xx[k];
             }
         }
-        sum = warp_sum_u64(sum); nz = warp_sum_u32(nz);
-        if (lane == 0) { s_wsum[warp] = sum; s_wnz[warp] = nz; }
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long ts = 0; uint32_t tn = 0;
-#pragma unroll
-            for (int i = 0; i < kTileWarps; i++) { ts += s_wsum[i]; tn += s_wnz[i]; }
-            P.tile_sum[t] = ts; P.tile_nz[t] = tn;
-        }
+        t = tn; desc = desc_n; er = er_n;
     }
 }
 
@@ -299,7 +324,9 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
     P.tile_nz = b->d_tile_nz.as<uint32_t>();
     P.n_tiles = b->n_tiles;
     if (b->n_tiles == 0) return CSV_OK;
-    uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 28 ? b->n_tiles : (uint32_t)ctx->sm_count * 28;
+    CSV_CUDA(cudaMemsetAsync(P.tile_sum, 0, (size_t)b->n_tiles * 8, ctx->stream));
+    CSV_CUDA(cudaMemsetAsync(P.tile_nz, 0, (size_t)b->n_tiles * 4, ctx->stream));
+    uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 20 ? b->n_tiles : (uint32_t)ctx->sm_count * 20;
     k_depth_tiles<<<grid, kTileThreads, 0, ctx->stream>>>(P);
     k_region_stats<<<b->n_regions, 256, 0, ctx->stream>>>(b->d_reg_tab.as<uint32_t>(), P.tile_sum, P.tile_nz,
                                                           b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());

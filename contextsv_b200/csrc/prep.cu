@@ -33,6 +33,7 @@ int launch_prep(csv_ctx* ctx, csv_batch* b)
     const uint8_t* mapq = b->d_mapq.as<uint8_t>();
     uint4* meta = b->d_meta.as<uint4>();
     uint32_t* ne_idx = b->d_ne_idx.as<uint32_t>();
+    unsigned long long* key = b->d_key.as<unsigned long long>();
     uint32_t* headbits = b->d_headbits.as<uint32_t>();
     const TidDev* tids = b->d_tids.as<TidDev>();
     const RegionDev* regs = b->d_regs.as<RegionDev>();
@@ -49,11 +50,11 @@ int launch_prep(csv_ctx* ctx, csv_batch* b)
         int32_t t = tid ? tid[i] : 0;
         uint4 m;
         m.x = (uint32_t)pos0[i];
-        m.y = (uint32_t)t;                                   // raw contig id: (tid, pos0 + 1) is the sort key of the batch
         m.z = (uint32_t)flag[i] | ((uint32_t)mapq[i] << 16);
-        if (t < 0 || (uint32_t)t >= n_tids || tids[t].count == 0) { m.z |= 0x80000000u; m.w = kNone; }   // contig not requested
-        else m.w = find_owner(tids[t], regs, m.x + 1u);
+        if (t < 0 || (uint32_t)t >= n_tids || tids[t].count == 0) { m.y = 0u; m.w = kNone; }   // contig not requested
+        else { m.y = tids[t].map_size; m.w = find_owner(tids[t], regs, m.x + 1u); }
         meta[k] = m;
+        key[k] = ((unsigned long long)(uint32_t)t << 32) | (uint32_t)(m.x + 1u);     // coordinate sort key of the batch
         ne_idx[k] = (uint32_t)i;
     };
     return chained_scan(ctx, in, out, n_reads, nullptr, b->d_scalars.as<uint32_t>() + SC_N_NONEMPTY);

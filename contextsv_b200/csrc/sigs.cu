@@ -56,7 +56,7 @@ __global__ void k_sig_gather(const GatherParams P)
             // exact sequential restatement (sv_caller.cpp:563-655) for the rare records that reach or
             // pass the end of their contig: a soft clip there skips the query advance (:602-604)
             const uint4 m = P.meta[k];
-            const uint32_t map_size = P.tids[m.y].map_size;
+            const uint32_t map_size = m.y;
             uint32_t pos = m.x, q = 0;
             for (unsigned long long o = c0; o < (unsigned long long)g; o++) {
                 const uint32_t w = P.cigar[o], op = w & 15u, len = w >> 4;

@@ -7,9 +7,11 @@
 //   1. each thread loads 8 ops with two 128-bit loads plus the 9 head bits that
 //      say where records start;
 //   2. a segmented scan (reset at record heads) of (reference, query)
-//      consumption runs thread -> warp -> CTA -> chained look-back across spans;
-//      plain sums of head bits (-> record index) and of depth-event counts
-//      (-> event slot) ride along;
+//      consumption runs thread -> warp -> CTA; the carry-in of every span comes
+//      from a cheap aggregate pre-pass (k_span_agg) and a two-level scan over the
+//      span aggregates -- deterministic, no spinning on other CTAs.  Plain sums of
+//      head bits (-> record index) and of depth-event counts (-> event slot) ride
+//      along;
 //   3. every op now knows its reference position, query offset and event slot:
 //        - I/D/S ops >= min_len become signatures;
 //        - depth events are written in op order: a record contributes +1 at its
@@ -30,13 +32,10 @@ struct WalkParams {
     const uint32_t* cigar;
     uint32_t n_ops;
     const uint8_t* headbits;
-    const uint4* meta;
-    const TidDev* tids;
-    WalkAgg* span_agg;
-    WalkAgg* span_pre;
-    uint32_t* span_status;
-    uint32_t* ticket;
-    uint32_t epoch;
+    const uint4* meta;          // {pos0, map_size (0 = contig not requested), flag | mapq << 16, owner region}
+    WalkAgg* span_agg;          // per-span aggregate
+    WalkAgg* span_pre;          // exclusive prefix of the span inside its chunk of kSpanChunk spans
+    WalkAgg* chunk_agg;         // per-chunk aggregate, then exclusive prefix over chunks
     uint32_t n_spans;
     uint32_t* events;
     uint32_t ev_cap;
@@ -50,6 +49,8 @@ struct WalkParams {
     int want_depth, want_sigs;
 };
 
+constexpr int kSpanChunk = 2048;    // spans per scan chunk (256 threads x 8)
+
 __device__ __forceinline__ WalkAgg combine(const WalkAgg a, const WalkAgg b)
 {
     WalkAgg r;
@@ -60,195 +61,221 @@ __device__ __forceinline__ WalkAgg combine(const WalkAgg a, const WalkAgg b)
     return r;
 }
 
-__device__ __forceinline__ WalkAgg shfl_agg(const WalkAgg v, int src)
+__device__ __forceinline__ WalkAgg warp_incl_scan_agg(WalkAgg inc, uint32_t lane)
 {
-    WalkAgg r;
-    r.heads = __shfl_sync(0xffffffffu, v.heads, src);
-    r.ref = __shfl_sync(0xffffffffu, v.ref, src);
-    r.qry = __shfl_sync(0xffffffffu, v.qry, src);
-    r.ev = __shfl_sync(0xffffffffu, v.ev, src);
-    return r;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        WalkAgg t;
+        t.heads = __shfl_up_sync(0xffffffffu, inc.heads, d);
+        t.ref = __shfl_up_sync(0xffffffffu, inc.ref, d);
+        t.qry = __shfl_up_sync(0xffffffffu, inc.qry, d);
+        t.ev = __shfl_up_sync(0xffffffffu, inc.ev, d);
+        if (lane >= (uint32_t)d) inc = combine(t, inc);
+    }
+    return inc;
+}
+__device__ __forceinline__ WalkAgg shfl_up1_agg(const WalkAgg inc, uint32_t lane)
+{
+    WalkAgg e;
+    e.heads = __shfl_up_sync(0xffffffffu, inc.heads, 1);
+    e.ref = __shfl_up_sync(0xffffffffu, inc.ref, 1);
+    e.qry = __shfl_up_sync(0xffffffffu, inc.qry, 1);
+    e.ev = __shfl_up_sync(0xffffffffu, inc.ev, 1);
+    if (lane == 0) e = WalkAgg{0, 0, 0, 0};
+    return e;
 }
 
-// Chained look-back over spans for the 4-word state.  Payloads live in span_agg /
-// span_pre; span_status carries (epoch << 2 | flag) and is published after a
-// __threadfence().  Called by warp 0; returns the exclusive state of span s.
-__device__ __forceinline__ WalkAgg walk_lookback(const WalkParams& P, uint32_t s, const WalkAgg total)
+// 8 ops of one thread + the 9 head bits around them
+struct ThreadOps { uint32_t w[kWalkOpsPerThread]; uint32_t hb, n_valid; };
+
+__device__ __forceinline__ ThreadOps load_ops(const uint32_t* __restrict__ cigar, const uint8_t* __restrict__ headbits, uint32_t n_ops, uint32_t g0)
 {
-    const uint32_t lane = lane_id();
-    const uint32_t tag = P.epoch << 2;
-    WalkAgg excl = {0, 0, 0, 0};
-    if (lane == 0) {
-        if (s == 0) { P.span_pre[0] = total; __threadfence(); st_volatile_u32(&P.span_status[0], tag | kFlagPrefix); }
-        else { P.span_agg[s] = total; __threadfence(); st_volatile_u32(&P.span_status[s], tag | kFlagAgg); }
+    ThreadOps t;
+    t.hb = 0;
+    if (g0 + kWalkOpsPerThread <= n_ops) {
+        uint4 a = ld_nc_v4(cigar + g0), c = ld_nc_v4(cigar + g0 + 4);
+        t.w[0] = a.x; t.w[1] = a.y; t.w[2] = a.z; t.w[3] = a.w; t.w[4] = c.x; t.w[5] = c.y; t.w[6] = c.z; t.w[7] = c.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kWalkOpsPerThread; j++) t.w[j] = (g0 + j < n_ops) ? __ldg(cigar + g0 + j) : 0u;
     }
-    if (s == 0) return excl;
-    int64_t look = (int64_t)s - 1;
-    bool have = false;   // excl currently holds the combination of spans (look, s)
-    for (;;) {
-        int64_t idx = look - lane;
-        uint32_t flag;
-        do {
-            if (idx >= 0) { uint32_t w = ld_volatile_u32(&P.span_status[idx]); flag = ((w >> 2) == P.epoch) ? (w & 3u) : 0u; }
-            else flag = kFlagPrefix;
-        } while (__any_sync(0xffffffffu, flag == 0));
-        __threadfence();
-        WalkAgg v = {0, 0, 0, 0};
-        if (idx >= 0) v = (flag == kFlagPrefix) ? P.span_pre[idx] : P.span_agg[idx];
-        uint32_t pm = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
-        int last = pm ? (__ffs(pm) - 1) : 31;     // farthest lane that contributes
-        WalkAgg acc = shfl_agg(v, last);
-        for (int i = last - 1; i >= 0; i--) acc = combine(acc, shfl_agg(v, i));
-        excl = have ? combine(acc, excl) : acc;
-        have = true;
-        if (pm) break;
-        look -= 32;
-    }
-    if (lane == 0) { P.span_pre[s] = combine(excl, total); __threadfence(); st_volatile_u32(&P.span_status[s], tag | kFlagPrefix); }
-    return excl;
+    if (g0 < n_ops) t.hb = (uint32_t)__ldg(headbits + (g0 >> 3)) | ((uint32_t)__ldg(headbits + (g0 >> 3) + 1) << 8);
+    t.n_valid = g0 >= n_ops ? 0u : (n_ops - g0 < kWalkOpsPerThread ? n_ops - g0 : kWalkOpsPerThread);
+    return t;
 }
 
+__device__ __forceinline__ uint32_t bit_of(uint32_t mask, uint32_t op) { return (mask >> op) & 1u; }
+
+// Aggregate of the 8 ops of one thread.  Heads / event counts are popcounts of the head bits;
+// (ref, qry) only count the ops from the LAST record head of the thread onwards.
+__device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t)
+{
+    WalkAgg a;
+    const uint32_t vmask = (1u << t.n_valid) - 1u;          // n_valid <= 8
+    const uint32_t hbv = t.hb & vmask;
+    a.heads = __popc(hbv);
+    const int lh = 31 - __clz(hbv);                         // index of the last head, -1 if none
+    uint32_t ref = 0, qry = 0, gaps = 0;
+#pragma unroll
+    for (int j = 0; j < kWalkOpsPerThread; j++) {
+        const uint32_t op = t.w[j] & 15u;                   // ops beyond n_valid are zero words: M of length 0
+        const uint32_t len = (j >= lh) ? (t.w[j] >> 4) : 0u;
+        ref += bit_of(kRefMask, op) * len;
+        qry += bit_of(kQryMask, op) * len;
+        gaps += bit_of(kGapMask, op) & (uint32_t)((t.w[j] >> 4) != 0u);
+    }
+    a.ref = ref; a.qry = qry;
+    a.ev = a.heads + __popc((t.hb >> 1) & vmask) + 2u * gaps;
+    return a;
+}
+
+// pre-pass: aggregate of every span (one CTA per span; pure streaming read of the CIGAR words)
+__global__ void __launch_bounds__(kWalkThreads) k_span_agg(const WalkParams P)
+{
+    __shared__ WalkAgg s_warp[kWalkThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t span = blockIdx.x;
+    const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread);
+    const WalkAgg inc = warp_incl_scan_agg(thread_aggregate(t), lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        WalkAgg total = s_warp[0];
+#pragma unroll
+        for (int i = 1; i < kWalkThreads / 32; i++) total = combine(total, s_warp[i]);
+        P.span_agg[span] = total;
+    }
+}
+
+// level 1: exclusive segmented scan of the span aggregates inside chunks of kSpanChunk spans
+__global__ void __launch_bounds__(256) k_span_scan_local(const WalkParams P)
+{
+    __shared__ WalkAgg s_warp[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t base = blockIdx.x * (uint32_t)kSpanChunk + tid * 8u;
+    WalkAgg v[8], run = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = (base + j < P.n_spans) ? P.span_agg[base + j] : WalkAgg{0, 0, 0, 0}; run = combine(run, v[j]); }
+    const WalkAgg inc = warp_incl_scan_agg(run, lane);
+    WalkAgg pre = shfl_up1_agg(inc, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    WalkAgg wpre = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < warp; i++) wpre = combine(wpre, s_warp[i]);
+    pre = combine(wpre, pre);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { if (base + j < P.n_spans) P.span_pre[base + j] = pre; pre = combine(pre, v[j]); }
+    if (tid == 255) P.chunk_agg[blockIdx.x] = pre;
+}
+
+// level 2: one CTA turns the chunk aggregates into exclusive prefixes (in place)
+__global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, uint32_t n_chunks)
+{
+    __shared__ WalkAgg s_warp[32];
+    __shared__ WalkAgg s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = WalkAgg{0, 0, 0, 0};
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_chunks; b0 += 1024) {
+        const uint32_t i = b0 + tid;
+        const WalkAgg v = i < n_chunks ? P.chunk_agg[i] : WalkAgg{0, 0, 0, 0};
+        const WalkAgg inc = warp_incl_scan_agg(v, lane);
+        WalkAgg pre = shfl_up1_agg(inc, lane);
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        WalkAgg wpre = s_carry;
+        for (uint32_t w = 0; w < warp; w++) wpre = combine(wpre, s_warp[w]);
+        pre = combine(wpre, pre);
+        if (i < n_chunks) P.chunk_agg[i] = pre;
+        __syncthreads();
+        if (tid == 1023) s_carry = combine(pre, v);
+        __syncthreads();
+    }
+}
+
+// Replay of one thread's ops with their full prefixes.  FULL = all 8 ops valid (every span but the last).
+template <bool DEPTH, bool SIGS, bool FULL>
+__device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps& t, const WalkAgg T, uint32_t g0)
+{
+    uint32_t k = T.heads - 1u, Rc = T.ref, Qc = T.qry, slot = T.ev;
+    uint4 m = make_uint4(0, 0, 0, kNone);
+    uint32_t a0 = 0;
+    bool live = false, sok = false;
+    auto load_meta = [&]() {
+        m = __ldg(P.meta + k);
+        const uint32_t flags = m.z & 0xffffu, mq = (m.z >> 16) & 0xffu;
+        a0 = m.x + 1u;                                                       // (uint32)pos + 1, cnv_caller.cpp:499
+        live = m.y != 0u && !(flags & kDepthSkipFlags) && a0 < m.y;
+        sok = m.w != kNone && !(flags & kSigSkipFlags) && mq >= P.min_mapq;
+    };
+    if (!(t.hb & 1u) && (FULL || t.n_valid)) load_meta();                    // first op continues an earlier record
+#pragma unroll
+    for (int j = 0; j < kWalkOpsPerThread; j++) {
+        if (!FULL && (uint32_t)j >= t.n_valid) break;
+        const uint32_t op = t.w[j] & 15u, len = t.w[j] >> 4;
+        if ((t.hb >> j) & 1u) {                                              // first op of a record
+            k++; Rc = 0; Qc = 0;
+            load_meta();
+            if (DEPTH) P.events[slot++] = live ? a0 : kNone;
+        }
+        const uint32_t pos1 = m.x + Rc + 1u;                                 // reference's `pos + 1` at this op (uint32)
+        if (SIGS && len >= P.min_len && bit_of(kSigMask, op) && sok) {
+            const bool beyond = pos1 >= m.y;
+            if (!(op == 4 && beyond)) {                                      // sv_caller.cpp:602-604
+                const uint32_t start = pos1, end = start + len - 1u;
+                if (start <= end) {                                          // sv_object.cpp:25-28
+                    const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
+                    if (sl < P.sig_cap) {
+                        P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
+                        P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
+                        P.sig.k[sl] = k;
+                        P.sig.qpos[sl] = Qc;
+                        const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
+                        P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
+                        atomicAdd(&P.reg_sig_cnt[m.w], 1u);
+                    }
+                }
+            }
+        }
+        if (DEPTH) {                                                         // D / N: -1 at its first index, +1 one past its last
+            const bool gap = bit_of(kGapMask, op) && len;
+            const uint32_t ia = pos1, ib = pos1 + len;                       // no overflow when ia < map_size <= 2^31
+            const bool in = live && ia < m.y;
+            const uint32_t va = in ? ia : kNone, vb = (in && ib < m.y) ? ib : kNone;
+            if (gap) { P.events[slot] = va; P.events[slot + 1] = vb; }
+            slot += gap ? 2u : 0u;
+        }
+        Rc += bit_of(kRefMask, op) * len;
+        Qc += bit_of(kQryMask, op) * len;
+        if (DEPTH && ((t.hb >> (j + 1)) & 1u)) {                             // last op of the record
+            const uint32_t ie = a0 + Rc;
+            const bool in = live && ie >= a0 && ie < m.y;                    // ie < a0: 32-bit wrap (absurd record)
+            P.events[slot++] = in ? ie : kNone;
+            P.ev_start[k + 1] = slot;
+            P.ref_end[k] = live ? (in ? ie : m.y) : 0u;
+        }
+    }
+}
+
+template <bool DEPTH, bool SIGS>
 __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
 {
     __shared__ WalkAgg s_warp[kWalkThreads / 32];
-    __shared__ WalkAgg s_excl;
-    __shared__ uint32_t s_span;
-
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_span = atomicAdd(P.ticket, 1u);
-        __syncthreads();
-        const uint32_t span = s_span;
-        if (span >= P.n_spans) break;
-        const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
-
-        // ---- 1. load 8 ops + head bits
-        uint32_t w[kWalkOpsPerThread];
-        uint32_t hb = 0;
-        if (g0 + kWalkOpsPerThread <= P.n_ops) {
-            uint4 a = ld_nc_v4(P.cigar + g0), c = ld_nc_v4(P.cigar + g0 + 4);
-            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < kWalkOpsPerThread; j++) w[j] = (g0 + j < P.n_ops) ? __ldg(P.cigar + g0 + j) : 0u;
-        }
-        if (g0 < P.n_ops) hb = (uint32_t)P.headbits[g0 >> 3] | ((uint32_t)P.headbits[(g0 >> 3) + 1] << 8);
-        const uint32_t n_valid = g0 >= P.n_ops ? 0u : (P.n_ops - g0 < kWalkOpsPerThread ? P.n_ops - g0 : kWalkOpsPerThread);
-
-        // ---- 2a. thread aggregate
-        WalkAgg a = {0, 0, 0, 0};
-#pragma unroll
-        for (int j = 0; j < kWalkOpsPerThread; j++) {
-            if ((uint32_t)j < n_valid) {
-                const uint32_t op = w[j] & 15u, len = w[j] >> 4;
-                if ((hb >> j) & 1u) { a.heads++; a.ref = 0; a.qry = 0; }
-                a.ref += ((kRefMask >> op) & 1u) ? len : 0u;
-                a.qry += ((kQryMask >> op) & 1u) ? len : 0u;
-                a.ev += ((hb >> j) & 1u) + ((hb >> (j + 1)) & 1u) + ((((kGapMask >> op) & 1u) && len) ? 2u : 0u);
-            }
-        }
-        // ---- 2b. warp segmented inclusive scan
-        WalkAgg inc = a;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            WalkAgg t;
-            t.heads = __shfl_up_sync(0xffffffffu, inc.heads, d);
-            t.ref = __shfl_up_sync(0xffffffffu, inc.ref, d);
-            t.qry = __shfl_up_sync(0xffffffffu, inc.qry, d);
-            t.ev = __shfl_up_sync(0xffffffffu, inc.ev, d);
-            if (lane >= (uint32_t)d) inc = combine(t, inc);
-        }
-        WalkAgg lane_excl;
-        lane_excl.heads = __shfl_up_sync(0xffffffffu, inc.heads, 1);
-        lane_excl.ref = __shfl_up_sync(0xffffffffu, inc.ref, 1);
-        lane_excl.qry = __shfl_up_sync(0xffffffffu, inc.qry, 1);
-        lane_excl.ev = __shfl_up_sync(0xffffffffu, inc.ev, 1);
-        if (lane == 0) lane_excl = WalkAgg{0, 0, 0, 0};
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        // ---- 2c. CTA level + chained look-back
-        WalkAgg wpre = {0, 0, 0, 0};
-        for (uint32_t i = 0; i < warp; i++) wpre = combine(wpre, s_warp[i]);
-        if (warp == 0) {
-            WalkAgg total = s_warp[0];
-#pragma unroll
-            for (int i = 1; i < kWalkThreads / 32; i++) total = combine(total, s_warp[i]);
-            const WalkAgg ex = walk_lookback(P, span, total);
-            if (lane == 0) s_excl = ex;
-        }
-        __syncthreads();
-        const WalkAgg T = combine(s_excl, combine(wpre, lane_excl));
-
-        // ---- 3. replay with full prefixes
-        uint32_t Hc = T.heads, Rc = T.ref, Qc = T.qry, slot = T.ev;
-        uint32_t kcur = kNone;
-        uint4 m = make_uint4(0, 0, 0x80000000u, kNone);
-        uint32_t map_size = 0;
-        bool dok = false, sok = false;
-#pragma unroll
-        for (int j = 0; j < kWalkOpsPerThread; j++) {
-            if ((uint32_t)j >= n_valid) break;
-            const uint32_t op = w[j] & 15u, len = w[j] >> 4;
-            const bool head = (hb >> j) & 1u, tail = (hb >> (j + 1)) & 1u;
-            if (head) { Hc++; Rc = 0; Qc = 0; }
-            const uint32_t k = Hc - 1u;
-            if (k != kcur) {
-                kcur = k; m = __ldg(P.meta + k);
-                const bool ignored = m.z >> 31;
-                map_size = ignored ? 0u : P.tids[m.y].map_size;
-                const uint32_t flags = m.z & 0xffffu, mq = (m.z >> 16) & 0xffu;
-                dok = !ignored && !(flags & kDepthSkipFlags);
-                sok = !ignored && !(flags & kSigSkipFlags) && mq >= P.min_mapq && m.w != kNone;
-            }
-            const uint32_t rl = ((kRefMask >> op) & 1u) ? len : 0u;
-            const uint32_t pos = m.x + Rc;   // 0-based position at this op, uint32 like the reference's `pos`
-
-            if (P.want_sigs && sok && len >= P.min_len && ((kSigMask >> op) & 1u)) {
-                const bool beyond = (pos + 1u) >= map_size;
-                if (!(op == 4 && beyond)) {                                     // sv_caller.cpp:602-604
-                    const uint32_t start = pos + 1u, end = start + len - 1u;
-                    if (start <= end) {                                         // sv_object.cpp:25-28
-                        const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
-                        if (sl < P.sig_cap) {
-                            P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
-                            P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
-                            P.sig.k[sl] = k;
-                            P.sig.qpos[sl] = Qc;
-                            const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
-                            P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
-                            atomicAdd(&P.reg_sig_cnt[m.w], 1u);
-                        }
-                    }
-                }
-            }
-            if (P.want_depth) {
-                const uint32_t a0 = m.x + 1u;                                   // (uint32)pos + 1, cnv_caller.cpp:499
-                const bool live = dok && a0 < map_size;
-                if (head) {
-                    if (slot < P.ev_cap) P.events[slot] = live ? a0 : kNone;
-                    slot++;
-                }
-                if (((kGapMask >> op) & 1u) && len) {
-                    const unsigned long long ia = (unsigned long long)(uint32_t)(pos + 1u), ib = ia + len;
-                    if (slot + 1 < P.ev_cap) {
-                        P.events[slot] = (live && ia < map_size) ? (uint32_t)ia : kNone;
-                        P.events[slot + 1] = (live && ib < map_size) ? (uint32_t)ib : kNone;
-                    }
-                    slot += 2;
-                }
-                if (tail) {
-                    const unsigned long long ie = (unsigned long long)a0 + Rc + rl;
-                    if (slot < P.ev_cap) P.events[slot] = (live && ie < map_size) ? (uint32_t)ie : kNone;
-                    slot++;
-                    P.ev_start[k + 1] = slot;
-                    P.ref_end[k] = live ? (uint32_t)(ie < map_size ? ie : map_size) : 0u;
-                }
-            }
-            Rc += rl;
-            Qc += ((kQryMask >> op) & 1u) ? len : 0u;
-        }
-    }
+    const uint32_t span = blockIdx.x;
+    const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
+    // independent loads first: ops, head bits and the span's carry-in (one memory round trip)
+    const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, g0);
+    const WalkAgg span_excl = combine(P.chunk_agg[span / kSpanChunk], P.span_pre[span]);
+    const WalkAgg inc = warp_incl_scan_agg(thread_aggregate(t), lane);
+    const WalkAgg lane_excl = shfl_up1_agg(inc, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    WalkAgg wpre = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < warp; i++) wpre = combine(wpre, s_warp[i]);
+    const WalkAgg T = combine(span_excl, combine(wpre, lane_excl));
+    if (t.n_valid == kWalkOpsPerThread) walk_replay<DEPTH, SIGS, true>(P, t, T, g0);
+    else walk_replay<DEPTH, SIGS, false>(P, t, T, g0);
 }
 
 int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
@@ -259,12 +286,9 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.n_ops = (uint32_t)b->n_ops;
     P.headbits = b->d_headbits.as<uint8_t>();
     P.meta = b->d_meta.as<uint4>();
-    P.tids = b->d_tids.as<TidDev>();
     P.span_agg = b->d_span_agg.as<WalkAgg>();
     P.span_pre = b->d_span_pre.as<WalkAgg>();
-    P.span_status = b->d_span_status.as<uint32_t>();
-    CSV_TRY(next_ticket(ctx, &P.ticket));
-    P.epoch = next_epoch(ctx);
+    P.chunk_agg = b->d_span_status.as<WalkAgg>();
     P.n_spans = b->n_spans;
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
@@ -280,9 +304,14 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
     P.want_depth = p->want_depth; P.want_sigs = p->want_sigs;
-    uint32_t grid = b->n_spans < (uint32_t)ctx->sm_count * 4 ? b->n_spans : (uint32_t)ctx->sm_count * 4;
-    k_walk<<<grid, kWalkThreads, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    const uint32_t n_chunks = (b->n_spans + kSpanChunk - 1) / kSpanChunk;
+    k_span_agg<<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
+    k_span_scan_local<<<n_chunks, 256, 0, ctx->stream>>>(P);
+    k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, n_chunks);
+    if (p->want_depth && p->want_sigs) k_walk<true, true><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
+    else if (p->want_depth) k_walk<true, false><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
+    else k_walk<false, true><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
+    ctx->launches += 4;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
