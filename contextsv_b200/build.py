@@ -90,6 +90,8 @@ def build_oracle():
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     if os.path.exists("/root/reference/src/sv_caller.cpp"):
         _run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        if os.path.exists(LIB_CUDA):
+            _run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "dropin"])
 
 
 def build_all(force=False):

@@ -55,8 +55,24 @@ StageTimer::StageTimer(csv_ctx* c, int s) : ctx(c), stage(s)
 }
 StageTimer::~StageTimer() { if (e1) cudaEventRecord(e1, ctx->stream); }
 
+int side_fork(csv_ctx* ctx)
+{
+    CSV_CUDA(cudaEventRecord(ctx->ev_fork, ctx->main_stream));
+    CSV_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    return CSV_OK;
+}
+int side_join(csv_ctx* ctx)
+{
+    if (!ctx->side_busy) return CSV_OK;
+    CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0));
+    ctx->side_busy = false;
+    return CSV_OK;
+}
+
 static int read_scalars(csv_ctx* ctx, csv_batch* b, uint32_t* out /* SC_COUNT */)
 {
+    CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaMemcpyAsync(ctx->pinned_small, b->d_scalars.p, SC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CSV_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(out, ctx->pinned_small, SC_COUNT * sizeof(uint32_t));
@@ -101,7 +117,11 @@ int csv_ctx_create(int device, csv_ctx** out)
     csv_ctx* ctx = new csv_ctx;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    CSV_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CSV_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
+    CSV_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->main_stream;
+    CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CSV_CUDA(cudaEventCreate(&ctx->ev0));
     CSV_CUDA(cudaEventCreate(&ctx->ev1));
     CSV_CUDA(cudaHostAlloc(&ctx->pinned_small, 4096, cudaHostAllocDefault));
@@ -113,7 +133,8 @@ void csv_ctx_destroy(csv_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamSynchronize(ctx->main_stream);
     ctx->pool.trim();
     for (auto& v : ctx->stage_events) for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto e : ctx->spare_events) cudaEventDestroy(e);
@@ -122,13 +143,16 @@ void csv_ctx_destroy(csv_ctx* ctx)
     for (auto& b : ctx->db) b.release();
     if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->side_stream);
+    cudaStreamDestroy(ctx->main_stream);
     delete ctx;
 }
 
 int csv_ctx_sync(csv_ctx* ctx)
 {
     if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
+    CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaStreamSynchronize(ctx->stream));
     return CSV_OK;
 }
@@ -143,11 +167,13 @@ void csv_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int csv_timer_begin(csv_ctx* ctx)
 {
+    CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     return CSV_OK;
 }
 int csv_timer_end(csv_ctx* ctx, float* ms_out)
 {
+    CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     CSV_CUDA(cudaEventSynchronize(ctx->ev1));
     CSV_CUDA(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
@@ -166,7 +192,7 @@ int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, doubl
 {
     static const char* kNames[ST_COUNT] = {"prep", "walk", "tile_ranges", "depth_tiles", "sig_sort", "dbscan1d"};
     if (!ctx) { set_error("null context"); return -CSV_ERR_ARG; }
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("csv_profile_read: stream synchronisation failed"); return -CSV_ERR_CUDA; }
+    if (side_join(ctx) != CSV_OK || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("csv_profile_read: stream synchronisation failed"); return -CSV_ERR_CUDA; }
     for (int s = 0; s < ST_COUNT; s++) {
         for (auto& e : ctx->stage_events[s]) {
             float ms = 0;
@@ -298,7 +324,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
 void csv_batch_free(csv_ctx* ctx, csv_batch* b)
 {
     if (!b) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); side_join(ctx); cudaStreamSynchronize(ctx->stream); }
     b->release(ctx ? &ctx->pool : nullptr);
     delete b;
 }
@@ -307,17 +333,26 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
 {
     if (!ctx || !b || !p) { set_error("csv_scan_run: null argument"); return CSV_ERR_ARG; }
     if (!p->want_depth && !p->want_sigs) { set_error("csv_scan_run: nothing requested"); return CSV_ERR_ARG; }
+    CSV_TRY(side_join(ctx));            // the previous pass's signature work may still be reading this batch
     cudaStream_t st = ctx->stream;
     b->last_min_len = p->min_len;
     CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
     if (p->want_depth) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));
     { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b)); }
     { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p)); }
+    if (p->want_sigs && p->want_depth) {   // sort + gather of the signatures run beside the depth kernels
+        CSV_TRY(side_fork(ctx));
+        SideScope side(ctx);
+        StageTimer t(ctx, ST_SIG_SORT);
+        CSV_TRY(launch_sig_finish(ctx, b));
+    } else if (p->want_sigs) {
+        StageTimer t(ctx, ST_SIG_SORT);
+        CSV_TRY(launch_sig_finish(ctx, b));
+    }
     if (p->want_depth) {
         { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b)); }
         { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b)); }
     }
-    if (p->want_sigs) { StageTimer t(ctx, ST_SIG_SORT); CSV_TRY(launch_sig_finish(ctx, b)); }
     b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;
     return CSV_OK;
 }
@@ -397,9 +432,17 @@ int csv_sigs_dbscan1d(csv_ctx* ctx, csv_batch* b, double eps, int min_pts, int32
 {
     if (!ctx || !b) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_dbscan1d: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
-    { StageTimer t(ctx, ST_DBSCAN); CSV_TRY(launch_sig_dbscan(ctx, b, eps, min_pts)); }
+    if (ctx->side_busy) {               // the signature sort is still on the side stream: follow it there
+        SideScope side(ctx);
+        StageTimer t(ctx, ST_DBSCAN);
+        CSV_TRY(launch_sig_dbscan(ctx, b, eps, min_pts));
+    } else {
+        StageTimer t(ctx, ST_DBSCAN);
+        CSV_TRY(launch_sig_dbscan(ctx, b, eps, min_pts));
+    }
     b->have_labels = true;
     if (labels_out) {
+        CSV_TRY(side_join(ctx));
         uint32_t sc[SC_COUNT];
         CSV_TRY(check_overflow(ctx, b, sc));
         const uint64_t n = sc[SC_N_SIG];
@@ -445,6 +488,7 @@ int csv_dbscan1d_seg(csv_ctx* ctx, const int32_t* pts, const uint32_t* seg_id, u
     if (n == 0) return CSV_OK;
     if (n >= (1ull << 30)) { set_error("csv_dbscan1d: %llu points exceed the 2^30 limit", (unsigned long long)n); return CSV_ERR_LIMIT; }
     CSV_CUDA(cudaSetDevice(ctx->device));
+    CSV_TRY(side_join(ctx));            // shares scratch buffers with the batch pipeline
     DevBuf& d_pts = ctx->sort_tmp[4]; DevBuf& d_misc = ctx->sort_tmp[5];
     CSV_TRY(d_pts.ensure(n * 4));
     // d_misc: labels | seg | n_clusters

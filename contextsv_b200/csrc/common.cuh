@@ -110,7 +110,11 @@ struct WalkAgg { uint32_t heads, ref, qry, ev; };
 // ------------------------------------------------------------------ context
 struct csv_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream kernels are launched on right now (main, or side inside a SideScope)
+    cudaStream_t main_stream = nullptr; // depth pipeline, copies, timers
+    cudaStream_t side_stream = nullptr; // signature sort + DBSCAN1D: only depend on the walk, run beside the depth tiles
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_busy = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     uint32_t epoch = 1;                 // look-back epoch, bumped per chained launch
@@ -134,6 +138,14 @@ namespace csv {
 int next_ticket(csv_ctx* ctx, uint32_t** out);
 inline uint32_t next_epoch(csv_ctx* ctx) { ctx->epoch++; if (ctx->epoch >= 0x3fffffffu) ctx->epoch = 1; return ctx->epoch; }
 int ensure_status(csv_ctx* ctx, size_t words);   // u64 words; never needs clearing (epoch-tagged)
+// Fork/join between the main and the side stream.
+int side_fork(csv_ctx* ctx);            // side waits for everything enqueued on main so far
+int side_join(csv_ctx* ctx);            // main waits for everything enqueued on side so far
+struct SideScope {                      // kernels launched inside the scope go to the side stream
+    csv_ctx* ctx;
+    explicit SideScope(csv_ctx* c) : ctx(c) { ctx->stream = ctx->side_stream; ctx->side_busy = true; }
+    ~SideScope() { ctx->stream = ctx->main_stream; }
+};
 // RAII stage timer: records an event pair around a pipeline stage when profiling is on.
 struct StageTimer {
     csv_ctx* ctx; int stage; cudaEvent_t e1 = nullptr;

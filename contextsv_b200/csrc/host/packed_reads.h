@@ -1,0 +1,39 @@
+// packed_reads.h -- host packer: htslib records -> the flat SoA of include/contextsv_b200.h.
+//
+// This is the C++ host side above the C ABI.  It only uses the htslib calls the reference itself
+// uses (sam_itr_next, bam_get_cigar, ... -- src/cnv_caller.cpp:488-503, src/sv_caller.cpp:509-546),
+// so it links against real htslib in the reference's own build and against oracle/htslib_shim here.
+#pragma once
+#include <htslib/sam.h>
+
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "contextsv_b200.h"
+
+namespace csvhost {
+
+struct PackedReads {
+    std::vector<int32_t> tid, pos0;
+    std::vector<uint16_t> flag;
+    std::vector<uint8_t> mapq;
+    std::vector<uint64_t> cig_off{0};
+    std::vector<uint32_t> cigar;
+    // 4-bit bases of the few records that carry an I / S op of exactly 50 bases: the only place the
+    // reference looks at the sequence on this path (literal ALT allele, src/sv_caller.cpp:572-591)
+    std::unordered_map<uint32_t, std::vector<uint8_t>> seq4;
+
+    void append(const bam1_t* b, bool keep_seq);
+    csv_reads view() const;
+    size_t size() const { return pos0.size(); }
+};
+
+// Every record an iterator yields, in file order.
+void pack_iterator(samFile* fp, hts_itr_t* itr, bam1_t* scratch, PackedReads& out, bool keep_seq);
+
+// seq_nt16_str[bam_seqi(seq, i)] with the IUPAC -> N mapping of src/sv_caller.cpp:554-559,576-580
+char base_at(const std::vector<uint8_t>& seq4, uint32_t i);
+
+}  // namespace csvhost

@@ -49,6 +49,7 @@ extern "C" int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint
     const csv_region& g = b->regions[region];
     if (g.beg != 0 || g.end != g.map_size) { set_error("csv_window_sums needs a whole-contig region"); return CSV_ERR_ARG; }
     if (n_sv == 0) return CSV_OK;
+    CSV_TRY(side_join(ctx));
     const size_t n_win = (size_t)n_sv * sample_size;
     DevBuf& in = ctx->sort_tmp[4]; DevBuf& out = ctx->sort_tmp[5];
     CSV_TRY(in.ensure((size_t)n_sv * 8));
