@@ -293,9 +293,15 @@ def main_ours(args):
     tile_bytes = 4 * depth_words
     achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
     path_gbs = b_alg / (ms / args.steps * 1e-3) / 1e9
+    traffic = None          # dram bytes read + written by one launch of the dominant kernel, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload and world == 1:
+            traffic = tj["traffic_bytes_per_launch"]
     roofline = {
         "bound": "hbm", "kernel": "k_depth_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": tile_ms,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": tile_ms,
         "path": {"algorithmic_bytes_per_step": b_alg, "achieved": path_gbs, "frac": path_gbs / peak},
         "stage_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in stages.items()},
     }

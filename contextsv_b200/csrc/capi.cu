@@ -280,7 +280,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
     CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / 2048 + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
     CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
-    CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
+    CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ref_total.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pmax.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_pmax_part.ensure((nr / 2048 + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_tile_desc.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_ev.ensure(nt * 8 + 16, &ctx->pool));
     CSV_TRY(b->d_tile_sum.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_nz.ensure(nt * 4 + 16, &ctx->pool));
@@ -338,7 +338,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     b->last_min_len = p->min_len;
     CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
     if (p->want_depth) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));
-    { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b)); }
+    { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b, p->min_mapq)); }
     { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p)); }
     if (p->want_sigs && p->want_depth) {   // sort + gather of the signatures run beside the depth kernels
         CSV_TRY(side_fork(ctx));

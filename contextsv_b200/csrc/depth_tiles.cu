@@ -21,6 +21,8 @@
 #include "batch.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace csv {
 
 // ------------------------------------------------------- prefix max over records
@@ -172,12 +174,6 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
 }
 
 // --------------------------------------------------------------------- tile kernel
-constexpr int kTileThreads = 256;
-constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kPerThread = kTile / kTileThreads;   // 32 consecutive positions per thread
-constexpr int kPad = kPerThread + 4;               // padded row: 16-byte aligned, conflict-free 128-bit access
-static_assert(kPerThread == 32, "layout below assumes 32 positions per thread");
-
 struct TileParams {
     const uint4* tile_desc;          // static per tile: {region, positions in tile, T0, tid}
     const uint2* tile_ev;            // event slice [x, y)
@@ -189,59 +185,79 @@ struct TileParams {
     uint32_t n_tiles;
 };
 
-// shared-memory index of tile position q: thread-major rows of 32 positions, padded to 36 words
-__device__ __forceinline__ uint32_t tile_slot(uint32_t q) { return (q >> 5) * kPad + (q & 31u); }
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-__global__ void __launch_bounds__(kTileThreads, 5) k_depth_tiles(const TileParams P)
+// 256-bit streaming store (sm_100): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void st_na_v8(uint32_t* p, int a, int b, int c, int d, int e, int f, int g, int h)
 {
-    __shared__ __align__(16) int s_diff[kTileThreads * kPad];
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+                 "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
+// One CTA per tile of kTile positions, PT consecutive positions per thread (kTile / PT threads).
+// Shared-memory rows of PT words are padded by 4 words: 16-byte aligned and conflict-free for the 128-bit
+// accesses of their owner (PT = 32: stride 36 words; PT = 16: stride 20 words).
+// The kernel is limited by the L1/shared-memory pipe and by latency, not by HBM (profiles/r1_history.md), so
+// shared memory is touched as little as possible -- events in (atomics), one 128-bit read + one zeroing write per
+// 4 positions -- and the depths go from registers to HBM with 256-bit stores (full 32-byte sectors).
+template <int PT>
+__global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 5 : 3)) k_depth_tiles(const TileParams P)
+{
+    constexpr int kThreads = kTile / PT, kWarps = kThreads / 32, kPadW = PT + 4;
+    constexpr int kShift = (PT == 32 ? 5 : 4);
+    __shared__ __align__(16) int s_diff[kThreads * kPadW];
     __shared__ uint32_t s_scan[40];
-    __shared__ int s_wcarry[kTileWarps];
+    __shared__ int s_wcarry[2][kWarps];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (uint32_t i = tid; i < kTileThreads * kPad / 4; i += kTileThreads) reinterpret_cast<int4*>(s_diff)[i] = make_int4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < kThreads * kPadW / 4; i += kThreads) reinterpret_cast<int4*>(s_diff)[i] = make_int4(0, 0, 0, 0);
     uint32_t t = blockIdx.x;
     uint4 desc = make_uint4(0, 0, 0, 0);
     uint2 er = make_uint2(0, 0);
     if (t < P.n_tiles) { desc = __ldg(P.tile_desc + t); er = __ldg(P.tile_ev + t); }
     __syncthreads();
 
-    while (t < P.n_tiles) {
+    for (uint32_t it = 0; t < P.n_tiles; it++) {
         // descriptor of the NEXT tile of this CTA: loaded now, used one iteration later
         const uint32_t tn = t + gridDim.x;
         uint4 desc_n = make_uint4(0, 0, 0, 0);
         uint2 er_n = make_uint2(0, 0);
         if (tn < P.n_tiles) { desc_n = __ldg(P.tile_desc + tn); er_n = __ldg(P.tile_ev + tn); }
 
-        const uint32_t n_here = desc.y, T0 = desc.z, T1 = desc.z + desc.y;
+        const uint32_t n_here = desc.y, T0 = desc.z;
         const uint32_t e1 = er.y < P.ev_cap ? er.y : P.ev_cap;
-        // ---- events of the records that overlap the tile (s_diff is all zero here)
-        // All loads of a batch are issued before the first shared-memory atomic, so a tile pays
-        // one memory round trip per 2048 events instead of one per 256.
+        // ---- events of the records that overlap the tile (s_diff is all zero here).  All loads of a batch are
+        // issued before the first shared-memory atomic: one memory round trip per batch.
+        constexpr int kBatch = 2048 / kThreads;                    // 2048 events per batch
         int mycarry = 0;
-        const int sgn = 1 - 2 * (int)((er.x + tid) & 1u);          // slot parity; the stride (256) is even
-        for (uint32_t base = er.x + tid; base < e1; base += kTileThreads * 8u) {
-            uint32_t p[8];
+        const int sgn = 1 - 2 * (int)((er.x + tid) & 1u);          // slot parity; the stride is even
+        for (uint32_t base = er.x + tid; base < e1; base += kThreads * kBatch) {
+            uint32_t p[kBatch];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { const uint32_t e = base + u * kTileThreads; p[u] = e < e1 ? __ldg(P.events + e) : kNone; }
+            for (int u = 0; u < kBatch; u++) { const uint32_t e = base + u * kThreads; p[u] = e < e1 ? __ldg(P.events + e) : kNone; }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (p[u] < T0) mycarry += sgn;
-                else if (p[u] < T1) atomicAdd(&s_diff[tile_slot(p[u] - T0)], sgn);
+            for (int u = 0; u < kBatch; u++) {
+                const uint32_t q = p[u] - T0;                      // wraps to a huge value for events left of the tile
+                mycarry += (p[u] < T0) ? sgn : 0;
+                if (q < n_here) atomicAdd(&s_diff[q + (q >> kShift) * 4u], sgn);
             }
         }
-        mycarry = (int)warp_sum_u32((uint32_t)mycarry);
-        if (lane == 0) s_wcarry[warp] = mycarry;
+        mycarry = (int)__reduce_add_sync(0xffffffffu, mycarry);
+        if (lane == 0) s_wcarry[it & 1][warp] = mycarry;
+        // pull the next tile's event slice towards L2 while this tile is scanned and written
+        if (tn < P.n_tiles) {
+            const uint32_t pe = er_n.y < P.ev_cap ? er_n.y : P.ev_cap;
+            for (uint32_t a = er_n.x + tid * 32u; a < pe; a += kThreads * 32u) prefetch_l2(P.events + a);
+        }
         __syncthreads();
-        // ---- thread-sequential prefix over 32 consecutive positions
-        int v[kPerThread];
-        int4* mine = reinterpret_cast<int4*>(s_diff + tid * kPad);
+        // ---- my PT positions: read once, zero behind (the barriers of the block scan below order this zeroing
+        // before any thread starts the next tile's atomics)
+        int v[PT];
+        int4* mine = reinterpret_cast<int4*>(s_diff + tid * kPadW);
         int tot = 0;
 #pragma unroll
-        for (int i = 0; i < kPerThread / 4; i++) {
+        for (int i = 0; i < PT / 4; i++) {
             const int4 x = mine[i];
+            mine[i] = make_int4(0, 0, 0, 0);
             v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
             tot += (x.x + x.y) + (x.z + x.w);
         }
@@ -249,47 +265,39 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_depth_tiles(const TileParam
         const uint32_t ex = block_excl_scan_u32((uint32_t)tot, s_scan, &dummy);
         int carry_in = 0;
 #pragma unroll
-        for (int i = 0; i < kTileWarps; i++) carry_in += s_wcarry[i];
+        for (int i = 0; i < kWarps; i++) carry_in += s_wcarry[it & 1][i];
         int run = carry_in + (int)ex;
-        // no depth in the tile exceeds carry_in + #events: 32 of them fit a 32-bit sum unless that bound is absurd
+        // no depth in the tile exceeds carry_in + #events: PT of them fit a 32-bit sum unless that bound is absurd
         const bool wide = (unsigned long long)(uint32_t)carry_in + (e1 - er.x) >= (1ull << 26);
-        const uint32_t q0 = tid * kPerThread;
-        const uint32_t cnt = q0 >= n_here ? 0u : (n_here - q0 < (uint32_t)kPerThread ? n_here - q0 : (uint32_t)kPerThread);
+        const uint32_t q0 = tid * PT;
+        const uint32_t cnt = q0 >= n_here ? 0u : (n_here - q0 < (uint32_t)PT ? n_here - q0 : (uint32_t)PT);
         uint32_t sum32 = 0, mn = 0xffffffffu, nz;
 #pragma unroll
-        for (int i = 0; i < kPerThread; i++) { run += v[i]; v[i] = run; sum32 += (uint32_t)run; mn = min(mn, (uint32_t)run); }
+        for (int i = 0; i < PT; i++) { run += v[i]; v[i] = run; sum32 += (uint32_t)run; mn = min(mn, (uint32_t)run); }
+        // ---- write my positions
+        uint32_t* out = P.depth + (size_t)t * kTile + q0;
+        if (cnt == (uint32_t)PT) {
+#pragma unroll
+            for (int i = 0; i < PT / 8; i++)
+                st_na_v8(out + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PT; i++) if ((uint32_t)i < cnt) out[i] = (uint32_t)v[i];
+        }
         unsigned long long sum = sum32;
         nz = cnt;
-        if (cnt != (uint32_t)kPerThread || mn == 0u || wide) {            // rare: ragged tile end, zero depth, absurd depth
+        if (cnt != (uint32_t)PT || mn == 0u || wide) {                    // rare: ragged tile end, zero depth, absurd depth
             sum = 0; nz = 0;
 #pragma unroll
-            for (int i = 0; i < kPerThread; i++) if ((uint32_t)i < cnt) { sum += (uint32_t)v[i]; nz += v[i] != 0; }
+            for (int i = 0; i < PT; i++) if ((uint32_t)i < cnt) { sum += (uint32_t)v[i]; nz += v[i] != 0; }
         }
-#pragma unroll
-        for (int i = 0; i < kPerThread / 4; i++) mine[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        sum = warp_sum_u64(sum); nz = warp_sum_u32(nz);
+        // warp totals with the redux unit: the 32-bit thread sums are split in 16-bit halves so they cannot overflow
+        if (__all_sync(0xffffffffu, sum <= 0xffffffffull)) {
+            const uint32_t s32 = (uint32_t)sum;
+            sum = (unsigned long long)__reduce_add_sync(0xffffffffu, s32 & 0xffffu) + ((unsigned long long)__reduce_add_sync(0xffffffffu, s32 >> 16) << 16);
+        } else sum = warp_sum_u64(sum);
+        nz = __reduce_add_sync(0xffffffffu, nz);
         if (lane == 0 && (sum | nz)) { atomicAdd(&P.tile_sum[t], sum); atomicAdd(&P.tile_nz[t], nz); }
-        // pull the next tile's event slice towards L2 while this tile is written out
-        if (tn < P.n_tiles) {
-            const uint32_t pe = er_n.y < P.ev_cap ? er_n.y : P.ev_cap;
-            for (uint32_t a = er_n.x + tid * 32u; a < pe; a += kTileThreads * 32u) prefetch_l2(P.events + a);
-        }
-        __syncthreads();
-        // ---- coalesced copy-out: each warp streams 8 rows of 128 positions, zeroing behind itself
-        uint32_t* out = P.depth + (size_t)t * kTile;
-#pragma unroll
-        for (int i = 0; i < kTile / 128 / kTileWarps; i++) {
-            const uint32_t q = (warp * (kTile / 128 / kTileWarps) + i) * 128u + lane * 4u;
-            int4* sp = reinterpret_cast<int4*>(s_diff + tile_slot(q));
-            const int4 x = *sp;
-            *sp = make_int4(0, 0, 0, 0);
-            if (q + 4 <= n_here) st_cs_v4(out + q, make_uint4((uint32_t)x.x, (uint32_t)x.y, (uint32_t)x.z, (uint32_t)x.w));
-            else if (q < n_here) {
-                const int xx[4] = {x.x, x.y, x.z, x.w};
-                for (uint32_t k = 0; k < 4 && q + k < n_here; k++) out[q + k] = (uint32_t)xx[k];
-            }
-        }
-        __syncthreads();
         t = tn; desc = desc_n; er = er_n;
     }
 }
@@ -326,8 +334,14 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
     if (b->n_tiles == 0) return CSV_OK;
     CSV_CUDA(cudaMemsetAsync(P.tile_sum, 0, (size_t)b->n_tiles * 8, ctx->stream));
     CSV_CUDA(cudaMemsetAsync(P.tile_nz, 0, (size_t)b->n_tiles * 4, ctx->stream));
-    uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 20 ? b->n_tiles : (uint32_t)ctx->sm_count * 20;
-    k_depth_tiles<<<grid, kTileThreads, 0, ctx->stream>>>(P);
+    static const int pt = getenv("CSV_TILE_PT") ? atoi(getenv("CSV_TILE_PT")) : 32;     // tuning knob: positions per thread
+    if (pt == 32) {
+        uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 20 ? b->n_tiles : (uint32_t)ctx->sm_count * 20;
+        k_depth_tiles<32><<<grid, kTile / 32, 0, ctx->stream>>>(P);
+    } else {
+        uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 12 ? b->n_tiles : (uint32_t)ctx->sm_count * 12;
+        k_depth_tiles<16><<<grid, kTile / 16, 0, ctx->stream>>>(P);
+    }
     k_region_stats<<<b->n_regions, 256, 0, ctx->stream>>>(b->d_reg_tab.as<uint32_t>(), P.tile_sum, P.tile_nz,
                                                           b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());
     ctx->launches += 2;

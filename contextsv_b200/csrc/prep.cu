@@ -20,7 +20,7 @@ __device__ __forceinline__ uint32_t find_owner(const TidDev td, const RegionDev*
     return kNone;
 }
 
-int launch_prep(csv_ctx* ctx, csv_batch* b)
+int launch_prep(csv_ctx* ctx, csv_batch* b, uint32_t min_mapq)
 {
     const uint64_t n_ops = b->n_ops;
     CSV_CUDA(cudaMemsetAsync(b->d_headbits.p, 0, n_ops / 8 + 16, ctx->stream));
@@ -52,7 +52,12 @@ int launch_prep(csv_ctx* ctx, csv_batch* b)
         m.x = (uint32_t)pos0[i];
         m.z = (uint32_t)flag[i] | ((uint32_t)mapq[i] << 16);
         if (t < 0 || (uint32_t)t >= n_tids || tids[t].count == 0) { m.y = 0u; m.w = kNone; }   // contig not requested
-        else { m.y = tids[t].map_size; m.w = find_owner(tids[t], regs, m.x + 1u); }
+        else {
+            m.y = tids[t].map_size; m.w = find_owner(tids[t], regs, m.x + 1u);
+            // the two record filters, decided once: depth (cnv_caller.cpp:491-495) and signatures (sv_caller.cpp:526)
+            if (!(m.z & kDepthSkipFlags)) m.z |= 1u << 30;
+            if (!(m.z & kSigSkipFlags) && (uint32_t)mapq[i] >= min_mapq && m.w != kNone) m.z |= 1u << 31;
+        }
         meta[k] = m;
         key[k] = ((unsigned long long)(uint32_t)t << 32) | (uint32_t)(m.x + 1u);     // coordinate sort key of the batch
         ne_idx[k] = (uint32_t)i;

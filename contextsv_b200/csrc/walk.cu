@@ -32,7 +32,7 @@ struct WalkParams {
     const uint32_t* cigar;
     uint32_t n_ops;
     const uint8_t* headbits;
-    const uint4* meta;          // {pos0, map_size (0 = contig not requested), flag | mapq << 16, owner region}
+    const uint4* meta;          // {pos0, map_size (0 = contig not requested), flag | mapq << 16 | depth-live << 30 | sig-ok << 31, owner region}
     WalkAgg* span_agg;          // per-span aggregate
     WalkAgg* span_pre;          // exclusive prefix of the span inside its chunk of kSpanChunk spans
     WalkAgg* chunk_agg;         // per-chunk aggregate, then exclusive prefix over chunks
@@ -40,7 +40,8 @@ struct WalkParams {
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1]
-    uint32_t* ref_end;      // [n_nonempty]
+    uint32_t* ref_total;    // [n_nonempty] reference bases consumed by the record
+    uint32_t n_meta;        // entries allocated in meta
     uint32_t min_len, min_mapq;
     uint32_t* scalars;
     SigRaw sig;
@@ -136,8 +137,17 @@ __global__ void __launch_bounds__(kWalkThreads) k_span_agg(const WalkParams P)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t span = blockIdx.x;
     const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread);
-    const WalkAgg inc = warp_incl_scan_agg(thread_aggregate(t), lane);
-    if (lane == 31) s_warp[warp] = inc;
+    const WalkAgg a = thread_aggregate(t);
+    // warp aggregate with the redux unit: plain sums for heads / events; (ref, qry) count from the last lane
+    // that saw a record head (that lane's own values already start at its last head)
+    WalkAgg w;
+    w.heads = __reduce_add_sync(0xffffffffu, a.heads);
+    w.ev = __reduce_add_sync(0xffffffffu, a.ev);
+    const uint32_t hm = __ballot_sync(0xffffffffu, a.heads != 0u);
+    const bool counts = hm == 0u || lane >= (uint32_t)(31 - __clz(hm));
+    w.ref = __reduce_add_sync(0xffffffffu, counts ? a.ref : 0u);
+    w.qry = __reduce_add_sync(0xffffffffu, counts ? a.qry : 0u);
+    if (lane == 0) s_warp[warp] = w;
     __syncthreads();
     if (tid == 0) {
         WalkAgg total = s_warp[0];
@@ -193,33 +203,34 @@ __global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, u
     }
 }
 
+constexpr int kMetaStage = 128;     // record metadata of a span staged in shared memory (typical span: ~35 records)
+
 // Replay of one thread's ops with their full prefixes.  FULL = all 8 ops valid (every span but the last).
+// Only the per-op work lives here: D/N gap events and (rarely) signatures.  The two events every record
+// owes at its first and last index are written by k_record_events from (ev_start, ref_total), so a record
+// head / tail costs this loop a handful of instructions instead of a divergent block.
 template <bool DEPTH, bool SIGS, bool FULL>
-__device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps& t, const WalkAgg T, uint32_t g0)
+__device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps& t, const WalkAgg T, uint32_t g0,
+                                            const uint4* s_meta, uint32_t k_first)
 {
     uint32_t k = T.heads - 1u, Rc = T.ref, Qc = T.qry, slot = T.ev;
-    uint4 m = make_uint4(0, 0, 0, kNone);
-    uint32_t a0 = 0;
-    bool live = false, sok = false;
-    auto load_meta = [&]() {
-        m = __ldg(P.meta + k);
-        const uint32_t flags = m.z & 0xffffu, mq = (m.z >> 16) & 0xffu;
-        a0 = m.x + 1u;                                                       // (uint32)pos + 1, cnv_caller.cpp:499
-        live = m.y != 0u && !(flags & kDepthSkipFlags) && a0 < m.y;
-        sok = m.w != kNone && !(flags & kSigSkipFlags) && mq >= P.min_mapq;
+    auto fetch = [&](uint32_t kk) -> uint4 {
+        const uint32_t l = kk - k_first;
+        return l < (uint32_t)kMetaStage ? s_meta[l] : __ldg(P.meta + kk);
     };
-    if (!(t.hb & 1u) && (FULL || t.n_valid)) load_meta();                    // first op continues an earlier record
+    uint4 m = make_uint4(0, 0, 0, kNone);
+    if (!(t.hb & 1u) && (FULL || t.n_valid)) m = fetch(k);                   // first op continues an earlier record
 #pragma unroll
     for (int j = 0; j < kWalkOpsPerThread; j++) {
         if (!FULL && (uint32_t)j >= t.n_valid) break;
         const uint32_t op = t.w[j] & 15u, len = t.w[j] >> 4;
         if ((t.hb >> j) & 1u) {                                              // first op of a record
             k++; Rc = 0; Qc = 0;
-            load_meta();
-            if (DEPTH) P.events[slot++] = live ? a0 : kNone;
+            m = fetch(k);
+            if (DEPTH) slot++;                                               // the record's +1 event (k_record_events)
         }
         const uint32_t pos1 = m.x + Rc + 1u;                                 // reference's `pos + 1` at this op (uint32)
-        if (SIGS && len >= P.min_len && bit_of(kSigMask, op) && sok) {
+        if (SIGS && len >= P.min_len && bit_of(kSigMask, op) && (m.z >> 31)) {
             const bool beyond = pos1 >= m.y;
             if (!(op == 4 && beyond)) {                                      // sv_caller.cpp:602-604
                 const uint32_t start = pos1, end = start + len - 1u;
@@ -240,7 +251,7 @@ __device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps
         if (DEPTH) {                                                         // D / N: -1 at its first index, +1 one past its last
             const bool gap = bit_of(kGapMask, op) && len;
             const uint32_t ia = pos1, ib = pos1 + len;                       // no overflow when ia < map_size <= 2^31
-            const bool in = live && ia < m.y;
+            const bool in = ((m.z >> 30) & 1u) && ia < m.y;
             const uint32_t va = in ? ia : kNone, vb = (in && ib < m.y) ? ib : kNone;
             if (gap) { P.events[slot] = va; P.events[slot + 1] = vb; }
             slot += gap ? 2u : 0u;
@@ -248,11 +259,9 @@ __device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps
         Rc += bit_of(kRefMask, op) * len;
         Qc += bit_of(kQryMask, op) * len;
         if (DEPTH && ((t.hb >> (j + 1)) & 1u)) {                             // last op of the record
-            const uint32_t ie = a0 + Rc;
-            const bool in = live && ie >= a0 && ie < m.y;                    // ie < a0: 32-bit wrap (absurd record)
-            P.events[slot++] = in ? ie : kNone;
+            slot++;                                                          // the record's -1 event (k_record_events)
             P.ev_start[k + 1] = slot;
-            P.ref_end[k] = live ? (in ? ie : m.y) : 0u;
+            P.ref_total[k] = Rc;
         }
     }
 }
@@ -261,12 +270,18 @@ template <bool DEPTH, bool SIGS>
 __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
 {
     __shared__ WalkAgg s_warp[kWalkThreads / 32];
+    __shared__ uint4 s_meta[kMetaStage];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t span = blockIdx.x;
     const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
-    // independent loads first: ops, head bits and the span's carry-in (one memory round trip)
+    // independent loads first: ops, head bits, the span's carry-in and the metadata of the span's records
     const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, g0);
     const WalkAgg span_excl = combine(P.chunk_agg[span / kSpanChunk], P.span_pre[span]);
+    const uint32_t k_first = span_excl.heads - 1u;                           // record running into this span (may be -1)
+    if (tid < (uint32_t)kMetaStage) {
+        const uint32_t kk = k_first + tid;
+        s_meta[tid] = (kk < P.n_meta) ? __ldg(P.meta + kk) : make_uint4(0, 0, 0, kNone);
+    }
     const WalkAgg inc = warp_incl_scan_agg(thread_aggregate(t), lane);
     const WalkAgg lane_excl = shfl_up1_agg(inc, lane);
     if (lane == 31) s_warp[warp] = inc;
@@ -274,8 +289,27 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
     WalkAgg wpre = {0, 0, 0, 0};
     for (uint32_t i = 0; i < warp; i++) wpre = combine(wpre, s_warp[i]);
     const WalkAgg T = combine(span_excl, combine(wpre, lane_excl));
-    if (t.n_valid == kWalkOpsPerThread) walk_replay<DEPTH, SIGS, true>(P, t, T, g0);
-    else walk_replay<DEPTH, SIGS, false>(P, t, T, g0);
+    if (t.n_valid == kWalkOpsPerThread) walk_replay<DEPTH, SIGS, true>(P, t, T, g0, s_meta, k_first);
+    else walk_replay<DEPTH, SIGS, false>(P, t, T, g0, s_meta, k_first);
+}
+
+// The two events every record owes: +1 at its first index, -1 one past its last covered base; plus ref_end,
+// the input of the prefix-max that finds the records overlapping a tile.
+__global__ void __launch_bounds__(256) k_record_events(const uint4* __restrict__ meta, const uint32_t* __restrict__ ev_start,
+                                                       const uint32_t* __restrict__ ref_total, const uint32_t* scalars,
+                                                       uint32_t* events, uint32_t* ref_end)
+{
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint4 m = __ldg(meta + k);
+        const uint32_t a0 = m.x + 1u;                                        // (uint32)pos + 1, cnv_caller.cpp:499
+        const bool live = ((m.z >> 30) & 1u) && a0 < m.y;
+        const uint32_t ie = a0 + ref_total[k];
+        const bool in = live && ie >= a0 && ie < m.y;                        // ie < a0: 32-bit wrap (absurd record)
+        events[ev_start[k]] = live ? a0 : kNone;
+        events[ev_start[k + 1] - 1u] = in ? ie : kNone;
+        ref_end[k] = live ? (in ? ie : m.y) : 0u;
+    }
 }
 
 int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
@@ -293,7 +327,8 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.ev_start = b->d_ev_start.as<uint32_t>();
-    P.ref_end = b->d_ref_end.as<uint32_t>();
+    P.ref_total = b->d_ref_total.as<uint32_t>();
+    P.n_meta = b->n_reads;
     P.min_len = p->min_len; P.min_mapq = p->min_mapq;
     P.scalars = b->d_scalars.as<uint32_t>();
     P.sig.key_hi = b->d_sig_hi.as<unsigned long long>();
@@ -312,6 +347,11 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     else if (p->want_depth) k_walk<true, false><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
     else k_walk<false, true><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
     ctx->launches += 4;
+    if (p->want_depth) {
+        const uint32_t grid = (b->n_reads + 255) / 256 < (uint32_t)ctx->sm_count * 16 ? (b->n_reads + 255) / 256 : (uint32_t)ctx->sm_count * 16;
+        k_record_events<<<grid, 256, 0, ctx->stream>>>(P.meta, P.ev_start, P.ref_total, P.scalars, P.events, b->d_ref_end.as<uint32_t>());
+        ctx->launches++;
+    }
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
