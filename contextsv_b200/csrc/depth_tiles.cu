@@ -10,20 +10,30 @@
 //   (a u64 prefix-max over records, then two binary searches per tile).  Their
 //   events are one contiguous slice of the event array.
 //
-// k_depth_tiles: one CTA owns one tile.  It zeroes a kTile-int difference array
-//   in shared memory and streams the slice: an event left of the tile adds its
-//   sign to the tile's carry-in (depth at T0), an event inside goes into the
-//   difference array with a shared-memory atomic, the rest is skipped.  Sign =
-//   parity of the event slot.  No inter-tile dependency, no global atomics.
-//   Then prefix sum + carry, every depth word is written exactly once with
-//   128-bit streaming stores, and sum(depth) / count(depth > 0) are reduced per
-//   tile and summed per region by k_region_stats.
+// k_depth_tiles16: one CTA owns one tile.  Events come in PAIRS: every record starts on an even slot and
+//   owns an even number of events, so slots (2i, 2i+1) are the two ends [p0, p1) of one covered stretch of a
+//   record: +1 at p0, -1 at p1.  The CTA streams the pairs of the slice with 64-bit loads: an end left of the
+//   tile moves the tile's carry-in (depth at T0), an end inside goes into a shared-memory difference array,
+//   the rest is skipped.  No inter-tile dependency, no global atomics.
+//   The difference array holds 16-bit counters, two per word, biased by 0x8000 so that no borrow ever crosses
+//   the halves: 16 KB per tile, a quarter of the shared-memory traffic of 32-bit counters.  A tile whose slice
+//   holds more than 32767 pairs (local coverage in the thousands) could overflow them: those tiles go to
+//   k_depth_tiles_wide (32-bit counters) through a list k_tile_ranges builds.
+//   Thread ownership is chosen for the memory system, not for the scan: lane l of warp w owns the four
+//   8-position chunks l, l+32, l+64, l+96 of the warp's 1024 positions, so every 128-bit shared-memory access
+//   and every 256-bit global store of a warp covers one contiguous kilobyte.  The prefix sum is IDP.2A
+//   (dot product of the two halves with {1,0} / {1,1}, accumulate in the running depth): one FMA-pipe
+//   instruction per position, beside the ALU-pipe reductions (sum, min).  Four warp scans (one per chunk row)
+//   + one redux per row order the chunks.  sum(depth) / count(depth > 0) are reduced per tile and summed per
+//   region by k_region_stats.
 #include "batch.cuh"
 #include "scan.cuh"
 
 #include <cstdlib>
 
 namespace csv {
+
+constexpr uint32_t kNarrowMaxPairs = 32767;     // a 16-bit counter cannot overflow below this many pairs per slice
 
 // ------------------------------------------------------- prefix max over records
 constexpr int kPmThreads = 256, kPmItems = 8, kPmTile = kPmThreads * kPmItems;
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
 // ------------------------------------------------------------ tile -> event slice
 __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_tiles, const unsigned long long* __restrict__ key,
                               const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
-                              const uint32_t* scalars, uint2* tile_ev)
+                              uint32_t* scalars, uint2* tile_ev, uint4* tile_q, uint32_t* wide_list)
 {
     const uint32_t n = scalars[SC_N_NONEMPTY];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
@@ -145,7 +155,10 @@ __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_ti
             if (pmax[mid] <= key_lo) lo = mid + 1; else hi = mid;
         }
         const uint32_t r_lo = lo;
-        tile_ev[t] = r_lo < r_hi ? make_uint2(ev_start[r_lo], ev_start[r_hi]) : make_uint2(0u, 0u);
+        const uint2 er = r_lo < r_hi ? make_uint2(ev_start[r_lo], ev_start[r_hi]) : make_uint2(0u, 0u);
+        tile_ev[t] = er;
+        tile_q[t] = make_uint4(d.z, d.y, er.x, er.y);
+        if (((er.y - er.x) >> 1) > kNarrowMaxPairs) wide_list[atomicAdd(&scalars[SC_N_WIDE], 1u)] = t;   // rare: 32-bit counters
     }
 }
 
@@ -167,7 +180,7 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
     }
     const uint32_t grid_t = (b->n_tiles + 255) / 256;
     k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), b->n_tiles, meta, pmax, b->d_ev_start.as<uint32_t>(),
-                                                  scalars, b->d_tile_ev.as<uint2>());
+                                                  scalars, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_wide_list.as<uint32_t>());
     ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
@@ -177,12 +190,15 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
 struct TileParams {
     const uint4* tile_desc;          // static per tile: {region, positions in tile, T0, tid}
     const uint2* tile_ev;            // event slice [x, y)
+    const uint4* tile_q;             // {T0, positions, x, y}: all the 16-bit kernel needs, one 128-bit load
     const uint32_t* events;
     uint32_t ev_cap;
     uint32_t* depth;                 // n_tiles * kTile words
     unsigned long long* tile_sum;    // per-tile partial reductions (no contended atomics)
     uint32_t* tile_nz;
     uint32_t n_tiles;
+    const uint32_t* wide_list;       // tiles that need 32-bit counters
+    const uint32_t* scalars;
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -193,64 +209,80 @@ __device__ __forceinline__ void st_na_v8(uint32_t* p, int a, int b, int c, int d
                  "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
 }
 
-// One CTA per tile of kTile positions, PT consecutive positions per thread (kTile / PT threads).
-// Shared-memory rows of PT words are padded by 4 words: 16-byte aligned and conflict-free for the 128-bit
-// accesses of their owner (PT = 32: stride 36 words; PT = 16: stride 20 words).
-// The kernel is limited by the L1/shared-memory pipe and by latency, not by HBM (profiles/r1_history.md), so
-// shared memory is touched as little as possible -- events in (atomics), one 128-bit read + one zeroing write per
-// 4 positions -- and the depths go from registers to HBM with 256-bit stores (full 32-byte sectors).
+// 32-bit counters, for the tiles on the wide list (and the reference implementation of the tile logic).
+// One CTA per tile, PT consecutive positions per thread; shared-memory rows of PT words are padded by 4 words:
+// 16-byte aligned and conflict-free for the 128-bit accesses of their owner.
 template <int PT>
-__global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 5 : 3)) k_depth_tiles(const TileParams P)
+__global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 4 : 2)) k_depth_tiles_wide(const TileParams P)
 {
     constexpr int kThreads = kTile / PT, kWarps = kThreads / 32, kPadW = PT + 4;
     constexpr int kShift = (PT == 32 ? 5 : 4);
+    constexpr int kPP = 1024 / kThreads;                           // pairs per thread and batch (2048 events per batch)
+    static_assert(kWarps <= 32, "one lane per warp in the offset reduction");
     __shared__ __align__(16) int s_diff[kThreads * kPadW];
-    __shared__ uint32_t s_scan[40];
-    __shared__ int s_wcarry[2][kWarps];
+    __shared__ int s_wtot[kWarps], s_wcar[kWarps];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(P.events);
+    const uint32_t pair_cap = P.ev_cap >> 1;
 
     for (uint32_t i = tid; i < kThreads * kPadW / 4; i += kThreads) reinterpret_cast<int4*>(s_diff)[i] = make_int4(0, 0, 0, 0);
-    uint32_t t = blockIdx.x;
+    const uint32_t n_list = P.scalars[SC_N_WIDE];
+    uint32_t li = blockIdx.x;
+    uint32_t t = li < n_list ? P.wide_list[li] : P.n_tiles;
     uint4 desc = make_uint4(0, 0, 0, 0);
     uint2 er = make_uint2(0, 0);
-    if (t < P.n_tiles) { desc = __ldg(P.tile_desc + t); er = __ldg(P.tile_ev + t); }
+    uint2 pf[kPP];
+#pragma unroll
+    for (int u = 0; u < kPP; u++) pf[u] = make_uint2(kNone, kNone);
+    if (t < P.n_tiles) {
+        desc = __ldg(P.tile_desc + t); er = __ldg(P.tile_ev + t);
+        const uint32_t pb = er.x >> 1, pe = min(er.y >> 1, pair_cap);
+#pragma unroll
+        for (int u = 0; u < kPP; u++) { const uint32_t i = pb + tid + u * kThreads; if (i < pe) pf[u] = __ldg(pairs + i); }
+    }
     __syncthreads();
 
-    for (uint32_t it = 0; t < P.n_tiles; it++) {
-        // descriptor of the NEXT tile of this CTA: loaded now, used one iteration later
-        const uint32_t tn = t + gridDim.x;
+    while (t < P.n_tiles) {
+        // descriptor of the NEXT tile of this CTA: loaded now, used in the middle of this iteration
+        li += gridDim.x;
+        const uint32_t tn = li < n_list ? P.wide_list[li] : P.n_tiles;
         uint4 desc_n = make_uint4(0, 0, 0, 0);
         uint2 er_n = make_uint2(0, 0);
         if (tn < P.n_tiles) { desc_n = __ldg(P.tile_desc + tn); er_n = __ldg(P.tile_ev + tn); }
 
         const uint32_t n_here = desc.y, T0 = desc.z;
-        const uint32_t e1 = er.y < P.ev_cap ? er.y : P.ev_cap;
-        // ---- events of the records that overlap the tile (s_diff is all zero here).  All loads of a batch are
-        // issued before the first shared-memory atomic: one memory round trip per batch.
-        constexpr int kBatch = 2048 / kThreads;                    // 2048 events per batch
+        const uint32_t pb = er.x >> 1, pe = min(er.y >> 1, pair_cap);
+        // ---- stretches of the records that overlap the tile (s_diff is all zero here)
         int mycarry = 0;
-        const int sgn = 1 - 2 * (int)((er.x + tid) & 1u);          // slot parity; the stride is even
-        for (uint32_t base = er.x + tid; base < e1; base += kThreads * kBatch) {
-            uint32_t p[kBatch];
+        auto apply = [&](const uint2 pr) {
+            const uint32_t q0 = pr.x - T0, q1 = pr.y - T0;         // wrap to huge values left of the tile
+            mycarry += (pr.x < T0) ? 1 : 0;
+            mycarry -= (pr.y < T0) ? 1 : 0;
+            if (q0 < n_here) atomicAdd(&s_diff[q0 + (q0 >> kShift) * 4u], 1);
+            if (q1 < n_here) atomicAdd(&s_diff[q1 + (q1 >> kShift) * 4u], -1);
+        };
 #pragma unroll
-            for (int u = 0; u < kBatch; u++) { const uint32_t e = base + u * kThreads; p[u] = e < e1 ? __ldg(P.events + e) : kNone; }
+        for (int u = 0; u < kPP; u++) apply(pf[u]);
+        for (uint32_t base = pb + kThreads * kPP; base < pe; base += kThreads * kPP) {      // rare: > 2048 events
+            uint2 p[kPP];
 #pragma unroll
-            for (int u = 0; u < kBatch; u++) {
-                const uint32_t q = p[u] - T0;                      // wraps to a huge value for events left of the tile
-                mycarry += (p[u] < T0) ? sgn : 0;
-                if (q < n_here) atomicAdd(&s_diff[q + (q >> kShift) * 4u], sgn);
-            }
+            for (int u = 0; u < kPP; u++) { const uint32_t i = base + tid + u * kThreads; p[u] = i < pe ? __ldg(pairs + i) : make_uint2(kNone, kNone); }
+#pragma unroll
+            for (int u = 0; u < kPP; u++) apply(p[u]);
+        }
+        // first batch of the next tile: in flight while this tile is scanned and written
+#pragma unroll
+        for (int u = 0; u < kPP; u++) pf[u] = make_uint2(kNone, kNone);
+        if (tn < P.n_tiles) {
+            const uint32_t nb = er_n.x >> 1, ne = min(er_n.y >> 1, pair_cap);
+#pragma unroll
+            for (int u = 0; u < kPP; u++) { const uint32_t i = nb + tid + u * kThreads; if (i < ne) pf[u] = __ldg(pairs + i); }
         }
         mycarry = (int)__reduce_add_sync(0xffffffffu, mycarry);
-        if (lane == 0) s_wcarry[it & 1][warp] = mycarry;
-        // pull the next tile's event slice towards L2 while this tile is scanned and written
-        if (tn < P.n_tiles) {
-            const uint32_t pe = er_n.y < P.ev_cap ? er_n.y : P.ev_cap;
-            for (uint32_t a = er_n.x + tid * 32u; a < pe; a += kThreads * 32u) prefetch_l2(P.events + a);
-        }
+        if (lane == 0) s_wcar[warp] = mycarry;
         __syncthreads();
-        // ---- my PT positions: read once, zero behind (the barriers of the block scan below order this zeroing
-        // before any thread starts the next tile's atomics)
+        // ---- my PT positions: read once, zero behind (the second barrier orders this zeroing before any thread
+        // starts the next tile's atomics)
         int v[PT];
         int4* mine = reinterpret_cast<int4*>(s_diff + tid * kPadW);
         int tot = 0;
@@ -261,14 +293,21 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 5 : 3)) k_depth_tiles(
             v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
             tot += (x.x + x.y) + (x.z + x.w);
         }
-        uint32_t dummy;
-        const uint32_t ex = block_excl_scan_u32((uint32_t)tot, s_scan, &dummy);
-        int carry_in = 0;
+        int incl = tot;
 #pragma unroll
-        for (int i = 0; i < kWarps; i++) carry_in += s_wcarry[it & 1][i];
-        int run = carry_in + (int)ex;
+        for (int d = 1; d < 32; d <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        // depth at the tile start + everything in the warps before mine, in one redux
+        int part = 0;
+        if (lane < (uint32_t)kWarps) part = s_wcar[lane] + (lane < warp ? s_wtot[lane] : 0);
+        const int woff = (int)__reduce_add_sync(0xffffffffu, part);
+        int carry_in = 0;
+        if (lane < (uint32_t)kWarps) carry_in = s_wcar[lane];
+        carry_in = (int)__reduce_add_sync(0xffffffffu, carry_in);
+        int run = woff + incl - tot;
         // no depth in the tile exceeds carry_in + #events: PT of them fit a 32-bit sum unless that bound is absurd
-        const bool wide = (unsigned long long)(uint32_t)carry_in + (e1 - er.x) >= (1ull << 26);
+        const bool wide = (unsigned long long)(uint32_t)carry_in + (er.y - er.x) >= (1ull << 26);
         const uint32_t q0 = tid * PT;
         const uint32_t cnt = q0 >= n_here ? 0u : (n_here - q0 < (uint32_t)PT ? n_here - q0 : (uint32_t)PT);
         uint32_t sum32 = 0, mn = 0xffffffffu, nz;
@@ -302,6 +341,156 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 5 : 3)) k_depth_tiles(
     }
 }
 
+// ---------------------------------------------------------------- 16-bit counters
+constexpr uint32_t kBias2 = 0x80008000u;       // both halves of a counter word at zero
+
+__device__ __forceinline__ int dp2(uint32_t w, int sel, int c) { return __dp2a_lo((int)w, sel, c); }   // c + lo*sel.b0 + hi*sel.b1
+
+// predicated shared-memory reduction: no branch, no generic-address arithmetic
+__device__ __forceinline__ void red_shared_if_lt(uint32_t q, uint32_t n, uint32_t saddr, uint32_t val)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}" ::"r"(q), "r"(n), "r"(saddr), "r"(val) : "memory");
+}
+// one step of an inclusive warp scan: SHFL + predicated add
+__device__ __forceinline__ int scan_step(int x, int d)
+{
+    asm volatile("{\n\t.reg .s32 t;\n\t.reg .pred p;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.s32 %0, %0, t;\n\t}" : "+r"(x) : "r"(d));
+    return x;
+}
+
+__global__ void __launch_bounds__(256, 4) k_depth_tiles16(const TileParams P)
+{
+    constexpr int kThreads = 256, kWarps = kThreads / 32, kPP = 1024 / kThreads;
+    static_assert(kTile == kWarps * 1024, "a warp owns 1024 positions: 4 rows of 32 chunks of 8");
+    __shared__ __align__(16) uint32_t s_d[kTile / 2];
+    __shared__ int s_wtot[kWarps], s_wcar[kWarps];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(P.events);
+    const uint32_t pair_cap = P.ev_cap >> 1;
+    const uint4 bias4 = make_uint4(kBias2, kBias2, kBias2, kBias2);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_d);
+
+    for (uint32_t i = tid; i < kTile / 8; i += kThreads) reinterpret_cast<uint4*>(s_d)[i] = bias4;
+    // tile descriptors {T0, positions, first event, end event} run two tiles ahead of the tile being scanned
+    const uint32_t g = gridDim.x;
+    uint32_t t = blockIdx.x;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    uint4 cur = t < P.n_tiles ? __ldg(P.tile_q + t) : zero4;
+    uint4 nxt = t + g < P.n_tiles ? __ldg(P.tile_q + t + g) : zero4;
+    uint2 pf[kPP];
+    {
+        const uint32_t pb = cur.z >> 1, pe = min(cur.w >> 1, pair_cap);
+#pragma unroll
+        for (int u = 0; u < kPP; u++) { const uint32_t i = pb + tid + u * kThreads; pf[u] = i < pe ? __ldg(pairs + i) : make_uint2(kNone, kNone); }
+    }
+    __syncthreads();
+
+    while (t < P.n_tiles) {
+        const uint4 nn = t + 2 * g < P.n_tiles ? __ldg(P.tile_q + t + 2 * g) : zero4;
+        const uint32_t T0 = cur.x, n_here = cur.y;
+        const uint32_t pb = cur.z >> 1, pe = min(cur.w >> 1, pair_cap);
+        const bool narrow = ((cur.w - cur.z) >> 1) <= kNarrowMaxPairs;    // CTA-uniform; wide tiles belong to k_depth_tiles_wide
+        // ---- stretches of the records that overlap the tile (every counter is at its bias here)
+        int mycarry = 0;
+        auto apply = [&](const uint2 pr) {
+            const uint32_t q0 = pr.x - T0, q1 = pr.y - T0;         // wrap to huge values left of the tile
+            mycarry += (pr.x < T0) ? 1 : 0;
+            mycarry -= (pr.y < T0) ? 1 : 0;
+            red_shared_if_lt(q0, n_here, (sbase + 2u * q0) & ~3u, (q0 & 1u) * 0x0000ffffu + 1u);             // +1 in its half
+            red_shared_if_lt(q1, n_here, (sbase + 2u * q1) & ~3u, (q1 & 1u) * 0xffff0001u + 0xffffffffu);     // -1 in its half
+        };
+        if (narrow) {
+#pragma unroll
+            for (int u = 0; u < kPP; u++) apply(pf[u]);
+            for (uint32_t base = pb + kThreads * kPP; base < pe; base += kThreads * kPP) {      // > 2048 events
+                uint2 p[kPP];
+#pragma unroll
+                for (int u = 0; u < kPP; u++) { const uint32_t i = base + tid + u * kThreads; p[u] = i < pe ? __ldg(pairs + i) : make_uint2(kNone, kNone); }
+#pragma unroll
+                for (int u = 0; u < kPP; u++) apply(p[u]);
+            }
+        }
+        // first batch of the next tile: in flight while this tile is scanned and written
+        {
+            const uint32_t nb = nxt.z >> 1, ne = min(nxt.w >> 1, pair_cap);
+#pragma unroll
+            for (int u = 0; u < kPP; u++) { const uint32_t i = nb + tid + u * kThreads; pf[u] = i < ne ? __ldg(pairs + i) : make_uint2(kNone, kNone); }
+        }
+        if (!narrow) { t += g; cur = nxt; nxt = nn; continue; }
+        mycarry = (int)__reduce_add_sync(0xffffffffu, mycarry);
+        if (lane == 0) s_wcar[warp] = mycarry;
+        __syncthreads();
+        // ---- my four chunks: read once, reset behind (the second barrier orders the reset before any thread
+        // starts the next tile's atomics)
+        uint4* rowp = reinterpret_cast<uint4*>(s_d) + warp * 128 + lane;
+        uint32_t w[16];
+        int tot[4], inc[4], R[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 x = rowp[32 * i];
+            rowp[32 * i] = bias4;
+            w[4 * i] = x.x ^ kBias2; w[4 * i + 1] = x.y ^ kBias2; w[4 * i + 2] = x.z ^ kBias2; w[4 * i + 3] = x.w ^ kBias2;
+            tot[i] = dp2(w[4 * i + 3], 0x0101, dp2(w[4 * i + 2], 0x0101, dp2(w[4 * i + 1], 0x0101, dp2(w[4 * i], 0x0101, 0))));
+        }
+        // Two rows per scan: every partial sum of counters is bounded by the pairs of the slice (<= 32767), so the
+        // integer a + 65536 b carries both exactly
+        int s01 = tot[0] + (tot[1] << 16), s23 = tot[2] + (tot[3] << 16);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { s01 = scan_step(s01, d); s23 = scan_step(s23, d); }
+        inc[0] = (int)(short)s01; inc[1] = (s01 - inc[0]) >> 16;
+        inc[2] = (int)(short)s23; inc[3] = (s23 - inc[2]) >> 16;
+        const int r01 = __shfl_sync(0xffffffffu, s01, 31), r23 = __shfl_sync(0xffffffffu, s23, 31);
+        R[0] = (int)(short)r01; R[1] = (r01 - R[0]) >> 16;
+        R[2] = (int)(short)r23; R[3] = (r23 - R[2]) >> 16;
+        if (lane == 0) s_wtot[warp] = (R[0] + R[1]) + (R[2] + R[3]);
+        __syncthreads();
+        // depth at the tile start + everything in the warps before mine, in one redux
+        int part = 0;
+        if (lane < (uint32_t)kWarps) part = s_wcar[lane] + (lane < warp ? s_wtot[lane] : 0);
+        const int woff = (int)__reduce_add_sync(0xffffffffu, part);
+        int base[4];
+        base[0] = woff + inc[0] - tot[0];
+        base[1] = woff + R[0] + inc[1] - tot[1];
+        base[2] = woff + R[0] + R[1] + inc[2] - tot[2];
+        base[3] = woff + R[0] + R[1] + R[2] + inc[3] - tot[3];
+        // depths never exceed carry-in + pairs <= 65534 here: 32-bit sums of 32 of them cannot overflow
+        const uint32_t q_first = warp * 1024u + lane * 8u;                 // my chunk of row 0; row i is 256 positions further
+        uint32_t* out = P.depth + (size_t)t * kTile + q_first;
+        uint32_t sum32 = 0, mn = 0xffffffffu;
+        const bool full = q_first + 3u * 256u + 8u <= n_here;              // all four chunks inside the tile
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int v[8], run = base[i];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { v[2 * k] = dp2(w[4 * i + k], 0x0001, run); run = v[2 * k + 1] = dp2(w[4 * i + k], 0x0101, run); }
+                st_na_v8(out + 256 * i, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) { sum32 += (uint32_t)v[k]; mn = min(mn, (uint32_t)v[k]); }
+            }
+        }
+        uint32_t nz = 32;
+        if (!full || mn == 0u) {                                            // ragged tile end or zero depth: count exactly
+            sum32 = 0; nz = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int v[8], run = base[i];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { v[2 * k] = dp2(w[4 * i + k], 0x0001, run); run = v[2 * k + 1] = dp2(w[4 * i + k], 0x0101, run); }
+                const uint32_t qc = q_first + 256u * i;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (qc + k < n_here) { if (!full) out[256 * i + k] = (uint32_t)v[k]; sum32 += (uint32_t)v[k]; nz += v[k] != 0; }
+            }
+        }
+        // warp totals with the redux unit: thread sums <= 32 * 65534 < 2^21, so the warp sum fits 32 bits
+        sum32 = __reduce_add_sync(0xffffffffu, sum32);
+        nz = __reduce_add_sync(0xffffffffu, nz);
+        if (lane == 0 && (sum32 | nz)) { atomicAdd(&P.tile_sum[t], (unsigned long long)sum32); atomicAdd(&P.tile_nz[t], nz); }
+        t += g; cur = nxt; nxt = nn;
+    }
+}
+
 // one CTA per region: sum the per-tile partials (cnv_caller.cpp:534-535)
 __global__ void __launch_bounds__(256) k_region_stats(const uint32_t* __restrict__ reg_tile_base, const unsigned long long* __restrict__ tile_sum,
                                                        const uint32_t* __restrict__ tile_nz, unsigned long long* reg_sum, uint32_t* reg_nz)
@@ -325,6 +514,7 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
     TileParams P;
     P.tile_desc = b->d_tile_desc.as<uint4>();
     P.tile_ev = b->d_tile_ev.as<uint2>();
+    P.tile_q = b->d_tile_q.as<uint4>();
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.depth = b->d_depth.as<uint32_t>();
@@ -334,14 +524,14 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
     if (b->n_tiles == 0) return CSV_OK;
     CSV_CUDA(cudaMemsetAsync(P.tile_sum, 0, (size_t)b->n_tiles * 8, ctx->stream));
     CSV_CUDA(cudaMemsetAsync(P.tile_nz, 0, (size_t)b->n_tiles * 4, ctx->stream));
-    static const int pt = getenv("CSV_TILE_PT") ? atoi(getenv("CSV_TILE_PT")) : 32;     // tuning knob: positions per thread
-    if (pt == 32) {
-        uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 20 ? b->n_tiles : (uint32_t)ctx->sm_count * 20;
-        k_depth_tiles<32><<<grid, kTile / 32, 0, ctx->stream>>>(P);
-    } else {
-        uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * 12 ? b->n_tiles : (uint32_t)ctx->sm_count * 12;
-        k_depth_tiles<16><<<grid, kTile / 16, 0, ctx->stream>>>(P);
-    }
+    P.wide_list = b->d_wide_list.as<uint32_t>();
+    P.scalars = b->d_scalars.as<uint32_t>();
+    static const int mult = getenv("CSV_TILE_GRID") ? atoi(getenv("CSV_TILE_GRID")) : 20;   // tuning knob: CTAs per SM in the grid
+    const uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * mult ? b->n_tiles : (uint32_t)ctx->sm_count * mult;
+    k_depth_tiles16<<<grid, 256, 0, ctx->stream>>>(P);
+    const uint32_t grid_w = b->n_tiles < (uint32_t)ctx->sm_count * 4 ? b->n_tiles : (uint32_t)ctx->sm_count * 4;
+    k_depth_tiles_wide<32><<<grid_w, kTile / 32, 0, ctx->stream>>>(P);    // exits at once when the wide list is empty
+    ctx->launches++;
     k_region_stats<<<b->n_regions, 256, 0, ctx->stream>>>(b->d_reg_tab.as<uint32_t>(), P.tile_sum, P.tile_nz,
                                                           b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());
     ctx->launches += 2;

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import util
+from util import M, I, D, N, S, H, P, EQ, X
 from contextsv_b200 import api
 from contextsv_b200._capi import CsvReads, CsvRegion, CsvSigs, check, lib, ptr, reads_struct
 
@@ -89,6 +90,24 @@ def test_long_reads_spanning_many_spans(ctx, oracle):
     r = util.synth_reads([3_000_000], seed=21, profile=1, coverage=6.0, read_len_mean=50000, indel_rate=0.1, indel_len_max=4, n_sv=60)
     assert (np.diff(r["cig_off"]).max()) > 5000
     check_contigs(ctx, oracle, r, [3_000_000])
+
+
+def test_pileups_deep_coverage(ctx, oracle):
+    """Thousands of records starting / ending / deleting at the same base: tiles whose slice holds more than
+    32767 pairs take the 32-bit-counter kernel, the others run the 16-bit one close to its bound."""
+    from oracle.oracle_py import make_reads
+    rng = np.random.default_rng(77)
+    for n, L in ((70_000, 30_000), (20_000, 30_000), (33_000, 9_000)):
+        pos0 = np.sort(np.concatenate([np.full(n // 2, 4000), rng.integers(0, L - 3000, n - n // 2)])).astype(np.int32)
+        cig = []
+        for p in pos0:
+            if p == 4000:
+                cig.append([(100, M), (7, D), (300, M)])                      # same start, same gap, same end
+            else:
+                a = int(rng.integers(1, 800))
+                cig.append([(a, M), (int(rng.integers(1, 30)), D), (int(rng.integers(1, 900)), EQ)] if rng.random() < 0.5 else [(a, M)])
+        r = make_reads(pos0, cig)
+        check_contigs(ctx, oracle, r, [L])
 
 
 def test_synthetic_hifi_multi_contig(ctx, oracle):
