@@ -6,7 +6,7 @@ namespace csv {
 constexpr uint32_t kNone = 0xffffffffu;
 
 // u32 slots of csv_batch::d_scalars
-enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_COUNT = 16 };
+enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_COUNT = 16 };
 
 struct SigRaw {          // emission-order signature records (device)
     unsigned long long* key_hi;   // owner region << 32 | start
@@ -42,7 +42,7 @@ struct csv_batch {
     csv::DevBuf d_span_agg, d_span_pre, d_span_status;
     // depth
     csv::DevBuf d_events;    // uint32 depth-map indices, sign = slot parity
-    csv::DevBuf d_ev_start, d_ref_total, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
+    csv::DevBuf d_ev_start, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
     csv::DevBuf d_depth, d_sum, d_nz, d_tile_desc, d_tile_ev, d_tile_sum, d_tile_nz, d_wide_list, d_tile_q;
     // signatures
     csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_qpos, d_sig_kind, d_sig_payload;
@@ -51,7 +51,7 @@ struct csv_batch {
     void release(csv::DevPool* pool = nullptr) {
         csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
                               &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status,
-                              &d_events, &d_ev_start, &d_ref_total, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
+                              &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
         for (auto* b : all) b->release(pool);

@@ -86,6 +86,10 @@ static int check_overflow(csv_ctx* ctx, csv_batch* b, uint32_t* sc)
         set_error("records are not sorted by (contig, position): the depth path needs coordinate-sorted input, like the indexed BAM the reference requires");
         return CSV_ERR_ARG;
     }
+    if (sc[SC_ABSURD]) {
+        set_error("a record consumes 2^31 or more reference bases: not a valid alignment (BAM positions are int32)");
+        return CSV_ERR_LIMIT;
+    }
     if (b->have_sigs && sc[SC_N_SIG] > b->sig_cap) {
         set_error("signatures: %u emitted, batch capacity is %llu", sc[SC_N_SIG], (unsigned long long)b->sig_cap);
         return CSV_ERR_CAPACITY;
@@ -280,7 +284,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
     CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / 2048 + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
     CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
-    CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ref_total.ensure(nr * 4 + 16, &ctx->pool));
+    CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pmax.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_pmax_part.ensure((nr / 2048 + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_tile_desc.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_ev.ensure(nt * 8 + 16, &ctx->pool));
     CSV_TRY(b->d_wide_list.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_q.ensure(nt * 16 + 16, &ctx->pool));

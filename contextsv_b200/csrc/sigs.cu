@@ -27,7 +27,8 @@ __global__ void k_sig_iota(uint32_t* val, const uint32_t* scalars)
 struct GatherParams {
     const unsigned long long *hi, *lo;
     const uint32_t* val;
-    const uint32_t *raw_k, *raw_qpos;
+    const uint32_t* raw_k;
+    const WalkAgg *span_pre, *chunk_agg;      // pre-pass prefixes: .qry = query consumed since the last record head before the span
     const uint8_t* raw_kind;
     const uint32_t* ne_idx;
     const unsigned long long* cig_off;
@@ -51,8 +52,24 @@ __global__ void k_sig_gather(const GatherParams P)
         const uint32_t read = P.ne_idx[k];
         const unsigned long long c0 = P.cig_off[read];
         const uint8_t kr = P.raw_kind[slot];
-        uint32_t qpos = P.raw_qpos[slot];
-        if (kr & 0x80u) {
+        uint32_t qpos;
+        if (!(kr & 0x80u)) {
+            // query offset of the op (sv_caller.cpp:547,653-655): the pre-pass knows it at the start of the op's
+            // span; the ops between the span start (or the record head, if later) and g are summed here
+            const uint32_t sp = g / (uint32_t)kWalkSpan;
+            unsigned long long from = c0;
+            uint32_t q = 0;
+            if (c0 < (unsigned long long)sp * kWalkSpan) {
+                const WalkAgg ch = P.chunk_agg[sp / 2048u], pr = P.span_pre[sp];
+                q = pr.heads ? pr.qry : ch.qry + pr.qry;
+                from = (unsigned long long)sp * kWalkSpan;
+            }
+            for (unsigned long long o = from; o < (unsigned long long)g; o++) {
+                const uint32_t w = P.cigar[o];
+                if ((kQryMask >> (w & 15u)) & 1u) q += w >> 4;
+            }
+            qpos = q;
+        } else {
             // exact sequential restatement (sv_caller.cpp:563-655) for the rare records that reach or
             // pass the end of their contig: a soft clip there skips the query advance (:602-604)
             const uint4 m = P.meta[k];
@@ -102,7 +119,7 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
     CSV_TRY(radix_sort_pairs(ctx, sb, cap, scalars + SC_N_SIG_EFF, mask));
     GatherParams P;
     P.hi = sb.hi; P.lo = sb.lo; P.val = sb.val;
-    P.raw_k = b->d_sig_k.as<uint32_t>(); P.raw_qpos = b->d_sig_qpos.as<uint32_t>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
+    P.raw_k = b->d_sig_k.as<uint32_t>(); P.span_pre = b->d_span_pre.as<WalkAgg>(); P.chunk_agg = b->d_span_status.as<WalkAgg>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
     P.ne_idx = b->d_ne_idx.as<uint32_t>(); P.cig_off = b->d_cig_off.as<unsigned long long>(); P.cigar = b->d_cigar.as<uint32_t>();
     P.meta = b->d_meta.as<uint4>(); P.tids = b->d_tids.as<TidDev>(); P.scalars = scalars; P.cap = cap;
     P.o_start = b->d_out_start.as<uint32_t>(); P.o_end = b->d_out_end.as<uint32_t>(); P.o_read = b->d_out_read.as<uint32_t>();

@@ -3,26 +3,22 @@
 //
 // Work is cut into spans of kWalkSpan consecutive ops regardless of record
 // boundaries, so HiFi (64 ops/record) and ONT (1e4+ ops/record) batches are
-// equally balanced.  Per span:
-//   1. each thread loads 8 ops with two 128-bit loads plus the 9 head bits that
-//      say where records start;
-//   2. a segmented scan (reset at record heads) of (reference, query)
-//      consumption runs thread -> warp -> CTA; the carry-in of every span comes
-//      from a cheap aggregate pre-pass (k_span_agg) and a two-level scan over the
-//      span aggregates -- deterministic, no spinning on other CTAs.  Plain sums of
-//      head bits (-> record index) and of depth-event counts (-> event slot) ride
-//      along;
-//   3. every op now knows its reference position, query offset and event slot:
-//        - I/D/S ops >= min_len become signatures;
-//        - depth events are written in op order: a record contributes +1 at its
-//          first index, -1/+1 around every D/N gap, -1 one past its last base --
-//          exactly the bases its M/=/X ops cover (cnv_caller.cpp:507-519).
-//          Every record writes an EVEN number of events that alternate +,-,+,-...
-//          so the sign of an event is the parity of its slot: the event list is
-//          a plain array of uint32 depth-map indices (kNone = clipped/filtered),
-//          grouped by record, hence sorted by contig and (nearly) by position.
-// Per record the walk also leaves ev_start[k] (first event slot) and
-// ref_end[k] (one past the last covered index, 0 if filtered) for the tile kernel.
+// equally balanced.  A cheap pre-pass (k_span_agg) reduces every span to one
+// aggregate -- record heads, depth events, reference / query consumed since the
+// last record head -- and a two-level scan turns the aggregates into the carry-in
+// of every span: deterministic, no spinning on other CTAs.  k_walk then gives
+// every op its reference position and event slot (see the comment above it):
+//   - I/D/S ops >= min_len become signatures (query_pos is filled in by
+//     k_sig_gather from the pre-pass's query prefix);
+//   - depth events are written in op order: a record contributes +1 at its first
+//     index, -1/+1 around every D/N gap, -1 one past its last base -- exactly the
+//     bases its M/=/X ops cover (cnv_caller.cpp:507-519).  Every record writes an
+//     EVEN number of events that alternate +,-,+,-... so the sign of an event is
+//     the parity of its slot: the event list is a plain array of uint32 depth-map
+//     indices, grouped by record, hence sorted by contig and (nearly) by position.
+//     Events are not clipped to the map: a tile ignores what lies outside it.
+// Per record the walk also leaves ev_start[k] (first event slot) and ref_end[k]
+// (one past the last covered index, 0 if the record takes no part) for the tiles.
 #include "batch.cuh"
 #include "scan.cuh"
 
@@ -39,15 +35,14 @@ struct WalkParams {
     uint32_t n_spans;
     uint32_t* events;
     uint32_t ev_cap;
-    uint32_t* ev_start;     // [n_nonempty + 1]
-    uint32_t* ref_total;    // [n_nonempty] reference bases consumed by the record
+    uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
+    uint32_t* ref_end;      // [n_nonempty] one past the last covered index, clipped to the map; 0 = takes no part in the depth
     uint32_t n_meta;        // entries allocated in meta
-    uint32_t min_len, min_mapq;
+    uint32_t min_len, sig_lut;
     uint32_t* scalars;
     SigRaw sig;
     uint32_t sig_cap;
     uint32_t* reg_sig_cnt;
-    int want_depth, want_sigs;
 };
 
 constexpr int kSpanChunk = 2048;    // spans per scan chunk (256 threads x 8)
@@ -105,10 +100,30 @@ __device__ __forceinline__ ThreadOps load_ops(const uint32_t* __restrict__ cigar
     return t;
 }
 
-__device__ __forceinline__ uint32_t bit_of(uint32_t mask, uint32_t op) { return (mask >> op) & 1u; }
+// Class bit of a CIGAR word without isolating its op nibble: the per-op bit masks are replicated in both
+// 16-bit halves, so a funnel shift by (w & 31) lands on the right bit whatever the length's low bit is.
+constexpr uint32_t kRefLut = kRefMask | (kRefMask << 16);
+constexpr uint32_t kQryLut = kQryMask | (kQryMask << 16);
+constexpr uint32_t kGapLut = kGapMask | (kGapMask << 16);
+constexpr uint32_t kSigLut = kSigMask | (kSigMask << 16);
+__device__ __forceinline__ uint32_t class_bit(uint32_t lut, uint32_t w) { return __funnelshift_r(lut, lut, w) & 1u; }
 
-// Aggregate of the 8 ops of one thread.  Heads / event counts are popcounts of the head bits;
-// (ref, qry) only count the ops from the LAST record head of the thread onwards.
+// one step of an inclusive warp scan: SHFL + predicated add
+__device__ __forceinline__ uint32_t scan_step_u32(uint32_t x, int d)
+{
+    asm volatile("{\n\t.reg .u32 t;\n\t.reg .pred p;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}" : "+r"(x) : "r"(d));
+    return x;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan_fast(uint32_t x)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) x = scan_step_u32(x, d);
+    return x;
+}
+
+// Aggregate of the 8 ops of one thread for the pre-pass.  Heads / event counts are popcounts of the head
+// bits; (ref, qry) only count the ops from the LAST record head of the thread onwards.  Every D/N op owns two
+// events, zero-length ones included (their -1/+1 land on the same index and cancel).
 __device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t)
 {
     WalkAgg a;
@@ -119,11 +134,11 @@ __device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t)
     uint32_t ref = 0, qry = 0, gaps = 0;
 #pragma unroll
     for (int j = 0; j < kWalkOpsPerThread; j++) {
-        const uint32_t op = t.w[j] & 15u;                   // ops beyond n_valid are zero words: M of length 0
-        const uint32_t len = (j >= lh) ? (t.w[j] >> 4) : 0u;
-        ref += bit_of(kRefMask, op) * len;
-        qry += bit_of(kQryMask, op) * len;
-        gaps += bit_of(kGapMask, op) & (uint32_t)((t.w[j] >> 4) != 0u);
+        const uint32_t w = t.w[j];                          // ops beyond n_valid are zero words: M of length 0
+        const uint32_t len = (j >= lh) ? (w >> 4) : 0u;
+        ref += class_bit(kRefLut, w) * len;
+        qry += class_bit(kQryLut, w) * len;
+        gaps += class_bit(kGapLut, w);
     }
     a.ref = ref; a.qry = qry;
     a.ev = a.heads + __popc((t.hb >> 1) & vmask) + 2u * gaps;
@@ -203,44 +218,118 @@ __global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, u
     }
 }
 
-constexpr int kMetaStage = 128;     // record metadata of a span staged in shared memory (typical span: ~35 records)
-
-// Replay of one thread's ops with their full prefixes.  FULL = all 8 ops valid (every span but the last).
-// Only the per-op work lives here: D/N gap events and (rarely) signatures.  The two events every record
-// owes at its first and last index are written by k_record_events from (ev_start, ref_total), so a record
-// head / tail costs this loop a handful of instructions instead of a divergent block.
-template <bool DEPTH, bool SIGS, bool FULL>
-__device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps& t, const WalkAgg T, uint32_t g0,
-                                            const uint4* s_meta, uint32_t k_first)
+// c[b] for a run-time b in 0..8 without local memory
+__device__ __forceinline__ uint32_t sel9(const uint32_t (&c)[kWalkOpsPerThread + 1], uint32_t b)
 {
-    uint32_t k = T.heads - 1u, Rc = T.ref, Qc = T.qry, slot = T.ev;
-    auto fetch = [&](uint32_t kk) -> uint4 {
-        const uint32_t l = kk - k_first;
-        return l < (uint32_t)kMetaStage ? s_meta[l] : __ldg(P.meta + kk);
-    };
-    uint4 m = make_uint4(0, 0, 0, kNone);
-    if (!(t.hb & 1u) && (FULL || t.n_valid)) m = fetch(k);                   // first op continues an earlier record
+    const bool b0 = b & 1u, b1 = b & 2u, b2 = b & 4u;
+    const uint32_t a0 = b0 ? c[1] : c[0], a1 = b0 ? c[3] : c[2], a2 = b0 ? c[5] : c[4], a3 = b0 ? c[7] : c[6];
+    const uint32_t d0 = b1 ? a1 : a0, d1 = b1 ? a3 : a2;
+    const uint32_t r = b2 ? d1 : d0;
+    return (b & 8u) ? c[8] : r;
+}
+
+constexpr uint32_t kDeadPos = 0x80000000u;   // "first index" of a record that takes no part in the depth: every event
+                                             // of such a record lands at or beyond 2^31 >= any map_size and no tile sees it
+
+// The walk proper.  One CTA per span of 2048 ops, 8 consecutive ops per thread.
+//   A. thread-local exclusive prefix c[0..8] of reference consumption (NOT reset at record heads), bit masks of
+//      the D/N ops and of the signature candidates.
+//   B. warp scans with SHFL + predicated add: one packed scan for (record heads, event counts), one plain scan of
+//      the reference totals; the segmented part -- reference consumed since the last record head -- comes from
+//      one ballot and one extra shuffle.  Warp aggregates meet in shared memory; the span's carry-in comes from
+//      the pre-pass.
+//   C. replay: position of op j = c[j] + bias, where bias = (first index of the record) - (c at its head); a
+//      record head only swaps the bias (one predicated shared-memory load).  D/N ops store their two events;
+//      nothing is clipped here -- the tile kernel ignores what lies outside its tile, and records that do not
+//      count get kDeadPos as their first index.  Candidate signatures branch to a rare path.
+//   D. record boundaries (about one per warp and pass for long reads) are handled in a sparse loop: the last
+//      event, ref_end and ev_start of the record that ends, the first event of the record that begins.
+template <bool DEPTH, bool SIGS>
+__global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
+{
+    __shared__ uint32_t s_pos1[kWalkSpan + 4];                               // first depth index of the span's records
+    __shared__ uint4 s_wagg[kWalkThreads / 32];                              // {heads << 16 | events, ref total, ref since last head, has head}
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t span = blockIdx.x;
+    const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
+    // independent loads first: ops, head bits, the span's carry-in and the first index of the span's records
+    const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, g0);
+    const WalkAgg span_excl = combine(P.chunk_agg[span / kSpanChunk], P.span_pre[span]);
+    const uint32_t k_first = span_excl.heads - 1u;                           // record running into this span (may be -1)
+    const uint32_t n_rec = P.span_agg[span].heads + 1u;
+    for (uint32_t i = tid; i < n_rec; i += kWalkThreads) {
+        const uint32_t kk = k_first + i;
+        uint32_t v = kDeadPos;
+        if (kk < P.n_meta) {
+            const uint4 m = __ldg(P.meta + kk);
+            if (((m.z >> 30) & 1u) && m.x + 1u < m.y) v = m.x + 1u;          // (uint32)pos + 1, cnv_caller.cpp:499
+        }
+        s_pos1[i] = v;
+    }
+    // ---- A
+    uint32_t c[kWalkOpsPerThread + 1];
+    uint32_t gm = 0, sm = 0;
+    c[0] = 0;
+    const uint32_t thr = P.min_len << 4;
 #pragma unroll
     for (int j = 0; j < kWalkOpsPerThread; j++) {
-        if (!FULL && (uint32_t)j >= t.n_valid) break;
-        const uint32_t op = t.w[j] & 15u, len = t.w[j] >> 4;
-        if ((t.hb >> j) & 1u) {                                              // first op of a record
-            k++; Rc = 0; Qc = 0;
-            m = fetch(k);
-            if (DEPTH) slot++;                                               // the record's +1 event (k_record_events)
-        }
-        const uint32_t pos1 = m.x + Rc + 1u;                                 // reference's `pos + 1` at this op (uint32)
-        if (SIGS && len >= P.min_len && bit_of(kSigMask, op) && (m.z >> 31)) {
-            const bool beyond = pos1 >= m.y;
-            if (!(op == 4 && beyond)) {                                      // sv_caller.cpp:602-604
+        const uint32_t w = t.w[j];
+        c[j + 1] = c[j] + class_bit(kRefLut, w) * (w >> 4);
+        if (DEPTH) gm |= class_bit(kGapLut, w) << j;
+        if (SIGS) sm |= (w >= thr ? class_bit(P.sig_lut, w) : 0u) << j;
+    }
+    const uint32_t vmask = (1u << t.n_valid) - 1u, hbv = t.hb & vmask, tails = (t.hb >> 1) & vmask;
+    const uint32_t heads = __popc(hbv);
+    const uint32_t evn = heads + __popc(tails) + 2u * __popc(gm);
+    const int lh = 31 - __clz(hbv);
+    const uint32_t reftail = c[kWalkOpsPerThread] - (lh < 0 ? 0u : sel9(c, (uint32_t)lh));
+    // ---- B
+    const uint32_t he = (heads << 16) | evn;                                 // a span holds <= 2048 heads and <= 8192 events
+    const uint32_t he_inc = warp_incl_scan_fast(he);
+    const uint32_t S = warp_incl_scan_fast(c[kWalkOpsPerThread]);
+    const uint32_t hm = __ballot_sync(0xffffffffu, heads != 0u);
+    const uint32_t lower = hm & lanemask_lt();
+    const uint32_t X = reftail - S;
+    const uint32_t Xs = __shfl_sync(0xffffffffu, X, (31 - __clz(lower)) & 31);
+    const uint32_t Xl = __shfl_sync(0xffffffffu, X, (31 - __clz(hm)) & 31);
+    if (lane == 31) s_wagg[warp] = make_uint4(he_inc, S, hm ? S + Xl : S, hm != 0u);
+    __syncthreads();
+    uint4 wa = make_uint4(0, 0, 0, 0);
+    if (lane < kWalkThreads / 32) wa = s_wagg[lane];
+    const uint32_t he_pre = __reduce_add_sync(0xffffffffu, lane < warp ? wa.x : 0u);
+    const uint32_t wh = __ballot_sync(0xffffffffu, lane < warp && wa.w);
+    uint32_t carry;                                                          // reference consumed since the last head before my warp
+    if (wh) {
+        const uint32_t lw = 31 - __clz(wh);
+        carry = __shfl_sync(0xffffffffu, wa.z, lw) + __reduce_add_sync(0xffffffffu, (lane > lw && lane < warp) ? wa.y : 0u);
+    } else carry = span_excl.ref + __reduce_add_sync(0xffffffffu, lane < warp ? wa.y : 0u);
+    if (t.n_valid == 0) return;
+    const uint32_t he_ex = he_pre + (he_inc - he);
+    const uint32_t T_ev = span_excl.ev + (he_ex & 0xffffu);
+    uint32_t kl = he_ex >> 16;                                               // s_pos1 slot of the record running into my ops
+    const uint32_t rc_entry = lower ? (S - c[kWalkOpsPerThread]) + Xs : carry + (S - c[kWalkOpsPerThread]);
+    const uint32_t kl_entry = kl, bias_entry = s_pos1[kl] + rc_entry;
+    uint32_t bias = bias_entry;
+    // ---- C
+    uint32_t* evp = P.events + T_ev;
+#pragma unroll
+    for (int j = 0; j < kWalkOpsPerThread; j++) {
+        if ((hbv >> j) & 1u) { kl++; bias = s_pos1[kl] - c[j]; if (DEPTH) evp += (j ? 2 : 1); }      // tail event of the record before + my head event
+        if (DEPTH && ((gm >> j) & 1u)) { evp[0] = c[j] + bias; evp[1] = c[j + 1] + bias; evp += 2; }   // D / N: -1 at its first index, +1 one past its last
+        if (SIGS && ((sm >> j) & 1u)) {                                      // rare: I / D / S of at least min_len
+            const uint32_t w = t.w[j], op = w & 15u, len = w >> 4;
+            const uint32_t k = k_first + kl;
+            const uint4 m = __ldg(P.meta + k);
+            if (m.z >> 31) {
+                const uint32_t pos1 = m.x + 1u + (c[j] + bias - s_pos1[kl]);  // reference's `pos + 1` at this op (uint32)
+                const bool beyond = pos1 >= m.y;
                 const uint32_t start = pos1, end = start + len - 1u;
-                if (start <= end) {                                          // sv_object.cpp:25-28
+                if (!(op == 4 && beyond) && start <= end) {                  // sv_caller.cpp:602-604, sv_object.cpp:25-28
                     const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
                     if (sl < P.sig_cap) {
                         P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
                         P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
                         P.sig.k[sl] = k;
-                        P.sig.qpos[sl] = Qc;
                         const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
                         P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
                         atomicAdd(&P.reg_sig_cnt[m.w], 1u);
@@ -248,67 +337,34 @@ __device__ __forceinline__ void walk_replay(const WalkParams& P, const ThreadOps
                 }
             }
         }
-        if (DEPTH) {                                                         // D / N: -1 at its first index, +1 one past its last
-            const bool gap = bit_of(kGapMask, op) && len;
-            const uint32_t ia = pos1, ib = pos1 + len;                       // no overflow when ia < map_size <= 2^31
-            const bool in = ((m.z >> 30) & 1u) && ia < m.y;
-            const uint32_t va = in ? ia : kNone, vb = (in && ib < m.y) ? ib : kNone;
-            if (gap) { P.events[slot] = va; P.events[slot + 1] = vb; }
-            slot += gap ? 2u : 0u;
-        }
-        Rc += bit_of(kRefMask, op) * len;
-        Qc += bit_of(kQryMask, op) * len;
-        if (DEPTH && ((t.hb >> (j + 1)) & 1u)) {                             // last op of the record
-            slot++;                                                          // the record's -1 event (k_record_events)
-            P.ev_start[k + 1] = slot;
-            P.ref_total[k] = Rc;
-        }
     }
-}
-
-template <bool DEPTH, bool SIGS>
-__global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
-{
-    __shared__ WalkAgg s_warp[kWalkThreads / 32];
-    __shared__ uint4 s_meta[kMetaStage];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t span = blockIdx.x;
-    const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
-    // independent loads first: ops, head bits, the span's carry-in and the metadata of the span's records
-    const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, g0);
-    const WalkAgg span_excl = combine(P.chunk_agg[span / kSpanChunk], P.span_pre[span]);
-    const uint32_t k_first = span_excl.heads - 1u;                           // record running into this span (may be -1)
-    if (tid < (uint32_t)kMetaStage) {
-        const uint32_t kk = k_first + tid;
-        s_meta[tid] = (kk < P.n_meta) ? __ldg(P.meta + kk) : make_uint4(0, 0, 0, kNone);
-    }
-    const WalkAgg inc = warp_incl_scan_agg(thread_aggregate(t), lane);
-    const WalkAgg lane_excl = shfl_up1_agg(inc, lane);
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    WalkAgg wpre = {0, 0, 0, 0};
-    for (uint32_t i = 0; i < warp; i++) wpre = combine(wpre, s_warp[i]);
-    const WalkAgg T = combine(span_excl, combine(wpre, lane_excl));
-    if (t.n_valid == kWalkOpsPerThread) walk_replay<DEPTH, SIGS, true>(P, t, T, g0, s_meta, k_first);
-    else walk_replay<DEPTH, SIGS, false>(P, t, T, g0, s_meta, k_first);
-}
-
-// The two events every record owes: +1 at its first index, -1 one past its last covered base; plus ref_end,
-// the input of the prefix-max that finds the records overlapping a tile.
-__global__ void __launch_bounds__(256) k_record_events(const uint4* __restrict__ meta, const uint32_t* __restrict__ ev_start,
-                                                       const uint32_t* __restrict__ ref_total, const uint32_t* scalars,
-                                                       uint32_t* events, uint32_t* ref_end)
-{
-    const uint32_t n = scalars[SC_N_NONEMPTY];
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint4 m = __ldg(meta + k);
-        const uint32_t a0 = m.x + 1u;                                        // (uint32)pos + 1, cnv_caller.cpp:499
-        const bool live = ((m.z >> 30) & 1u) && a0 < m.y;
-        const uint32_t ie = a0 + ref_total[k];
-        const bool in = live && ie >= a0 && ie < m.y;                        // ie < a0: 32-bit wrap (absurd record)
-        events[ev_start[k]] = live ? a0 : kNone;
-        events[ev_start[k + 1] - 1u] = in ? ie : kNone;
-        ref_end[k] = live ? (in ? ie : m.y) : 0u;
+    // ---- D
+    if (DEPTH) {
+        uint32_t bm = t.hb & ((2u << t.n_valid) - 1u);                       // bit b: a record ends with op b-1 and (b < n_valid) one begins at op b
+        uint32_t klb = kl_entry, biasb = bias_entry;
+        while (bm) {
+            const uint32_t b = __ffs(bm) - 1u;
+            bm &= bm - 1u;
+            const uint32_t cb = sel9(c, b);
+            const uint32_t low = (1u << b) - 1u;
+            const uint32_t slot = T_ev + __popc((hbv & low) | ((tails & low) << 9)) + 2u * __popc(gm & low);   // after the tail event of op b-1
+            if (b) {
+                const uint32_t kt = k_first + klb;
+                const uint4 m = __ldg(P.meta + kt);
+                const bool live = ((m.z >> 30) & 1u) && m.x + 1u < m.y;
+                const uint32_t ie = cb + biasb;                              // one past the last covered index
+                if (ie - s_pos1[klb] >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
+                P.events[slot - 1u] = ie;
+                P.ref_end[kt] = live ? (ie < m.y ? ie : m.y) : 0u;
+                P.ev_start[kt + 1u] = slot;
+            }
+            if (b < t.n_valid) {
+                klb++;
+                const uint32_t p1 = s_pos1[klb];
+                P.events[slot] = p1;
+                biasb = p1 - cb;
+            }
+        }
     }
 }
 
@@ -327,9 +383,10 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.ev_start = b->d_ev_start.as<uint32_t>();
-    P.ref_total = b->d_ref_total.as<uint32_t>();
+    P.ref_end = b->d_ref_end.as<uint32_t>();
     P.n_meta = b->n_reads;
-    P.min_len = p->min_len; P.min_mapq = p->min_mapq;
+    P.min_len = p->min_len < (1u << 28) ? p->min_len : 0u;
+    P.sig_lut = p->min_len < (1u << 28) ? kSigLut : 0u;                      // CIGAR lengths have 28 bits: nothing can reach a larger threshold
     P.scalars = b->d_scalars.as<uint32_t>();
     P.sig.key_hi = b->d_sig_hi.as<unsigned long long>();
     P.sig.key_lo = b->d_sig_lo.as<unsigned long long>();
@@ -338,7 +395,6 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.sig.kind = b->d_sig_kind.as<uint8_t>();
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
-    P.want_depth = p->want_depth; P.want_sigs = p->want_sigs;
     const uint32_t n_chunks = (b->n_spans + kSpanChunk - 1) / kSpanChunk;
     k_span_agg<<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
     k_span_scan_local<<<n_chunks, 256, 0, ctx->stream>>>(P);
@@ -347,11 +403,6 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     else if (p->want_depth) k_walk<true, false><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
     else k_walk<false, true><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
     ctx->launches += 4;
-    if (p->want_depth) {
-        const uint32_t grid = (b->n_reads + 255) / 256 < (uint32_t)ctx->sm_count * 16 ? (b->n_reads + 255) / 256 : (uint32_t)ctx->sm_count * 16;
-        k_record_events<<<grid, 256, 0, ctx->stream>>>(P.meta, P.ev_start, P.ref_total, P.scalars, P.events, b->d_ref_end.as<uint32_t>());
-        ctx->launches++;
-    }
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
