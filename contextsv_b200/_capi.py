@@ -42,7 +42,7 @@ class CsvSigs(C.Structure):
 # every entry point include/contextsv_b200.h declares for libcontextsv_b200.so
 EXPORTS = [
     "csv_ctx_create", "csv_ctx_destroy", "csv_ctx_sync", "csv_last_error", "csv_version", "csv_host_alloc", "csv_host_free",
-    "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
+    "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_ctx_set_pipeline_chunks", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
     "csv_depth_stats", "csv_depth_fetch", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
     "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_largest_cluster", "csv_window_sums",
 ]
@@ -71,6 +71,7 @@ def lib():
         L.csv_ctx_destroy.argtypes = [C.c_void_p]
         L.csv_ctx_sync.argtypes = [C.c_void_p]
         L.csv_timer_begin.argtypes = [C.c_void_p]
+        L.csv_ctx_set_pipeline_chunks.argtypes = [C.c_void_p, C.c_int]
         L.csv_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.csv_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.csv_profile_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]

@@ -59,6 +59,10 @@ class Context:
         check(lib().csv_timer_end(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def set_pipeline_chunks(self, n):
+        """Batches uploaded from now on are scanned in up to n pipelined chunks of whole contigs."""
+        check(lib().csv_ctx_set_pipeline_chunks(self.h, int(n)))
+
     def profile_enable(self, on=True):
         check(lib().csv_profile_enable(self.h, int(on)))
 

@@ -17,6 +17,18 @@ struct SigRaw {          // emission-order signature records (device)
 };
 }  // namespace csv
 
+namespace csv {
+// One stage of the pipelined pass: the walk covers spans [span0, span1); once the walk of the NEXT chunk is done,
+// every record of the contigs [first_tid, next chunk's first_tid) has its events, and the tiles of their regions run
+// on the tile stream beside the walk of later chunks.
+struct PipeChunk {
+    uint32_t span0 = 0, span1 = 0;
+    uint32_t first_tid = 0;
+    uint32_t rec_upper = 0;                                   // records of the chunk's contigs (upper bound: empty ones included)
+    std::vector<std::pair<uint32_t, uint32_t>> tiles;         // contiguous tile ranges of the chunk's regions
+};
+}  // namespace csv
+
 struct csv_batch {
     uint32_t n_reads = 0;
     uint64_t n_ops = 0;
@@ -39,7 +51,9 @@ struct csv_batch {
     csv::DevBuf d_regs, d_tids, d_reg_sig_cnt;
     csv::DevBuf d_reg_tab;   // u32 [tile_base (n_regions + 1) | len (n_regions)], caller order
     // walk
-    csv::DevBuf d_span_agg, d_span_pre, d_span_status;
+    csv::DevBuf d_span_agg, d_span_pre, d_span_status, d_scan_carry;
+    std::vector<csv::PipeChunk> chunks;
+    csv::DevBuf d_chunk_tid, d_chunk_bounds;
     // depth
     csv::DevBuf d_events;    // uint32 depth-map indices, sign = slot parity
     csv::DevBuf d_ev_start, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
@@ -50,7 +64,7 @@ struct csv_batch {
 
     void release(csv::DevPool* pool = nullptr) {
         csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
-                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status,
+                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_chunk_tid, &d_chunk_bounds,
                               &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_qpos,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
@@ -61,9 +75,12 @@ struct csv_batch {
 namespace csv {
 // kernels' host launchers (each enqueues on ctx->stream and bumps ctx->launches)
 int launch_prep(csv_ctx* ctx, csv_batch* b, uint32_t min_mapq);
-int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p);
-int launch_tile_ranges(csv_ctx* ctx, csv_batch* b);
-int launch_depth_tiles(csv_ctx* ctx, csv_batch* b);
+int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1);
+int launch_chunk_bounds(csv_ctx* ctx, csv_batch* b);
+int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t chunk);
+int launch_depth_begin(csv_ctx* ctx, csv_batch* b);
+int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t chunk);
+int launch_depth_finish(csv_ctx* ctx, csv_batch* b);
 int launch_sig_finish(csv_ctx* ctx, csv_batch* b);
 int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts);
 int launch_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv, const uint32_t* d_start,

@@ -3,6 +3,7 @@
 #include "batch.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <stdarg.h>
 
@@ -63,10 +64,16 @@ int side_fork(csv_ctx* ctx)
 }
 int side_join(csv_ctx* ctx)
 {
-    if (!ctx->side_busy) return CSV_OK;
-    CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-    CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0));
-    ctx->side_busy = false;
+    if (ctx->side_busy) {
+        CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0));
+        ctx->side_busy = false;
+    }
+    if (ctx->tile_busy) {
+        CSV_CUDA(cudaEventRecord(ctx->ev_tile_join, ctx->tile_stream));
+        CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_tile_join, 0));
+        ctx->tile_busy = false;
+    }
     return CSV_OK;
 }
 
@@ -121,11 +128,14 @@ int csv_ctx_create(int device, csv_ctx** out)
     csv_ctx* ctx = new csv_ctx;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (getenv("CSV_CHUNKS")) ctx->pipe_chunks = std::max(1, atoi(getenv("CSV_CHUNKS")));
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CSV_CUDA(cudaStreamCreateWithFlags(&ctx->tile_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->main_stream;
     CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_tile_join, cudaEventDisableTiming));
     CSV_CUDA(cudaEventCreate(&ctx->ev0));
     CSV_CUDA(cudaEventCreate(&ctx->ev1));
     CSV_CUDA(cudaHostAlloc(&ctx->pinned_small, 4096, cudaHostAllocDefault));
@@ -138,8 +148,12 @@ void csv_ctx_destroy(csv_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamSynchronize(ctx->tile_stream);
     cudaStreamSynchronize(ctx->main_stream);
     ctx->pool.trim();
+    for (auto e : ctx->ev_chunk) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->ev_tile_join);
+    cudaStreamDestroy(ctx->tile_stream);
     for (auto& v : ctx->stage_events) for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto e : ctx->spare_events) cudaEventDestroy(e);
     ctx->tickets.release(); ctx->scan_status.release();
@@ -184,6 +198,13 @@ int csv_timer_end(csv_ctx* ctx, float* ms_out)
     return CSV_OK;
 }
 uint64_t csv_ctx_launch_count(const csv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int csv_ctx_set_pipeline_chunks(csv_ctx* ctx, int n_chunks)
+{
+    if (!ctx || n_chunks < 1) { set_error("csv_ctx_set_pipeline_chunks: need a context and n_chunks >= 1"); return CSV_ERR_ARG; }
+    ctx->pipe_chunks = n_chunks;
+    return CSV_OK;
+}
 
 int csv_profile_enable(csv_ctx* ctx, int on)
 {
@@ -269,6 +290,40 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     for (uint32_t i = 0; i < n_regions; i++) reg_tab[n_regions + 1 + i] = regions[i].end - regions[i].beg;
 
     b->n_spans = (uint32_t)((r->n_ops + kWalkSpan - 1) / kWalkSpan);
+    // ---- pipeline chunks: cuts only between contigs, walk ranges aligned to the chunks of the span scan
+    {
+        const int want = ctx->pipe_chunks;
+        std::vector<uint32_t> utid;
+        for (uint32_t s = 0; s < n_regions; s++) { const uint32_t t = (uint32_t)regions[order[s]].tid; if (utid.empty() || utid.back() != t) utid.push_back(t); }
+        const uint32_t min_spans = std::max<uint32_t>((uint32_t)kSpanChunk, b->n_spans / (uint32_t)std::max(want, 1));
+        PipeChunk cur;
+        cur.span0 = 0; cur.first_tid = 0;
+        uint64_t rec0 = 0;
+        if (r->tid && want > 1) {
+            for (size_t i = 1; i < utid.size(); i++) {
+                const int32_t* it = std::lower_bound(r->tid, r->tid + r->n_reads, (int32_t)utid[i]);
+                const uint64_t ri = (uint64_t)(it - r->tid);
+                const uint64_t cut = (r->cig_off[ri] / kWalkSpan / kSpanChunk) * kSpanChunk;
+                if (cut >= (uint64_t)cur.span0 + min_spans && cut + min_spans <= b->n_spans) {
+                    cur.span1 = (uint32_t)cut; cur.rec_upper = (uint32_t)(ri - rec0);
+                    b->chunks.push_back(cur);
+                    cur = PipeChunk(); cur.span0 = (uint32_t)cut; cur.first_tid = utid[i]; rec0 = ri;
+                }
+            }
+        }
+        cur.span1 = b->n_spans; cur.rec_upper = (uint32_t)(r->n_reads - rec0);
+        b->chunks.push_back(cur);
+        for (size_t c = 0; c < b->chunks.size(); c++) {
+            const uint32_t lo = b->chunks[c].first_tid, hi = c + 1 < b->chunks.size() ? b->chunks[c + 1].first_tid : 0xffffffffu;
+            for (uint32_t i = 0; i < n_regions; i++) {
+                const uint32_t t = (uint32_t)regions[i].tid;
+                if (t < lo || t >= hi || b->tile_base[i] == b->tile_base[i + 1]) continue;
+                auto& tl = b->chunks[c].tiles;
+                if (!tl.empty() && tl.back().second == b->tile_base[i]) tl.back().second = b->tile_base[i + 1];
+                else tl.emplace_back(b->tile_base[i], b->tile_base[i + 1]);
+            }
+        }
+    }
     b->ev_cap = 2 * (r->n_ops + (uint64_t)r->n_reads) + 2;      // exact bound: 2 per record + 2 per D/N op
     b->sig_cap = std::max<uint64_t>(16, std::min<uint64_t>(r->n_ops, std::max<uint64_t>(1u << 20, r->n_ops / 16)));
 
@@ -282,7 +337,9 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev), &ctx->pool)); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev), &ctx->pool));
     CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4, &ctx->pool)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4, &ctx->pool));
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
-    CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / 2048 + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
+    CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / kSpanChunk + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
+    CSV_TRY(b->d_scan_carry.ensure(sizeof(WalkAgg), &ctx->pool));
+    CSV_TRY(b->d_chunk_tid.ensure(b->chunks.size() * 4 + 16, &ctx->pool)); CSV_TRY(b->d_chunk_bounds.ensure(b->chunks.size() * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
     CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pmax.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_pmax_part.ensure((nr / 2048 + 2) * 8, &ctx->pool));
@@ -312,6 +369,9 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_CUDA(cudaMemcpyAsync(b->d_regs.p, regs.data(), regs.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemcpyAsync(b->d_tids.p, tids.data(), tids.size() * sizeof(TidDev), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemcpyAsync(b->d_reg_tab.p, reg_tab.data(), reg_tab.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<uint32_t> chunk_tid(b->chunks.size());
+    for (size_t c = 0; c < b->chunks.size(); c++) chunk_tid[c] = b->chunks[c].first_tid;
+    CSV_CUDA(cudaMemcpyAsync(b->d_chunk_tid.p, chunk_tid.data(), chunk_tid.size() * 4, cudaMemcpyHostToDevice, st));
     std::vector<uint4> tile_desc(nt);
     for (uint32_t i = 0; i < n_regions; i++) {
         const uint32_t len = regions[i].end - regions[i].beg;
@@ -344,7 +404,43 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
     if (p->want_depth) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));
     { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b, p->min_mapq)); }
-    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p)); }
+    // The pass is pipelined over chunks of whole contigs.  Main stream: the walk, chunk after chunk.  Tile stream:
+    // tile ranges + depth tiles of chunk c as soon as the walk of chunk c + 1 is through (the records at the end of
+    // chunk c's contigs share their last span-scan chunk with chunk c + 1).  The walk is bound by instruction issue,
+    // the tiles by HBM writes: side by side they cost little more than the tiles alone.
+    const uint32_t nc = (uint32_t)b->chunks.size();
+    while (ctx->ev_chunk.size() < nc) {
+        cudaEvent_t e = nullptr;
+        CSV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_chunk.push_back(e);
+    }
+    if (p->want_depth) {
+        CSV_TRY(launch_chunk_bounds(ctx, b));
+        CSV_TRY(side_fork(ctx));
+        CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_fork, 0));
+        TileScope ts(ctx);
+        CSV_TRY(launch_depth_begin(ctx, b));
+    }
+    for (uint32_t c = 0; c < nc; c++) {
+        { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1)); }
+        CSV_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->main_stream));
+        if (p->want_depth && (c >= 1 || nc == 1)) {
+            const uint32_t tc = nc == 1 ? 0 : c - 1;                     // its records are complete now
+            CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_chunk[c], 0));
+            TileScope ts(ctx);
+            { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, tc)); }
+            { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b, tc)); }
+        }
+    }
+    if (p->want_depth) {
+        TileScope ts(ctx);
+        if (nc > 1) {
+            { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, nc - 1)); }
+            { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b, nc - 1)); }
+        }
+        StageTimer t(ctx, ST_DEPTH_TILES);
+        CSV_TRY(launch_depth_finish(ctx, b));
+    }
     if (p->want_sigs && p->want_depth) {   // sort + gather of the signatures run beside the depth kernels
         CSV_TRY(side_fork(ctx));
         SideScope side(ctx);
@@ -353,10 +449,6 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     } else if (p->want_sigs) {
         StageTimer t(ctx, ST_SIG_SORT);
         CSV_TRY(launch_sig_finish(ctx, b));
-    }
-    if (p->want_depth) {
-        { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b)); }
-        { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b)); }
     }
     b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;
     return CSV_OK;

@@ -39,6 +39,7 @@ constexpr int kTileShift = 13;
 constexpr int kWalkThreads = 256;
 constexpr int kWalkOpsPerThread = 8;
 constexpr int kWalkSpan = kWalkThreads * kWalkOpsPerThread;   // CIGAR ops per span
+constexpr int kSpanChunk = 2048;                              // spans per chunk of the two-level span scan (256 threads x 8)
 
 // BAM constants (SAM spec): which ops consume reference / query
 constexpr uint32_t kRefMask = (1u << 0) | (1u << 2) | (1u << 3) | (1u << 7) | (1u << 8);   // M D N = X
@@ -113,8 +114,11 @@ struct csv_ctx {
     cudaStream_t stream = nullptr;      // the stream kernels are launched on right now (main, or side inside a SideScope)
     cudaStream_t main_stream = nullptr; // depth pipeline, copies, timers
     cudaStream_t side_stream = nullptr; // signature sort + DBSCAN1D: only depend on the walk, run beside the depth tiles
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool side_busy = false;
+    cudaStream_t tile_stream = nullptr; // tile ranges + depth tiles of chunk c, beside the walk of chunks c + 2, c + 3, ...
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tile_join = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;  // walk of chunk c finished (main stream)
+    bool side_busy = false, tile_busy = false;
+    int pipe_chunks = 1;                // batches uploaded from now on are scanned in up to this many pipelined chunks of contigs
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     uint32_t epoch = 1;                 // look-back epoch, bumped per chained launch
@@ -145,6 +149,11 @@ struct SideScope {                      // kernels launched inside the scope go 
     csv_ctx* ctx;
     explicit SideScope(csv_ctx* c) : ctx(c) { ctx->stream = ctx->side_stream; ctx->side_busy = true; }
     ~SideScope() { ctx->stream = ctx->main_stream; }
+};
+struct TileScope {                      // ... to the tile stream
+    csv_ctx* ctx;
+    explicit TileScope(csv_ctx* c) : ctx(c) { ctx->stream = ctx->tile_stream; ctx->tile_busy = true; }
+    ~TileScope() { ctx->stream = ctx->main_stream; }
 };
 // RAII stage timer: records an event pair around a pipeline stage when profiling is on.
 struct StageTimer {

@@ -44,16 +44,18 @@ __device__ __forceinline__ unsigned long long pm_value(const unsigned long long*
 }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
+// The prefix max runs over the records [bounds[0], bounds[1]) of one pipeline chunk and restarts there: records of
+// earlier contigs can never exceed a (tid, position) of this chunk.
 __global__ void __launch_bounds__(kPmThreads) k_pm_partials(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
-                                                            const uint32_t* scalars, unsigned long long* part)
+                                                            const uint32_t* bounds, unsigned long long* part)
 {
     __shared__ unsigned long long s[kPmThreads / 32];
-    const uint32_t n = scalars[SC_N_NONEMPTY];
+    const uint32_t k0 = bounds[0], n = bounds[1] - k0;
     for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
         unsigned long long v = 0;
         for (int j = 0; j < kPmItems; j++) {
             const uint64_t k = (uint64_t)t * kPmTile + j * kPmThreads + threadIdx.x;
-            if (k < n) v = umax64(v, pm_value(meta, ref_end, (uint32_t)k));
+            if (k < n) v = umax64(v, pm_value(meta, ref_end, k0 + (uint32_t)k));
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v = umax64(v, __shfl_xor_sync(0xffffffffu, v, d));
@@ -69,11 +71,11 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_partials(const unsigned long 
 }
 
 // single CTA: part[t] <- max of part[0..t-1] (exclusive), in place
-__global__ void __launch_bounds__(1024) k_pm_scan_partials(const uint32_t* scalars, unsigned long long* part)
+__global__ void __launch_bounds__(1024) k_pm_scan_partials(const uint32_t* bounds, unsigned long long* part)
 {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_carry;
-    const uint32_t n = scalars[SC_N_NONEMPTY];
+    const uint32_t n = bounds[1] - bounds[0];
     const uint32_t n_part = (uint32_t)(((uint64_t)n + kPmTile - 1) / kPmTile);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
@@ -98,11 +100,12 @@ __global__ void __launch_bounds__(1024) k_pm_scan_partials(const uint32_t* scala
 }
 
 __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
-                                                         uint32_t* scalars, const unsigned long long* __restrict__ part,
+                                                         uint32_t* scalars, const uint32_t* bounds, const unsigned long long* __restrict__ part,
                                                          unsigned long long* pmax)
 {
     __shared__ unsigned long long s_w[kPmThreads / 32];
-    const uint32_t n = scalars[SC_N_NONEMPTY];
+    const uint32_t kb = bounds[0], n = bounds[1] - kb;
+    meta += kb; ref_end += kb; pmax += kb;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
         // blocked arrangement: thread owns kPmItems consecutive records
@@ -111,9 +114,9 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
 #pragma unroll
         for (int j = 0; j < kPmItems; j++) {
             v[j] = (k0 + j < n) ? pm_value(meta, ref_end, (uint32_t)(k0 + j)) : 0ull;
-            // coordinate order check rides along: (tid, pos0 + 1) must not decrease
-            if (k0 + j < n && k0 + j > 0) {
-                if (meta[k0 + j - 1] > meta[k0 + j]) scalars[SC_UNSORTED] = 1;
+            // coordinate order check rides along: (tid, pos0 + 1) must not decrease (also across chunk borders)
+            if (k0 + j < n && kb + k0 + j > 0) {
+                if (meta[(long long)(k0 + j) - 1] > meta[k0 + j]) scalars[SC_UNSORTED] = 1;
             }
             run = umax64(run, v[j]);
         }
@@ -134,24 +137,24 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
 }
 
 // ------------------------------------------------------------ tile -> event slice
-__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_tiles, const unsigned long long* __restrict__ key,
+__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t t_begin, uint32_t t_end, const unsigned long long* __restrict__ key,
                               const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
-                              uint32_t* scalars, uint2* tile_ev, uint4* tile_q, uint32_t* wide_list)
+                              uint32_t* scalars, const uint32_t* bounds, uint2* tile_ev, uint4* tile_q, uint32_t* wide_list)
 {
-    const uint32_t n = scalars[SC_N_NONEMPTY];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+    const uint32_t n = scalars[SC_N_NONEMPTY], kb = bounds[0];
+    for (uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x; t < t_end; t += gridDim.x * blockDim.x) {
         const uint4 d = tile_desc[t];            // {region, positions, T0, tid}
         const unsigned long long key_hi = ((unsigned long long)d.w << 32) | (unsigned long long)(d.z + d.y);   // (tid, T1)
         const unsigned long long key_lo = ((unsigned long long)d.w << 32) | (unsigned long long)d.z;           // (tid, T0)
-        uint32_t lo = 0, hi = n;
+        uint32_t lo = kb, hi = n;
         while (lo < hi) {                        // r_hi: first record with (tid, pos0 + 1) >= (tid, T1)
-            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t mid = lo + ((hi - lo) >> 1);
             if (key[mid] < key_hi) lo = mid + 1; else hi = mid;
         }
         const uint32_t r_hi = lo;
-        lo = 0; hi = r_hi;
+        lo = kb; hi = r_hi;
         while (lo < hi) {                        // r_lo: first record with running max (tid, ref_end) > (tid, T0)
-            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t mid = lo + ((hi - lo) >> 1);
             if (pmax[mid] <= key_lo) lo = mid + 1; else hi = mid;
         }
         const uint32_t r_lo = lo;
@@ -162,26 +165,58 @@ __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t n_ti
     }
 }
 
-int launch_tile_ranges(csv_ctx* ctx, csv_batch* b)
+// first compact record of every pipeline chunk: bounds[c] = first record with tid >= first_tid[c]
+__global__ void k_chunk_bounds(const unsigned long long* __restrict__ key, const uint32_t* scalars, const uint32_t* first_tid, uint32_t n_chunks,
+                               uint32_t* bounds)
 {
-    if (b->n_tiles == 0) return CSV_OK;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chunks) return;
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    if (c == n_chunks) { bounds[c] = n; return; }
+    const unsigned long long want = (unsigned long long)first_tid[c] << 32;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (key[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    bounds[c] = c == 0 ? 0u : lo;
+}
+
+int launch_chunk_bounds(csv_ctx* ctx, csv_batch* b)
+{
+    const uint32_t nc = (uint32_t)b->chunks.size();
+    k_chunk_bounds<<<(nc + 1 + 63) / 64, 64, 0, ctx->stream>>>(b->d_key.as<unsigned long long>(), b->d_scalars.as<uint32_t>(),
+                                                              b->d_chunk_tid.as<uint32_t>(), nc, b->d_chunk_bounds.as<uint32_t>());
+    ctx->launches++;
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
+// event slices of the tiles of pipeline chunk c (needs the walk of chunk c + 1: see csv_scan_run)
+int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
+{
+    const PipeChunk& ch = b->chunks[c];
+    if (ch.tiles.empty()) return CSV_OK;
     const unsigned long long* meta = b->d_key.as<unsigned long long>();
     const uint32_t* ref_end = b->d_ref_end.as<uint32_t>();
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
+    const uint32_t* bounds = b->d_chunk_bounds.as<uint32_t>() + c;
     unsigned long long* part = b->d_pmax_part.as<unsigned long long>();
     unsigned long long* pmax = b->d_pmax.as<unsigned long long>();
-    const uint32_t n_part = (uint32_t)(((uint64_t)b->n_reads + kPmTile - 1) / kPmTile);
+    const uint32_t n_part = (uint32_t)(((uint64_t)ch.rec_upper + kPmTile - 1) / kPmTile);
     if (n_part) {
         const uint32_t grid = n_part < (uint32_t)ctx->sm_count * 8 ? n_part : (uint32_t)ctx->sm_count * 8;
-        k_pm_partials<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, part);
-        k_pm_scan_partials<<<1, 1024, 0, ctx->stream>>>(scalars, part);
-        k_pm_final<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, part, pmax);
+        k_pm_partials<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, bounds, part);
+        k_pm_scan_partials<<<1, 1024, 0, ctx->stream>>>(bounds, part);
+        k_pm_final<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, bounds, part, pmax);
         ctx->launches += 3;
     }
-    const uint32_t grid_t = (b->n_tiles + 255) / 256;
-    k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), b->n_tiles, meta, pmax, b->d_ev_start.as<uint32_t>(),
-                                                  scalars, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_wide_list.as<uint32_t>());
-    ctx->launches++;
+    for (const auto& tr : ch.tiles) {
+        const uint32_t grid_t = (tr.second - tr.first + 255) / 256;
+        k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), tr.first, tr.second, meta, pmax, b->d_ev_start.as<uint32_t>(),
+                                                      scalars, bounds, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_wide_list.as<uint32_t>());
+        ctx->launches++;
+    }
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
@@ -196,7 +231,8 @@ struct TileParams {
     uint32_t* depth;                 // n_tiles * kTile words
     unsigned long long* tile_sum;    // per-tile partial reductions (no contended atomics)
     uint32_t* tile_nz;
-    uint32_t n_tiles;
+    uint32_t n_tiles;                // all tiles of the batch (wide kernel)
+    uint32_t t_begin, t_end;         // tiles of this launch (16-bit kernel)
     const uint32_t* wide_list;       // tiles that need 32-bit counters
     const uint32_t* scalars;
 };
@@ -358,7 +394,8 @@ __device__ __forceinline__ int scan_step(int x, int d)
     return x;
 }
 
-__global__ void __launch_bounds__(256, 4) k_depth_tiles16(const TileParams P)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
 {
     constexpr int kThreads = 256, kWarps = kThreads / 32, kPP = 1024 / kThreads;
     static_assert(kTile == kWarps * 1024, "a warp owns 1024 positions: 4 rows of 32 chunks of 8");
@@ -373,10 +410,10 @@ __global__ void __launch_bounds__(256, 4) k_depth_tiles16(const TileParams P)
     for (uint32_t i = tid; i < kTile / 8; i += kThreads) reinterpret_cast<uint4*>(s_d)[i] = bias4;
     // tile descriptors {T0, positions, first event, end event} run two tiles ahead of the tile being scanned
     const uint32_t g = gridDim.x;
-    uint32_t t = blockIdx.x;
+    uint32_t t = P.t_begin + blockIdx.x;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    uint4 cur = t < P.n_tiles ? __ldg(P.tile_q + t) : zero4;
-    uint4 nxt = t + g < P.n_tiles ? __ldg(P.tile_q + t + g) : zero4;
+    uint4 cur = t < P.t_end ? __ldg(P.tile_q + t) : zero4;
+    uint4 nxt = t + g < P.t_end ? __ldg(P.tile_q + t + g) : zero4;
     uint2 pf[kPP];
     {
         const uint32_t pb = cur.z >> 1, pe = min(cur.w >> 1, pair_cap);
@@ -385,8 +422,8 @@ __global__ void __launch_bounds__(256, 4) k_depth_tiles16(const TileParams P)
     }
     __syncthreads();
 
-    while (t < P.n_tiles) {
-        const uint4 nn = t + 2 * g < P.n_tiles ? __ldg(P.tile_q + t + 2 * g) : zero4;
+    while (t < P.t_end) {
+        const uint4 nn = t + 2 * g < P.t_end ? __ldg(P.tile_q + t + 2 * g) : zero4;
         const uint32_t T0 = cur.x, n_here = cur.y;
         const uint32_t pb = cur.z >> 1, pe = min(cur.w >> 1, pair_cap);
         const bool narrow = ((cur.w - cur.z) >> 1) <= kNarrowMaxPairs;    // CTA-uniform; wide tiles belong to k_depth_tiles_wide
@@ -491,25 +528,25 @@ __global__ void __launch_bounds__(256, 4) k_depth_tiles16(const TileParams P)
     }
 }
 
-// one CTA per region: sum the per-tile partials (cnv_caller.cpp:534-535)
-__global__ void __launch_bounds__(256) k_region_stats(const uint32_t* __restrict__ reg_tile_base, const unsigned long long* __restrict__ tile_sum,
+// sum the per-tile partials per region (cnv_caller.cpp:534-535): one thread per tile, one atomic per warp and region
+__global__ void __launch_bounds__(256) k_region_stats(const uint4* __restrict__ tile_desc, uint32_t n_tiles, const unsigned long long* __restrict__ tile_sum,
                                                        const uint32_t* __restrict__ tile_nz, unsigned long long* reg_sum, uint32_t* reg_nz)
 {
-    __shared__ unsigned long long s_s[8];
-    __shared__ uint32_t s_n[8];
-    const uint32_t r = blockIdx.x, t0 = reg_tile_base[r], t1 = reg_tile_base[r + 1];
-    unsigned long long s = 0; uint32_t n = 0;
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) { s += tile_sum[t]; n += tile_nz[t]; }
-    s = warp_sum_u64(s); n = warp_sum_u32(n);
-    if ((threadIdx.x & 31) == 0) { s_s[threadIdx.x >> 5] = s; s_n[threadIdx.x >> 5] = n; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; i++) { s += s_s[i]; n += s_n[i]; }
-        reg_sum[r] = s; reg_nz[r] = n;
+    for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < n_tiles; t0 += gridDim.x * blockDim.x) {
+        const uint32_t t = t0 + threadIdx.x;
+        const bool ok = t < n_tiles;
+        const uint32_t r = ok ? tile_desc[t].x : 0xffffffffu;
+        unsigned long long s = ok ? tile_sum[t] : 0ull;
+        uint32_t n = ok ? tile_nz[t] : 0u;
+        const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
+        if (__all_sync(0xffffffffu, r == r0)) {                               // the common case: a warp inside one region
+            s = warp_sum_u64(s); n = warp_sum_u32(n);
+            if ((threadIdx.x & 31) == 0 && (s | n)) { atomicAdd(&reg_sum[r0], s); atomicAdd(&reg_nz[r0], n); }
+        } else if (ok && (s | n)) { atomicAdd(&reg_sum[r], s); atomicAdd(&reg_nz[r], n); }
     }
 }
 
-int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
+static TileParams tile_params(csv_batch* b)
 {
     TileParams P;
     P.tile_desc = b->d_tile_desc.as<uint4>();
@@ -521,19 +558,51 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b)
     P.tile_sum = b->d_tile_sum.as<unsigned long long>();
     P.tile_nz = b->d_tile_nz.as<uint32_t>();
     P.n_tiles = b->n_tiles;
-    if (b->n_tiles == 0) return CSV_OK;
-    CSV_CUDA(cudaMemsetAsync(P.tile_sum, 0, (size_t)b->n_tiles * 8, ctx->stream));
-    CSV_CUDA(cudaMemsetAsync(P.tile_nz, 0, (size_t)b->n_tiles * 4, ctx->stream));
+    P.t_begin = 0; P.t_end = b->n_tiles;
     P.wide_list = b->d_wide_list.as<uint32_t>();
     P.scalars = b->d_scalars.as<uint32_t>();
+    return P;
+}
+
+// before the first chunk of a pass
+int launch_depth_begin(csv_ctx* ctx, csv_batch* b)
+{
+    if (b->n_tiles == 0) return CSV_OK;
+    CSV_CUDA(cudaMemsetAsync(b->d_tile_sum.p, 0, (size_t)b->n_tiles * 8, ctx->stream));
+    CSV_CUDA(cudaMemsetAsync(b->d_tile_nz.p, 0, (size_t)b->n_tiles * 4, ctx->stream));
+    CSV_CUDA(cudaMemsetAsync(b->d_sum.p, 0, (size_t)b->n_regions * 8, ctx->stream));
+    CSV_CUDA(cudaMemsetAsync(b->d_nz.p, 0, (size_t)b->n_regions * 4, ctx->stream));
+    return CSV_OK;
+}
+
+// the tiles of pipeline chunk c
+int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t c)
+{
+    TileParams P = tile_params(b);
     static const int mult = getenv("CSV_TILE_GRID") ? atoi(getenv("CSV_TILE_GRID")) : 20;   // tuning knob: CTAs per SM in the grid
-    const uint32_t grid = b->n_tiles < (uint32_t)ctx->sm_count * mult ? b->n_tiles : (uint32_t)ctx->sm_count * mult;
-    k_depth_tiles16<<<grid, 256, 0, ctx->stream>>>(P);
+    static const int minb = getenv("CSV_TILE_MINB") ? atoi(getenv("CSV_TILE_MINB")) : 4;
+    for (const auto& tr : b->chunks[c].tiles) {
+        P.t_begin = tr.first; P.t_end = tr.second;
+        const uint32_t nt = tr.second - tr.first;
+        const uint32_t grid = nt < (uint32_t)ctx->sm_count * mult ? nt : (uint32_t)ctx->sm_count * mult;
+        if (minb == 5) k_depth_tiles16<5><<<grid, 256, 0, ctx->stream>>>(P);
+        else if (minb == 6) k_depth_tiles16<6><<<grid, 256, 0, ctx->stream>>>(P);
+        else k_depth_tiles16<4><<<grid, 256, 0, ctx->stream>>>(P);
+        ctx->launches++;
+    }
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
+// after the last chunk: pile-up tiles with 32-bit counters, then the per-region reductions
+int launch_depth_finish(csv_ctx* ctx, csv_batch* b)
+{
+    if (b->n_tiles == 0) return CSV_OK;
+    TileParams P = tile_params(b);
     const uint32_t grid_w = b->n_tiles < (uint32_t)ctx->sm_count * 4 ? b->n_tiles : (uint32_t)ctx->sm_count * 4;
     k_depth_tiles_wide<32><<<grid_w, kTile / 32, 0, ctx->stream>>>(P);    // exits at once when the wide list is empty
-    ctx->launches++;
-    k_region_stats<<<b->n_regions, 256, 0, ctx->stream>>>(b->d_reg_tab.as<uint32_t>(), P.tile_sum, P.tile_nz,
-                                                          b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());
+    const uint32_t grid_r = (b->n_tiles + 255) / 256 < (uint32_t)ctx->sm_count * 8 ? (b->n_tiles + 255) / 256 : (uint32_t)ctx->sm_count * 8;
+    k_region_stats<<<grid_r, 256, 0, ctx->stream>>>(P.tile_desc, b->n_tiles, P.tile_sum, P.tile_nz, b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());
     ctx->launches += 2;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;

@@ -60,7 +60,7 @@ __global__ void k_sig_gather(const GatherParams P)
             unsigned long long from = c0;
             uint32_t q = 0;
             if (c0 < (unsigned long long)sp * kWalkSpan) {
-                const WalkAgg ch = P.chunk_agg[sp / 2048u], pr = P.span_pre[sp];
+                const WalkAgg ch = P.chunk_agg[sp / (uint32_t)kSpanChunk], pr = P.span_pre[sp];
                 q = pr.heads ? pr.qry : ch.qry + pr.qry;
                 from = (unsigned long long)sp * kWalkSpan;
             }

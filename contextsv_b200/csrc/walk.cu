@@ -22,6 +22,8 @@
 #include "batch.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace csv {
 
 struct WalkParams {
@@ -33,6 +35,7 @@ struct WalkParams {
     WalkAgg* span_pre;          // exclusive prefix of the span inside its chunk of kSpanChunk spans
     WalkAgg* chunk_agg;         // per-chunk aggregate, then exclusive prefix over chunks
     uint32_t n_spans;
+    uint32_t span_base;         // first span of this launch (the scan is pipelined in chunks of spans)
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
@@ -45,7 +48,6 @@ struct WalkParams {
     uint32_t* reg_sig_cnt;
 };
 
-constexpr int kSpanChunk = 2048;    // spans per scan chunk (256 threads x 8)
 
 __device__ __forceinline__ WalkAgg combine(const WalkAgg a, const WalkAgg b)
 {
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_span_agg(const WalkParams P)
 {
     __shared__ WalkAgg s_warp[kWalkThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t span = blockIdx.x;
+    const uint32_t span = blockIdx.x + P.span_base;
     const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread);
     const WalkAgg a = thread_aggregate(t);
     // warp aggregate with the redux unit: plain sums for heads / events; (ref, qry) count from the last lane
@@ -173,11 +175,12 @@ __global__ void __launch_bounds__(kWalkThreads) k_span_agg(const WalkParams P)
 }
 
 // level 1: exclusive segmented scan of the span aggregates inside chunks of kSpanChunk spans
-__global__ void __launch_bounds__(256) k_span_scan_local(const WalkParams P)
+__global__ void __launch_bounds__(256) k_span_scan_local(const WalkParams P, uint32_t sc_base)
 {
     __shared__ WalkAgg s_warp[8];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t base = blockIdx.x * (uint32_t)kSpanChunk + tid * 8u;
+    const uint32_t sc = blockIdx.x + sc_base;
+    const uint32_t base = sc * (uint32_t)kSpanChunk + tid * 8u;
     WalkAgg v[8], run = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 8; j++) { v[j] = (base + j < P.n_spans) ? P.span_agg[base + j] : WalkAgg{0, 0, 0, 0}; run = combine(run, v[j]); }
@@ -190,20 +193,22 @@ __global__ void __launch_bounds__(256) k_span_scan_local(const WalkParams P)
     pre = combine(wpre, pre);
 #pragma unroll
     for (int j = 0; j < 8; j++) { if (base + j < P.n_spans) P.span_pre[base + j] = pre; pre = combine(pre, v[j]); }
-    if (tid == 255) P.chunk_agg[blockIdx.x] = pre;
+    if (tid == 255) P.chunk_agg[sc] = pre;
 }
 
-// level 2: one CTA turns the chunk aggregates into exclusive prefixes (in place)
-__global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, uint32_t n_chunks)
+// level 2: one CTA turns the chunk aggregates [sc0, sc1) into exclusive prefixes (in place).  *carry is the
+// aggregate of everything before sc0 on entry and of everything before sc1 on exit: the pipeline calls this
+// once per chunk of spans, in order.
+__global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, uint32_t sc0, uint32_t sc1, WalkAgg* carry)
 {
     __shared__ WalkAgg s_warp[32];
     __shared__ WalkAgg s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = WalkAgg{0, 0, 0, 0};
+    if (tid == 0) s_carry = *carry;
     __syncthreads();
-    for (uint32_t b0 = 0; b0 < n_chunks; b0 += 1024) {
+    for (uint32_t b0 = sc0; b0 < sc1; b0 += 1024) {
         const uint32_t i = b0 + tid;
-        const WalkAgg v = i < n_chunks ? P.chunk_agg[i] : WalkAgg{0, 0, 0, 0};
+        const WalkAgg v = i < sc1 ? P.chunk_agg[i] : WalkAgg{0, 0, 0, 0};
         const WalkAgg inc = warp_incl_scan_agg(v, lane);
         WalkAgg pre = shfl_up1_agg(inc, lane);
         if (lane == 31) s_warp[warp] = inc;
@@ -211,11 +216,12 @@ __global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, u
         WalkAgg wpre = s_carry;
         for (uint32_t w = 0; w < warp; w++) wpre = combine(wpre, s_warp[w]);
         pre = combine(wpre, pre);
-        if (i < n_chunks) P.chunk_agg[i] = pre;
+        if (i < sc1) P.chunk_agg[i] = pre;
         __syncthreads();
         if (tid == 1023) s_carry = combine(pre, v);
         __syncthreads();
     }
+    if (tid == 0) *carry = s_carry;
 }
 
 // c[b] for a run-time b in 0..8 without local memory
@@ -244,27 +250,25 @@ constexpr uint32_t kDeadPos = 0x80000000u;   // "first index" of a record that t
 //      count get kDeadPos as their first index.  Candidate signatures branch to a rare path.
 //   D. record boundaries (about one per warp and pass for long reads) are handled in a sparse loop: the last
 //      event, ref_end and ev_start of the record that ends, the first event of the record that begins.
-template <bool DEPTH, bool SIGS>
-__global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
+template <bool DEPTH, bool SIGS, int MINB>
+__global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const WalkParams P)
 {
     __shared__ uint32_t s_pos1[kWalkSpan + 4];                               // first depth index of the span's records
     __shared__ uint4 s_wagg[kWalkThreads / 32];                              // {heads << 16 | events, ref total, ref since last head, has head}
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t span = blockIdx.x;
+    const uint32_t span = blockIdx.x + P.span_base;
     const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
     // independent loads first: ops, head bits, the span's carry-in and the first index of the span's records
     const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, g0);
     const WalkAgg span_excl = combine(P.chunk_agg[span / kSpanChunk], P.span_pre[span]);
     const uint32_t k_first = span_excl.heads - 1u;                           // record running into this span (may be -1)
     const uint32_t n_rec = P.span_agg[span].heads + 1u;
-    for (uint32_t i = tid; i < n_rec; i += kWalkThreads) {
-        const uint32_t kk = k_first + i;
-        uint32_t v = kDeadPos;
-        if (kk < P.n_meta) {
-            const uint4 m = __ldg(P.meta + kk);
-            if (((m.z >> 30) & 1u) && m.x + 1u < m.y) v = m.x + 1u;          // (uint32)pos + 1, cnv_caller.cpp:499
-        }
-        s_pos1[i] = v;
+    // first index of record k_first + tid: the load is issued here and consumed after the scans
+    uint32_t my_p1 = kDeadPos;
+    const uint32_t my_k = k_first + tid;                                     // wraps for the span that starts the batch (k_first == -1)
+    if (tid < n_rec && my_k < P.n_meta) {
+        const uint4 m = __ldg(P.meta + my_k);
+        if (((m.z >> 30) & 1u) && m.x + 1u < m.y) my_p1 = m.x + 1u;          // (uint32)pos + 1, cnv_caller.cpp:499
     }
     // ---- A
     uint32_t c[kWalkOpsPerThread + 1];
@@ -293,6 +297,16 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
     const uint32_t Xs = __shfl_sync(0xffffffffu, X, (31 - __clz(lower)) & 31);
     const uint32_t Xl = __shfl_sync(0xffffffffu, X, (31 - __clz(hm)) & 31);
     if (lane == 31) s_wagg[warp] = make_uint4(he_inc, S, hm ? S + Xl : S, hm != 0u);
+    s_pos1[tid] = my_p1;
+    for (uint32_t i = tid + kWalkThreads; i < n_rec; i += kWalkThreads) {    // spans of very short records
+        const uint32_t kk = k_first + i;
+        uint32_t v = kDeadPos;
+        if (kk < P.n_meta) {
+            const uint4 m = __ldg(P.meta + kk);
+            if (((m.z >> 30) & 1u) && m.x + 1u < m.y) v = m.x + 1u;
+        }
+        s_pos1[i] = v;
+    }
     __syncthreads();
     uint4 wa = make_uint4(0, 0, 0, 0);
     if (lane < kWalkThreads / 32) wa = s_wagg[lane];
@@ -368,9 +382,11 @@ __global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const WalkParams P)
     }
 }
 
-int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
+// Walks the spans [span0, span1); span0 must be a multiple of kSpanChunk and the chunks of one pass must come in
+// order on one stream (the carry of the span scan lives in b->d_scan_carry).
+int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1)
 {
-    if (b->n_ops == 0) return CSV_OK;
+    if (b->n_ops == 0 || span0 >= span1) return CSV_OK;
     WalkParams P;
     P.cigar = b->d_cigar.as<uint32_t>();
     P.n_ops = (uint32_t)b->n_ops;
@@ -380,6 +396,7 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.span_pre = b->d_span_pre.as<WalkAgg>();
     P.chunk_agg = b->d_span_status.as<WalkAgg>();
     P.n_spans = b->n_spans;
+    P.span_base = span0;
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.ev_start = b->d_ev_start.as<uint32_t>();
@@ -395,13 +412,19 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     P.sig.kind = b->d_sig_kind.as<uint8_t>();
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
-    const uint32_t n_chunks = (b->n_spans + kSpanChunk - 1) / kSpanChunk;
-    k_span_agg<<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
-    k_span_scan_local<<<n_chunks, 256, 0, ctx->stream>>>(P);
-    k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, n_chunks);
-    if (p->want_depth && p->want_sigs) k_walk<true, true><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
-    else if (p->want_depth) k_walk<true, false><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
-    else k_walk<false, true><<<b->n_spans, kWalkThreads, 0, ctx->stream>>>(P);
+    if (span0 == 0) CSV_CUDA(cudaMemsetAsync(b->d_scan_carry.p, 0, sizeof(WalkAgg), ctx->stream));
+    const uint32_t n = span1 - span0;
+    const uint32_t sc0 = span0 / kSpanChunk, sc1 = (span1 + kSpanChunk - 1) / kSpanChunk;
+    k_span_agg<<<n, kWalkThreads, 0, ctx->stream>>>(P);
+    k_span_scan_local<<<sc1 - sc0, 256, 0, ctx->stream>>>(P, sc0);
+    k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, sc0, sc1, b->d_scan_carry.as<WalkAgg>());
+    static const int minb = getenv("CSV_WALK_MINB") ? atoi(getenv("CSV_WALK_MINB")) : 4;    // tuning knob: CTAs per SM the compiler targets
+    if (p->want_depth && p->want_sigs) {
+        if (minb == 5) k_walk<true, true, 5><<<n, kWalkThreads, 0, ctx->stream>>>(P);
+        else if (minb == 6) k_walk<true, true, 6><<<n, kWalkThreads, 0, ctx->stream>>>(P);
+        else k_walk<true, true, 4><<<n, kWalkThreads, 0, ctx->stream>>>(P);
+    } else if (p->want_depth) k_walk<true, false, 4><<<n, kWalkThreads, 0, ctx->stream>>>(P);
+    else k_walk<false, true, 4><<<n, kWalkThreads, 0, ctx->stream>>>(P);
     ctx->launches += 4;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;

@@ -52,6 +52,11 @@ void  csv_host_free(void* p);
  * these because torch.cuda.Event only sees torch's current stream. */
 int csv_timer_begin(csv_ctx* ctx);
 int csv_timer_end(csv_ctx* ctx, float* ms_out);  /* synchronises the end event           */
+/* Batches uploaded after this call are scanned in up to n_chunks pipelined chunks of whole contigs: the CIGAR walk
+ * of chunk c+2 runs beside the depth tiles of chunk c on a second stream.  Results are identical for every value.
+ * Default 1 (also settable with the environment variable CSV_CHUNKS): on B200 both kernels are limited by the warps
+ * a register file holds, so running them side by side buys nothing today. */
+int csv_ctx_set_pipeline_chunks(csv_ctx* ctx, int n_chunks);
 /* Kernels launched by this context since creation. */
 uint64_t csv_ctx_launch_count(const csv_ctx* ctx);
 /* Per-stage device time of the scan pipeline (event pairs around each stage while

@@ -116,6 +116,20 @@ def test_synthetic_hifi_multi_contig(ctx, oracle):
     check_contigs(ctx, oracle, r, clen)
 
 
+def test_pipelined_chunks_of_contigs(ctx, oracle):
+    """Three contigs big enough for three pipeline chunks (cuts between contigs, walk ranges aligned to 2048 spans):
+    the chunked two-stream pass must give what the serial pass gives."""
+    clen = [45_000_000, 40_000_000, 42_000_000]
+    r = util.synth_reads(clen, seed=31, n_sv=200, coverage=30.0)
+    first_span = [int(r["cig_off"][int(np.searchsorted(r["tid"], t))]) // 2048 for t in (1, 2)]
+    assert first_span[0] // 2048 == 1 and first_span[1] // 2048 == 2 and int(r["n_ops"]) // 2048 >= 3 * 2048     # three chunks
+    ctx.set_pipeline_chunks(4)
+    try:
+        check_contigs(ctx, oracle, r, clen)
+    finally:
+        ctx.set_pipeline_chunks(1)
+
+
 def test_empty_and_degenerate_inputs(ctx, oracle):
     from oracle.oracle_py import make_reads
     # no reads at all
