@@ -190,6 +190,38 @@ class Batch:
         return su.reshape(len(s), sample_size), cn.reshape(len(s), sample_size)
 
 
+def scan_streamed(ctx, reads, contig_len, max_ops=(1 << 31) - (1 << 20), eps=None, min_pts=5, min_len=50, min_mapq=20):
+    """The whole hot path over records that do not fit one batch: shards planned by CIGAR-op budget
+    (shard.plan_by_ops), scanned one after the other on one device, results merged on the host exactly like
+    the shards of a multi-GPU run.  Returns (depth per contig, (sum, nonzero) per contig,
+    signatures per contig in the reference's vector order, DBSCAN1D labels per contig or None)."""
+    from . import shard
+    ends = shard.ref_end(reads)
+    plans = shard.plan_by_ops(reads, contig_len, max_ops, ends)
+    n_contigs = len(contig_len)
+    depth = [np.zeros(int(l) + 1, np.uint32) for l in contig_len]
+    sums = np.zeros(n_contigs, np.uint64); nzs = np.zeros(n_contigs, np.uint64)
+    parts = []
+    for regions in plans:
+        sub, base = shard.select_reads(reads, regions, ends)
+        b = Batch(ctx, sub, regions)
+        b.scan(want_depth=True, want_sigs=True, min_len=min_len, min_mapq=min_mapq)
+        s, nz = b.depth_stats()
+        for i, (t, beg, end, _) in enumerate(regions):
+            b.depth(i, out=depth[t][beg:end])
+            sums[t] += s[i]; nzs[t] += nz[i]
+        parts.append((b.sigs(), regions, base))
+        b.free()
+    sigs = shard.merge_signatures(parts)
+    labels = None
+    if eps is not None:
+        labels = {}
+        for t, sg in sigs.items():
+            seg = (sg["kind"] != 1).astype(np.uint32)                  # DEL | INS groups (sv_object.cpp:61-83)
+            labels[t] = dbscan1d_segments(sg["start"].astype(np.int32), seg, 2, eps, min_pts, ctx)[0] if len(seg) else np.zeros(0, np.int32)
+    return depth, (sums, nzs), sigs, labels
+
+
 # --------------------------------------------------------------------------- DBSCAN1D
 
 class DBSCAN1D:

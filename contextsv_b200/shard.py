@@ -79,6 +79,60 @@ def select_reads(reads, regions, ends=None):
     return sub, i0
 
 
+def plan_by_ops(reads, contig_len, max_ops, ends=None):
+    """Shards for ONE device when the records hold more CIGAR ops than a batch takes (csv_batch_upload: < 2^31;
+    BASELINE config 3, 60x ONT, is ~3.7e10): the same region sharding as across GPUs, in time instead of space.
+    Walks the records in order and cuts a region whenever the next record would push the ops of the slice
+    [first halo record, record] past max_ops.  Cuts fall between records with different pos0, so every record is
+    owned by exactly one shard.  Returns a list of region lists [(tid, beg, end, map_size), ...] in genome order."""
+    n = int(reads["n_reads"])
+    sizes = [int(l) + 1 for l in contig_len]
+    if n == 0:
+        return [[(t, 0, sz, sz) for t, sz in enumerate(sizes)]]
+    tid = np.zeros(n, np.int64) if reads.get("tid") is None else np.asarray(reads["tid"]).astype(np.int64)
+    idx = np.asarray(reads["pos0"]).astype(np.int64) + 1
+    off = np.asarray(reads["cig_off"]).astype(np.int64)
+    ends = ref_end(reads) if ends is None else ends
+    # first record each record's shard would have to start with if a region began at this record:
+    # the earliest record of the same contig that still reaches idx (running max of ends, per contig)
+    shards, cur = [], []
+    cur_tid, cur_beg = 0, 0                   # open region starts at (cur_tid, cur_beg)
+    i_first = 0                               # first record (halo included) of the open shard
+    i = 0
+    while i < n:
+        # group of records sharing (tid, pos0): never split
+        j = i + 1
+        while j < n and tid[j] == tid[i] and idx[j] == idx[i]:
+            j += 1
+        if off[j] - off[i_first] > max_ops and i > i_first and (tid[i] > cur_tid or idx[i] > cur_beg):
+            t, cut = int(tid[i]), int(min(idx[i], sizes[int(tid[i])]))
+            # close the open shard at (t, cut): whole contigs up to t, then [.., cut) of t
+            while cur_tid < t:
+                if cur_beg < sizes[cur_tid]:
+                    cur.append((cur_tid, cur_beg, sizes[cur_tid], sizes[cur_tid]))
+                cur_tid += 1; cur_beg = 0
+            if cut > cur_beg:
+                cur.append((t, cur_beg, cut, sizes[t]))
+                cur_beg = cut
+            if cur:
+                shards.append(cur); cur = []
+            # halo of the next shard: records of contig t before i that reach past cut
+            lo_t = int(np.searchsorted(tid, t, side="left"))
+            h = np.nonzero(ends[lo_t:i] > cut)[0]
+            i_first = lo_t + int(h[0]) if len(h) else i
+            if off[j] - off[i_first] > max_ops:
+                raise ValueError("max_ops=%d is too small: the records overlapping index %d of contig %d alone hold %d ops"
+                                 % (max_ops, cut, t, off[j] - off[i_first]))
+        i = j
+    while cur_tid < len(sizes):
+        if cur_beg < sizes[cur_tid]:
+            cur.append((cur_tid, cur_beg, sizes[cur_tid], sizes[cur_tid]))
+        cur_tid += 1; cur_beg = 0
+    if cur:
+        shards.append(cur)
+    return shards
+
+
 def merge_signatures(parts):
     """parts: list of (sigs dict from Batch.sigs(), regions, read index offset) per shard, in genome order.
     Returns one dict per contig id in the reference's vector order (start, end, reverse insertion order)."""

@@ -204,6 +204,48 @@ def test_region_sharding_with_halo_reads(ctx, oracle):
     b.free()
 
 
+def test_streamed_shards_by_op_budget(ctx, oracle):
+    """BASELINE config 3 in small: ONT-like dense CIGARs scanned as a sequence of shards whose records hold at
+    most max_ops ops (a batch takes < 2^31), merged on the host -- identical to one whole-contig scan."""
+    clen = [1_200_000, 500_000]
+    r = util.synth_reads(clen, seed=41, profile=1, coverage=12.0, read_len_mean=30000, indel_rate=0.08, indel_len_max=4, n_sv=80, sv_jitter_sd=5.0)
+    from contextsv_b200 import shard
+    plans = shard.plan_by_ops(r, clen, 600_000)
+    assert len(plans) >= 4
+    depth, (sums, nzs), sigs, labels = api.scan_streamed(ctx, r, clen, max_ops=600_000, eps=100.0, min_pts=5)
+    for tid in range(len(clen)):
+        d, s, nz = oracle.depth(r, tid, clen[tid] + 1)
+        assert np.array_equal(depth[tid], d) and int(sums[tid]) == s and int(nzs[tid]) == nz
+        o = oracle.cigar_scan(r, tid, clen[tid] + 1)
+        sg = sigs.get(tid, {k: np.zeros(0) for k in ("start",)})
+        assert len(sg["start"]) == len(o)
+        for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+            assert np.array_equal(sg[f].astype(np.int64), o[f].astype(np.int64)), f
+        for is_del in (True, False):
+            m = (sg["kind"] == 1) if is_del else (sg["kind"] != 1)
+            assert np.array_equal(labels[tid][m], oracle.dbscan1d(sg["start"][m].astype(np.int32), 100.0, 5, fast=True))
+    with pytest.raises(ValueError):
+        shard.plan_by_ops(r, clen, 2000)      # fewer ops than the records over one position hold
+
+
+def test_sv_rich_sweep_eps_minpts(ctx, oracle):
+    """BASELINE config 5 in small: SV-rich reads with per-read breakpoint jitter, DBSCAN1D over the signature starts
+    of every (contig, SVType) group for the whole eps x minPts grid."""
+    clen = [2_000_000]
+    r = util.synth_reads(clen, seed=55, n_sv=4000, coverage=30.0, sv_jitter_sd=10.0)
+    b = run_batch(ctx, r, api.whole_contig_regions(clen))
+    sg = b.sigs()
+    assert len(sg["start"]) > 20_000
+    for eps in (0, 1, 10, 50, 100, 500, 1000):
+        for mp in (1, 2, 3, 5, 10, 20):
+            lab = b.sigs_dbscan1d(float(eps), mp)
+            for is_del in (True, False):
+                m = (sg["kind"] == 1) if is_del else (sg["kind"] != 1)
+                want = oracle.dbscan1d(sg["start"][m].astype(np.int32), float(eps), mp, fast=True)
+                assert np.array_equal(lab[m], want), (eps, mp, is_del)
+    b.free()
+
+
 def test_dbscan1d_fuzz_and_large(ctx, oracle):
     rng = np.random.default_rng(3)
     for it in range(200):
