@@ -123,10 +123,18 @@ __device__ __forceinline__ uint32_t warp_incl_scan_fast(uint32_t x)
     return x;
 }
 
+// Per-op class table in shared memory: {consumes reference, consumes query} as 0/1 multipliers.  One LDS.64 per op
+// replaces two funnel-shift + mask pairs: the pre-pass is bound by the ALU pipe, the multipliers feed IMADs on the
+// FMA pipe instead.
+__device__ __forceinline__ void init_class_table(uint2* s_cls)
+{
+    if (threadIdx.x < 16) s_cls[threadIdx.x] = make_uint2((kRefMask >> threadIdx.x) & 1u, (kQryMask >> threadIdx.x) & 1u);
+}
+
 // Aggregate of the 8 ops of one thread for the pre-pass.  Heads / event counts are popcounts of the head
 // bits; (ref, qry) only count the ops from the LAST record head of the thread onwards.  Every D/N op owns two
 // events, zero-length ones included (their -1/+1 land on the same index and cancel).
-__device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t)
+__device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t, const uint2* s_cls)
 {
     WalkAgg a;
     const uint32_t vmask = (1u << t.n_valid) - 1u;          // n_valid <= 8
@@ -137,10 +145,11 @@ __device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t)
 #pragma unroll
     for (int j = 0; j < kWalkOpsPerThread; j++) {
         const uint32_t w = t.w[j];                          // ops beyond n_valid are zero words: M of length 0
+        const uint2 cl = s_cls[w & 15u];
         const uint32_t len = (j >= lh) ? (w >> 4) : 0u;
-        ref += class_bit(kRefLut, w) * len;
-        qry += class_bit(kQryLut, w) * len;
-        gaps += class_bit(kGapLut, w);
+        ref += cl.x * len;
+        qry += cl.y * len;
+        gaps += cl.x * (1u - cl.y);                         // D / N: reference only
     }
     a.ref = ref; a.qry = qry;
     a.ev = a.heads + __popc((t.hb >> 1) & vmask) + 2u * gaps;
@@ -151,10 +160,13 @@ __device__ __forceinline__ WalkAgg thread_aggregate(const ThreadOps& t)
 __global__ void __launch_bounds__(kWalkThreads) k_span_agg(const WalkParams P)
 {
     __shared__ WalkAgg s_warp[kWalkThreads / 32];
+    __shared__ uint2 s_cls[16];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t span = blockIdx.x + P.span_base;
     const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread);
-    const WalkAgg a = thread_aggregate(t);
+    init_class_table(s_cls);
+    __syncthreads();
+    const WalkAgg a = thread_aggregate(t, s_cls);
     // warp aggregate with the redux unit: plain sums for heads / events; (ref, qry) count from the last lane
     // that saw a record head (that lane's own values already start at its last head)
     WalkAgg w;
