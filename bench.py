@@ -300,7 +300,7 @@ def main_ours(args):
         if tj.get("workload") == args.workload and world == 1:
             traffic = tj["traffic_bytes_per_launch"]
     roofline = {
-        "bound": "hbm", "kernel": "k_depth_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "bound": "hbm", "kernel": "k_depth_tiles16", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": tile_ms,
         "path": {"algorithmic_bytes_per_step": b_alg, "achieved": path_gbs, "frac": path_gbs / peak},
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},

@@ -332,13 +332,13 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pos0.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16, &ctx->pool)); CSV_TRY(b->d_mapq.ensure(nr + 16, &ctx->pool));
     CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8, &ctx->pool)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64, &ctx->pool));
-    CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_key.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 64, &ctx->pool));
+    CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_key.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 512, &ctx->pool));   // the walk copies 272 bytes per span, also for the last one
     CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4, &ctx->pool));
     CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev), &ctx->pool)); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev), &ctx->pool));
     CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4, &ctx->pool)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4, &ctx->pool));
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
     CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / kSpanChunk + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
-    CSV_TRY(b->d_scan_carry.ensure(sizeof(WalkAgg), &ctx->pool));
+    CSV_TRY(b->d_scan_carry.ensure(sizeof(WalkAgg), &ctx->pool)); CSV_TRY(b->d_span_desc.ensure((size_t)b->n_spans * 16 + 16, &ctx->pool));
     CSV_TRY(b->d_chunk_tid.ensure(b->chunks.size() * 4 + 16, &ctx->pool)); CSV_TRY(b->d_chunk_bounds.ensure(b->chunks.size() * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
     CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));

@@ -36,6 +36,8 @@ struct WalkParams {
     WalkAgg* chunk_agg;         // per-chunk aggregate, then exclusive prefix over chunks
     uint32_t n_spans;
     uint32_t span_base;         // first span of this launch (the scan is pipelined in chunks of spans)
+    uint32_t span_end;          // one past the last span of this launch
+    uint4* span_desc;           // per span {record running in (may be -1), first event slot, ref consumed since the last head, records touched}
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
@@ -236,6 +238,36 @@ __global__ void __launch_bounds__(1024) k_span_scan_chunks(const WalkParams P, u
     if (tid == 0) *carry = s_carry;
 }
 
+// level 3: everything the walk needs to start a span, in one 16-byte word
+__global__ void __launch_bounds__(256) k_span_finalize(const WalkParams P)
+{
+    const uint32_t s = P.span_base + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.span_end) return;
+    const WalkAgg e = combine(P.chunk_agg[s / kSpanChunk], P.span_pre[s]);
+    P.span_desc[s] = make_uint4(e.heads - 1u, e.ev, e.ref, P.span_agg[s].heads + 1u);
+}
+
+// ---- TMA bulk copies (global -> shared, completion on an mbarrier): the walk is a persistent kernel whose next
+// span is in flight while the current one is processed; no registers are spent on the prefetch.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // c[b] for a run-time b in 0..8 without local memory
 __device__ __forceinline__ uint32_t sel9(const uint32_t (&c)[kWalkOpsPerThread + 1], uint32_t b)
 {
@@ -265,130 +297,174 @@ constexpr uint32_t kDeadPos = 0x80000000u;   // "first index" of a record that t
 template <bool DEPTH, bool SIGS, int MINB>
 __global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const WalkParams P)
 {
-    __shared__ uint32_t s_pos1[kWalkSpan + 4];                               // first depth index of the span's records
-    __shared__ uint4 s_wagg[kWalkThreads / 32];                              // {heads << 16 | events, ref total, ref since last head, has head}
+    __shared__ __align__(128) uint32_t s_ops[2][kWalkSpan];                  // CIGAR words of the span in hand and of the next one
+    __shared__ __align__(16) uint8_t s_hb[2][kWalkSpan / 8 + 16];            // their head bits (+ the byte that follows)
+    __shared__ __align__(16) uint4 s_desc[2];                                // their span descriptors
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ uint32_t s_pos1_[2][kWalkSpan + 4];                           // first depth index of the span's records       } double-buffered by
+    __shared__ uint4 s_wagg_[2][kWalkThreads / 32];                          // {heads << 16 | events, ref total, ref since   } span parity: one CTA
+                                                                             //  last head, has head} per warp                } barrier per span
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t span = blockIdx.x + P.span_base;
-    const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
-    // independent loads first: ops, head bits, the span's carry-in and the first index of the span's records
-    const ThreadOps t = load_ops(P.cigar, P.headbits, P.n_ops, g0);
-    const WalkAgg span_excl = combine(P.chunk_agg[span / kSpanChunk], P.span_pre[span]);
-    const uint32_t k_first = span_excl.heads - 1u;                           // record running into this span (may be -1)
-    const uint32_t n_rec = P.span_agg[span].heads + 1u;
-    // first index of record k_first + tid: the load is issued here and consumed after the scans
-    uint32_t my_p1 = kDeadPos;
-    const uint32_t my_k = k_first + tid;                                     // wraps for the span that starts the batch (k_first == -1)
-    if (tid < n_rec && my_k < P.n_meta) {
-        const uint4 m = __ldg(P.meta + my_k);
-        if (((m.z >> 30) & 1u) && m.x + 1u < m.y) my_p1 = m.x + 1u;          // (uint32)pos + 1, cnv_caller.cpp:499
-    }
-    // ---- A
-    uint32_t c[kWalkOpsPerThread + 1];
-    uint32_t gm = 0, sm = 0;
-    c[0] = 0;
-    const uint32_t thr = P.min_len << 4;
-#pragma unroll
-    for (int j = 0; j < kWalkOpsPerThread; j++) {
-        const uint32_t w = t.w[j];
-        c[j + 1] = c[j] + class_bit(kRefLut, w) * (w >> 4);
-        if (DEPTH) gm |= class_bit(kGapLut, w) << j;
-        if (SIGS) sm |= (w >= thr ? class_bit(P.sig_lut, w) : 0u) << j;
-    }
-    const uint32_t vmask = (1u << t.n_valid) - 1u, hbv = t.hb & vmask, tails = (t.hb >> 1) & vmask;
-    const uint32_t heads = __popc(hbv);
-    const uint32_t evn = heads + __popc(tails) + 2u * __popc(gm);
-    const int lh = 31 - __clz(hbv);
-    const uint32_t reftail = c[kWalkOpsPerThread] - (lh < 0 ? 0u : sel9(c, (uint32_t)lh));
-    // ---- B
-    const uint32_t he = (heads << 16) | evn;                                 // a span holds <= 2048 heads and <= 8192 events
-    const uint32_t he_inc = warp_incl_scan_fast(he);
-    const uint32_t S = warp_incl_scan_fast(c[kWalkOpsPerThread]);
-    const uint32_t hm = __ballot_sync(0xffffffffu, heads != 0u);
-    const uint32_t lower = hm & lanemask_lt();
-    const uint32_t X = reftail - S;
-    const uint32_t Xs = __shfl_sync(0xffffffffu, X, (31 - __clz(lower)) & 31);
-    const uint32_t Xl = __shfl_sync(0xffffffffu, X, (31 - __clz(hm)) & 31);
-    if (lane == 31) s_wagg[warp] = make_uint4(he_inc, S, hm ? S + Xl : S, hm != 0u);
-    s_pos1[tid] = my_p1;
-    for (uint32_t i = tid + kWalkThreads; i < n_rec; i += kWalkThreads) {    // spans of very short records
-        const uint32_t kk = k_first + i;
-        uint32_t v = kDeadPos;
-        if (kk < P.n_meta) {
-            const uint4 m = __ldg(P.meta + kk);
-            if (((m.z >> 30) & 1u) && m.x + 1u < m.y) v = m.x + 1u;
-        }
-        s_pos1[i] = v;
+    const uint32_t stride = gridDim.x;
+    auto issue = [&](uint32_t span, int buf) {                               // one thread: three bulk copies, one barrier phase
+        const uint32_t o0 = span * (uint32_t)kWalkSpan;
+        const uint32_t n = P.n_ops - o0 < (uint32_t)kWalkSpan ? P.n_ops - o0 : (uint32_t)kWalkSpan;
+        const uint32_t bytes_ops = (n * 4u + 15u) & ~15u, bytes_hb = kWalkSpan / 8 + 16;
+        mbar_expect_tx(&s_bar[buf], bytes_ops + bytes_hb + 16u);
+        tma_bulk_g2s(s_ops[buf], P.cigar + o0, bytes_ops, &s_bar[buf]);
+        tma_bulk_g2s(s_hb[buf], P.headbits + (o0 >> 3), bytes_hb, &s_bar[buf]);
+        tma_bulk_g2s(&s_desc[buf], P.span_desc + span, 16u, &s_bar[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint4 wa = make_uint4(0, 0, 0, 0);
-    if (lane < kWalkThreads / 32) wa = s_wagg[lane];
-    const uint32_t he_pre = __reduce_add_sync(0xffffffffu, lane < warp ? wa.x : 0u);
-    const uint32_t wh = __ballot_sync(0xffffffffu, lane < warp && wa.w);
-    uint32_t carry;                                                          // reference consumed since the last head before my warp
-    if (wh) {
-        const uint32_t lw = 31 - __clz(wh);
-        carry = __shfl_sync(0xffffffffu, wa.z, lw) + __reduce_add_sync(0xffffffffu, (lane > lw && lane < warp) ? wa.y : 0u);
-    } else carry = span_excl.ref + __reduce_add_sync(0xffffffffu, lane < warp ? wa.y : 0u);
-    if (t.n_valid == 0) return;
-    const uint32_t he_ex = he_pre + (he_inc - he);
-    const uint32_t T_ev = span_excl.ev + (he_ex & 0xffffu);
-    uint32_t kl = he_ex >> 16;                                               // s_pos1 slot of the record running into my ops
-    const uint32_t rc_entry = lower ? (S - c[kWalkOpsPerThread]) + Xs : carry + (S - c[kWalkOpsPerThread]);
-    const uint32_t kl_entry = kl, bias_entry = s_pos1[kl] + rc_entry;
-    uint32_t bias = bias_entry;
-    // ---- C
-    uint32_t* evp = P.events + T_ev;
+    const uint32_t first = P.span_base + blockIdx.x;
+    if (tid == 0) {
+        if (first < P.span_end) issue(first, 0);
+        if (first + stride < P.span_end) issue(first + stride, 1);
+    }
+    uint32_t it = 0;
+    for (uint32_t span = first; span < P.span_end; span += stride, it++) {
+        const int buf = it & 1;
+        uint32_t* const s_pos1 = s_pos1_[buf];
+        uint4* const s_wagg = s_wagg_[buf];
+        mbar_wait(&s_bar[buf], (it >> 1) & 1u);
+        const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
+        const uint4 desc = s_desc[buf];
+        const uint32_t k_first = desc.x, n_rec = desc.w;
+        // first index of record k_first + tid: the load is issued here and consumed after the scans
+        uint32_t my_p1 = kDeadPos;
+        const uint32_t my_k = k_first + tid;                                 // wraps for the span that starts the batch (k_first == -1)
+        if (tid < n_rec && my_k < P.n_meta) {
+            const uint4 m = __ldg(P.meta + my_k);
+            if (((m.z >> 30) & 1u) && m.x + 1u < m.y) my_p1 = m.x + 1u;      // (uint32)pos + 1, cnv_caller.cpp:499
+        }
+        ThreadOps t;
+        {
+            const uint4 a = reinterpret_cast<const uint4*>(s_ops[buf])[2 * tid], c4 = reinterpret_cast<const uint4*>(s_ops[buf])[2 * tid + 1];
+            t.w[0] = a.x; t.w[1] = a.y; t.w[2] = a.z; t.w[3] = a.w; t.w[4] = c4.x; t.w[5] = c4.y; t.w[6] = c4.z; t.w[7] = c4.w;
+            t.hb = (uint32_t)s_hb[buf][tid] | ((uint32_t)s_hb[buf][tid + 1] << 8);
+            t.n_valid = kWalkOpsPerThread;
+            if (g0 + kWalkOpsPerThread > P.n_ops) {                          // last span of the batch: what lies beyond n_ops is not CIGAR
+                t.n_valid = g0 >= P.n_ops ? 0u : P.n_ops - g0;
 #pragma unroll
-    for (int j = 0; j < kWalkOpsPerThread; j++) {
-        if ((hbv >> j) & 1u) { kl++; bias = s_pos1[kl] - c[j]; if (DEPTH) evp += (j ? 2 : 1); }      // tail event of the record before + my head event
-        if (DEPTH && ((gm >> j) & 1u)) { evp[0] = c[j] + bias; evp[1] = c[j + 1] + bias; evp += 2; }   // D / N: -1 at its first index, +1 one past its last
-        if (SIGS && ((sm >> j) & 1u)) {                                      // rare: I / D / S of at least min_len
-            const uint32_t w = t.w[j], op = w & 15u, len = w >> 4;
-            const uint32_t k = k_first + kl;
-            const uint4 m = __ldg(P.meta + k);
-            if (m.z >> 31) {
-                const uint32_t pos1 = m.x + 1u + (c[j] + bias - s_pos1[kl]);  // reference's `pos + 1` at this op (uint32)
-                const bool beyond = pos1 >= m.y;
-                const uint32_t start = pos1, end = start + len - 1u;
-                if (!(op == 4 && beyond) && start <= end) {                  // sv_caller.cpp:602-604, sv_object.cpp:25-28
-                    const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
-                    if (sl < P.sig_cap) {
-                        P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
-                        P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
-                        P.sig.k[sl] = k;
-                        const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
-                        P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
-                        atomicAdd(&P.reg_sig_cnt[m.w], 1u);
+                for (int j = 0; j < kWalkOpsPerThread; j++) if ((uint32_t)j >= t.n_valid) t.w[j] = 0u;
+                if (t.n_valid == 0) t.hb = 0;
+            }
+        }
+        // ---- A
+        uint32_t c[kWalkOpsPerThread + 1];
+        uint32_t gm = 0, sm = 0;
+        c[0] = 0;
+        const uint32_t thr = P.min_len << 4;
+#pragma unroll
+        for (int j = 0; j < kWalkOpsPerThread; j++) {
+            const uint32_t w = t.w[j];
+            c[j + 1] = c[j] + class_bit(kRefLut, w) * (w >> 4);
+            if (DEPTH) gm |= class_bit(kGapLut, w) << j;
+            if (SIGS) sm |= (w >= thr ? class_bit(P.sig_lut, w) : 0u) << j;
+        }
+        const uint32_t vmask = (1u << t.n_valid) - 1u, hbv = t.hb & vmask, tails = (t.hb >> 1) & vmask;
+        const uint32_t heads = __popc(hbv);
+        const uint32_t evn = heads + __popc(tails) + 2u * __popc(gm);
+        const int lh = 31 - __clz(hbv);
+        const uint32_t reftail = c[kWalkOpsPerThread] - (lh < 0 ? 0u : sel9(c, (uint32_t)lh));
+        // ---- B
+        const uint32_t he = (heads << 16) | evn;                             // a span holds <= 2048 heads and <= 8192 events
+        const uint32_t he_inc = warp_incl_scan_fast(he);
+        const uint32_t S = warp_incl_scan_fast(c[kWalkOpsPerThread]);
+        const uint32_t hm = __ballot_sync(0xffffffffu, heads != 0u);
+        const uint32_t lower = hm & lanemask_lt();
+        const uint32_t X = reftail - S;
+        const uint32_t Xs = __shfl_sync(0xffffffffu, X, (31 - __clz(lower)) & 31);
+        const uint32_t Xl = __shfl_sync(0xffffffffu, X, (31 - __clz(hm)) & 31);
+        if (lane == 31) s_wagg[warp] = make_uint4(he_inc, S, hm ? S + Xl : S, hm != 0u);
+        s_pos1[tid] = my_p1;
+        for (uint32_t i = tid + kWalkThreads; i < n_rec; i += kWalkThreads) {    // spans of very short records
+            const uint32_t kk = k_first + i;
+            uint32_t v = kDeadPos;
+            if (kk < P.n_meta) {
+                const uint4 m = __ldg(P.meta + kk);
+                if (((m.z >> 30) & 1u) && m.x + 1u < m.y) v = m.x + 1u;
+            }
+            s_pos1[i] = v;
+        }
+        __syncthreads();                                                     // the only CTA barrier of the span
+        // everybody holds its ops in registers: the buffer is free for the span after the next
+        if (tid == 0 && span + 2 * stride < P.span_end && span + 2 * stride >= span) issue(span + 2 * stride, buf);
+        uint4 wa = make_uint4(0, 0, 0, 0);
+        if (lane < kWalkThreads / 32) wa = s_wagg[lane];
+        const uint32_t he_pre = __reduce_add_sync(0xffffffffu, lane < warp ? wa.x : 0u);
+        const uint32_t wh = __ballot_sync(0xffffffffu, lane < warp && wa.w);
+        uint32_t carry;                                                      // reference consumed since the last head before my warp
+        if (wh) {
+            const uint32_t lw = 31 - __clz(wh);
+            carry = __shfl_sync(0xffffffffu, wa.z, lw) + __reduce_add_sync(0xffffffffu, (lane > lw && lane < warp) ? wa.y : 0u);
+        } else carry = desc.z + __reduce_add_sync(0xffffffffu, lane < warp ? wa.y : 0u);
+        if (t.n_valid != 0) {
+            const uint32_t he_ex = he_pre + (he_inc - he);
+            const uint32_t T_ev = desc.y + (he_ex & 0xffffu);
+            uint32_t kl = he_ex >> 16;                                       // s_pos1 slot of the record running into my ops
+            const uint32_t rc_entry = lower ? (S - c[kWalkOpsPerThread]) + Xs : carry + (S - c[kWalkOpsPerThread]);
+            const uint32_t kl_entry = kl, bias_entry = s_pos1[kl] + rc_entry;
+            uint32_t bias = bias_entry;
+            // ---- C
+            uint32_t* evp = P.events + T_ev;
+#pragma unroll
+            for (int j = 0; j < kWalkOpsPerThread; j++) {
+                if ((hbv >> j) & 1u) { kl++; bias = s_pos1[kl] - c[j]; if (DEPTH) evp += (j ? 2 : 1); }      // tail event of the record before + my head event
+                if (DEPTH && ((gm >> j) & 1u)) { evp[0] = c[j] + bias; evp[1] = c[j + 1] + bias; evp += 2; }   // D / N: -1 at its first index, +1 one past its last
+                if (SIGS && ((sm >> j) & 1u)) {                              // rare: I / D / S of at least min_len
+                    const uint32_t w = t.w[j], op = w & 15u, len = w >> 4;
+                    const uint32_t k = k_first + kl;
+                    const uint4 m = __ldg(P.meta + k);
+                    if (m.z >> 31) {
+                        const uint32_t pos1 = m.x + 1u + (c[j] + bias - s_pos1[kl]);  // reference's `pos + 1` at this op (uint32)
+                        const bool beyond = pos1 >= m.y;
+                        const uint32_t start = pos1, end = start + len - 1u;
+                        if (!(op == 4 && beyond) && start <= end) {          // sv_caller.cpp:602-604, sv_object.cpp:25-28
+                            const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
+                            if (sl < P.sig_cap) {
+                                P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
+                                P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
+                                P.sig.k[sl] = k;
+                                const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
+                                P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
+                                atomicAdd(&P.reg_sig_cnt[m.w], 1u);
+                            }
+                        }
                     }
                 }
             }
-        }
-    }
-    // ---- D
-    if (DEPTH) {
-        uint32_t bm = t.hb & ((2u << t.n_valid) - 1u);                       // bit b: a record ends with op b-1 and (b < n_valid) one begins at op b
-        uint32_t klb = kl_entry, biasb = bias_entry;
-        while (bm) {
-            const uint32_t b = __ffs(bm) - 1u;
-            bm &= bm - 1u;
-            const uint32_t cb = sel9(c, b);
-            const uint32_t low = (1u << b) - 1u;
-            const uint32_t slot = T_ev + __popc((hbv & low) | ((tails & low) << 9)) + 2u * __popc(gm & low);   // after the tail event of op b-1
-            if (b) {
-                const uint32_t kt = k_first + klb;
-                const uint4 m = __ldg(P.meta + kt);
-                const bool live = ((m.z >> 30) & 1u) && m.x + 1u < m.y;
-                const uint32_t ie = cb + biasb;                              // one past the last covered index
-                if (ie - s_pos1[klb] >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
-                P.events[slot - 1u] = ie;
-                P.ref_end[kt] = live ? (ie < m.y ? ie : m.y) : 0u;
-                P.ev_start[kt + 1u] = slot;
-            }
-            if (b < t.n_valid) {
-                klb++;
-                const uint32_t p1 = s_pos1[klb];
-                P.events[slot] = p1;
-                biasb = p1 - cb;
+            // ---- D
+            if (DEPTH) {
+                uint32_t bm = t.hb & ((2u << t.n_valid) - 1u);               // bit b: a record ends with op b-1 and (b < n_valid) one begins at op b
+                uint32_t klb = kl_entry, biasb = bias_entry;
+                while (bm) {
+                    const uint32_t b = __ffs(bm) - 1u;
+                    bm &= bm - 1u;
+                    const uint32_t cb = sel9(c, b);
+                    const uint32_t low = (1u << b) - 1u;
+                    const uint32_t slot = T_ev + __popc((hbv & low) | ((tails & low) << 9)) + 2u * __popc(gm & low);   // after the tail event of op b-1
+                    if (b) {
+                        const uint32_t kt = k_first + klb;
+                        const uint4 m = __ldg(P.meta + kt);
+                        const bool live = ((m.z >> 30) & 1u) && m.x + 1u < m.y;
+                        const uint32_t ie = cb + biasb;                      // one past the last covered index
+                        if (ie - s_pos1[klb] >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
+                        P.events[slot - 1u] = ie;
+                        P.ref_end[kt] = live ? (ie < m.y ? ie : m.y) : 0u;
+                        P.ev_start[kt + 1u] = slot;
+                    }
+                    if (b < t.n_valid) {
+                        klb++;
+                        const uint32_t p1 = s_pos1[klb];
+                        P.events[slot] = p1;
+                        biasb = p1 - cb;
+                    }
+                }
             }
         }
     }
@@ -409,6 +485,8 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     P.chunk_agg = b->d_span_status.as<WalkAgg>();
     P.n_spans = b->n_spans;
     P.span_base = span0;
+    P.span_end = span1;
+    P.span_desc = b->d_span_desc.as<uint4>();
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.ev_start = b->d_ev_start.as<uint32_t>();
@@ -430,14 +508,19 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     k_span_agg<<<n, kWalkThreads, 0, ctx->stream>>>(P);
     k_span_scan_local<<<sc1 - sc0, 256, 0, ctx->stream>>>(P, sc0);
     k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, sc0, sc1, b->d_scan_carry.as<WalkAgg>());
+    k_span_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P);
     static const int minb = getenv("CSV_WALK_MINB") ? atoi(getenv("CSV_WALK_MINB")) : 4;    // tuning knob: CTAs per SM the compiler targets
+    static const int gmul = getenv("CSV_WALK_GRID") ? atoi(getenv("CSV_WALK_GRID")) : 8;    // persistent CTAs per SM in the grid (4 resident)
+    const uint32_t per_sm = (uint32_t)(minb == 5 || minb == 6 ? minb : 4);
+    const uint32_t cap = (uint32_t)ctx->sm_count * (gmul > 0 ? (uint32_t)gmul : per_sm);
+    const uint32_t grid = n < cap ? n : cap;
     if (p->want_depth && p->want_sigs) {
-        if (minb == 5) k_walk<true, true, 5><<<n, kWalkThreads, 0, ctx->stream>>>(P);
-        else if (minb == 6) k_walk<true, true, 6><<<n, kWalkThreads, 0, ctx->stream>>>(P);
-        else k_walk<true, true, 4><<<n, kWalkThreads, 0, ctx->stream>>>(P);
-    } else if (p->want_depth) k_walk<true, false, 4><<<n, kWalkThreads, 0, ctx->stream>>>(P);
-    else k_walk<false, true, 4><<<n, kWalkThreads, 0, ctx->stream>>>(P);
-    ctx->launches += 4;
+        if (minb == 5) k_walk<true, true, 5><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
+        else if (minb == 6) k_walk<true, true, 6><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
+        else k_walk<true, true, 4><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
+    } else if (p->want_depth) k_walk<true, false, 4><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
+    else k_walk<false, true, 4><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
+    ctx->launches += 5;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
