@@ -163,7 +163,7 @@ __global__ void k_db_degenerate(const DbParams P)
 }
 
 int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, uint64_t n_upper, const uint32_t* n_dev,
-                    uint32_t n_seg, double eps, int min_pts, int32_t* d_labels, int32_t* d_n_clusters)
+                    uint32_t n_seg, double eps, int min_pts, int32_t* d_labels, int32_t* d_n_clusters, bool value_sorted)
 {
     if (n_upper >= (1ull << 30)) { set_error("dbscan1d: %llu points exceed the 2^30 limit", (unsigned long long)n_upper); return CSV_ERR_LIMIT; }
     if (n_upper == 0) return CSV_OK;
@@ -195,7 +195,9 @@ int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, u
     ctx->launches++;
     SortBufs sb;
     sb.hi = nullptr; sb.hi2 = nullptr; sb.lo = P.keys; sb.lo2 = s[1].as<unsigned long long>(); sb.val = P.idx; sb.val2 = s[3].as<uint32_t>();
-    uint32_t mask = 0x0fu;
+    // value_sorted: inside every segment the points already come in ascending order (the batch's signature list):
+    // a stable sort on the segment bytes alone is then the sort by (segment, value)
+    uint32_t mask = value_sorted ? 0u : 0x0fu;
     for (int d = 0; d < 4; d++) if (d == 0 ? n_seg > 1 : (n_seg >> (8 * d))) mask |= 1u << (4 + d);
     CSV_TRY(radix_sort_pairs(ctx, sb, n_upper, n_dev, mask));
     k_db_core<<<grid, 256, 0, ctx->stream>>>(P);
@@ -230,7 +232,8 @@ int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, u
     uint32_t rmask = 0;
     for (int d = 0; d < 4; d++) if (d == 0 || (n_upper >> (8 * d))) rmask |= 1u << d;
     for (int d = 0; d < 4; d++) if (d == 0 ? n_seg > 1 : (n_seg >> (8 * d))) rmask |= 1u << (4 + d);
-    CSV_TRY(radix_sort_pairs(ctx, rb, n_upper, P.counters + 1, rmask));
+    // ... and the runs, found in (segment, value) order, are already in (segment, smallest input index) order
+    if (!value_sorted) CSV_TRY(radix_sort_pairs(ctx, rb, n_upper, P.counters + 1, rmask));
     k_db_ids<<<grid, 256, 0, ctx->stream>>>(P);
     k_db_labels<<<grid, 256, 0, ctx->stream>>>(P);
     ctx->launches += 2;

@@ -579,7 +579,7 @@ int launch_depth_begin(csv_ctx* ctx, csv_batch* b)
 int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t c)
 {
     TileParams P = tile_params(b);
-    static const int mult = getenv("CSV_TILE_GRID") ? atoi(getenv("CSV_TILE_GRID")) : 20;   // tuning knob: CTAs per SM in the grid
+    static const int mult = getenv("CSV_TILE_GRID") ? atoi(getenv("CSV_TILE_GRID")) : 96;   // tuning knob: CTAs per SM in the grid
     static const int minb = getenv("CSV_TILE_MINB") ? atoi(getenv("CSV_TILE_MINB")) : 4;
     for (const auto& tr : b->chunks[c].tiles) {
         P.t_begin = tr.first; P.t_end = tr.second;

@@ -2,11 +2,15 @@
 // vector<SVCall> (addSVCall, sv_object.cpp:22-33: ascending (start,end), equal
 // keys in reverse insertion order) and materialise the output SoA.
 //
-// The walk appends signatures in arbitrary order; the 128-bit key
-//   hi = owner region << 32 | start      lo = end << 32 | ~(global op index)
-// is unique, so one stable radix sort gives a deterministic total order:
-// insertion order in the reference is (record order, op order) == ascending
-// global op index, hence ~index sorts equal (start,end) in reverse insertion order.
+// The walk appends signatures in arbitrary order with the 128-bit key
+//   hi = owner region << 32 | start      lo = end << 32 | ~(global op index).
+// Insertion order in the reference is (record order, op order) == ascending global
+// op index, hence ~index puts equal (start,end) in reverse insertion order, and the
+// key is unique.  Only hi is radix-sorted (5 byte passes instead of 13: the tiny
+// passes of this side stream compete with the tile kernel for SM slots, so their
+// NUMBER is what costs); the order inside a run of equal (region, start) -- a
+// handful of entries, one per read over the same breakpoint -- is fixed by ranking
+// lo inside the run.
 #include "batch.cuh"
 #include "scan.cuh"
 
@@ -24,8 +28,28 @@ __global__ void k_sig_iota(uint32_t* val, const uint32_t* scalars)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) val[i] = i;
 }
 
+// position of every entry inside its run of equal hi = number of entries of the run with a smaller lo
+__global__ void k_sig_tiefix(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ raw_lo, const uint32_t* __restrict__ val,
+                             const uint32_t* scalars, uint32_t* out)
+{
+    const uint32_t n = scalars[SC_N_SIG_EFF];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long h = hi[i];
+        uint32_t a = i, b = i + 1;
+        while (a > 0 && hi[a - 1] == h) a--;
+        while (b < n && hi[b] == h) b++;
+        const uint32_t mine = val[i];
+        uint32_t rank = 0;
+        if (b - a > 1) {
+            const unsigned long long my = raw_lo[mine];
+            for (uint32_t j = a; j < b; j++) rank += raw_lo[val[j]] < my ? 1u : 0u;
+        }
+        out[a + rank] = mine;
+    }
+}
+
 struct GatherParams {
-    const unsigned long long *hi, *lo;
+    const unsigned long long *hi, *lo;      // hi: sorted; lo: emission order (indexed by slot)
     const uint32_t* val;
     const uint32_t* raw_k;
     const WalkAgg *span_pre, *chunk_agg;      // pre-pass prefixes: .qry = query consumed since the last record head before the span
@@ -45,8 +69,8 @@ __global__ void k_sig_gather(const GatherParams P)
 {
     const uint32_t n = P.scalars[SC_N_SIG_EFF];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long hi = P.hi[i], lo = P.lo[i];
         const uint32_t slot = P.val[i];
+        const unsigned long long hi = P.hi[i], lo = P.lo[slot];
         const uint32_t g = 0xffffffffu - (uint32_t)lo;
         const uint32_t k = P.raw_k[slot];
         const uint32_t read = P.ne_idx[k];
@@ -103,22 +127,20 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
     k_sig_clamp<<<1, 1, 0, ctx->stream>>>(scalars, cap);
     k_sig_iota<<<grid, 256, 0, ctx->stream>>>(b->d_sig_payload.as<uint32_t>(), scalars);
     ctx->launches += 2;
-    // alternates for the sort live in the output buffers' neighbours (ctx scratch)
     CSV_TRY(ctx->sort_tmp[1].ensure((size_t)cap * 8));
-    CSV_TRY(ctx->sort_tmp[2].ensure((size_t)cap * 8));
     CSV_TRY(ctx->sort_tmp[3].ensure((size_t)cap * 4));
     SortBufs sb;
-    sb.hi = b->d_sig_hi.as<unsigned long long>(); sb.lo = b->d_sig_lo.as<unsigned long long>(); sb.val = b->d_sig_payload.as<uint32_t>();
-    sb.hi2 = ctx->sort_tmp[1].as<unsigned long long>(); sb.lo2 = ctx->sort_tmp[2].as<unsigned long long>(); sb.val2 = ctx->sort_tmp[3].as<uint32_t>();
-    // bytes that can vary: ~op index (as many bytes as n_ops needs), end, start, owner region
-    uint32_t mask = 0;
-    for (int d = 0; d < 4; d++) if (d == 0 || (b->n_ops >> (8 * d))) mask |= 1u << d;
-    mask |= 0xf0u | 0xf00u;
-    for (int d = 0; d < 4; d++) if (d == 0 ? b->n_regions > 1 : (b->n_regions >> (8 * d))) mask |= 1u << (12 + d);
+    sb.hi = nullptr; sb.hi2 = nullptr;
+    sb.lo = b->d_sig_hi.as<unsigned long long>(); sb.lo2 = ctx->sort_tmp[1].as<unsigned long long>();
+    sb.val = b->d_sig_payload.as<uint32_t>(); sb.val2 = ctx->sort_tmp[3].as<uint32_t>();
+    uint32_t mask = 0x0fu;                                                       // start
+    for (int d = 0; d < 4; d++) if (d == 0 ? b->n_regions > 1 : (b->n_regions >> (8 * d))) mask |= 1u << (4 + d);   // owner region
     // n_dev is clamped inside the kernels through cap: pass the upper bound and the device count
     CSV_TRY(radix_sort_pairs(ctx, sb, cap, scalars + SC_N_SIG_EFF, mask));
+    k_sig_tiefix<<<grid, 256, 0, ctx->stream>>>(sb.lo, b->d_sig_lo.as<unsigned long long>(), sb.val, scalars, sb.val2);
+    ctx->launches++;
     GatherParams P;
-    P.hi = sb.hi; P.lo = sb.lo; P.val = sb.val;
+    P.hi = sb.lo; P.lo = b->d_sig_lo.as<unsigned long long>(); P.val = sb.val2;
     P.raw_k = b->d_sig_k.as<uint32_t>(); P.span_pre = b->d_span_pre.as<WalkAgg>(); P.chunk_agg = b->d_span_status.as<WalkAgg>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
     P.ne_idx = b->d_ne_idx.as<uint32_t>(); P.cig_off = b->d_cig_off.as<unsigned long long>(); P.cigar = b->d_cigar.as<uint32_t>();
     P.meta = b->d_meta.as<uint4>(); P.tids = b->d_tids.as<TidDev>(); P.scalars = scalars; P.cap = cap;
@@ -136,7 +158,8 @@ int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts)
 {
     CSV_TRY(b->d_labels.ensure((size_t)b->sig_cap * 4 + 16));
     return dbscan1d_device(ctx, b->d_out_start.as<int32_t>(), b->d_out_seg.as<uint32_t>(), b->sig_cap,
-                           b->d_scalars.as<uint32_t>() + SC_N_SIG_EFF, b->n_regions * 2, eps, min_pts, b->d_labels.as<int32_t>(), nullptr);
+                           b->d_scalars.as<uint32_t>() + SC_N_SIG_EFF, b->n_regions * 2, eps, min_pts, b->d_labels.as<int32_t>(), nullptr,
+                           true /* the signature list is sorted by (region, start) */);
 }
 
 }  // namespace csv
