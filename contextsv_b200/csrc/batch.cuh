@@ -6,7 +6,7 @@ namespace csv {
 constexpr uint32_t kNone = 0xffffffffu;
 
 // u32 slots of csv_batch::d_scalars
-enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_COUNT = 16 };
+enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_HAS_EMPTY = 6 /* a record without CIGAR: tables need compaction */, SC_COUNT = 16 };
 
 struct SigRaw {          // emission-order signature records (device)
     unsigned long long* key_hi;   // owner region << 32 | start

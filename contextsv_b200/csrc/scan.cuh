@@ -60,10 +60,11 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 template <class In, class Out>
 __global__ void __launch_bounds__(kScanThreads) k_chained_scan(In in, Out out, const uint32_t* n_dev, uint64_t n_host,
                                                                uint32_t* ticket, unsigned long long* status, uint32_t epoch,
-                                                               uint32_t* total_out)
+                                                               uint32_t* total_out, const uint32_t* run_if)
 {
     __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_tile, s_excl;
+    if (run_if && *run_if == 0u) return;            // optional device-side switch: the whole launch is a no-op
     const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
     const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
     if (n == 0) { if (total_out && blockIdx.x == 0 && threadIdx.x == 0) *total_out = 0; return; }
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kScanThreads) k_chained_scan(In in, Out out, c
 }
 
 template <class In, class Out>
-int chained_scan(csv_ctx* ctx, In in, Out out, uint64_t n_upper, const uint32_t* n_dev, uint32_t* total_out)
+int chained_scan(csv_ctx* ctx, In in, Out out, uint64_t n_upper, const uint32_t* n_dev, uint32_t* total_out, const uint32_t* run_if = nullptr)
 {
     uint64_t tiles = (n_upper + kScanTile - 1) / kScanTile;
     if (tiles == 0) tiles = 1;
@@ -104,7 +105,7 @@ int chained_scan(csv_ctx* ctx, In in, Out out, uint64_t n_upper, const uint32_t*
     uint32_t epoch = next_epoch(ctx);
     uint64_t grid = tiles < (uint64_t)ctx->sm_count * 8 ? tiles : (uint64_t)ctx->sm_count * 8;
     k_chained_scan<<<(unsigned)grid, kScanThreads, 0, ctx->stream>>>(in, out, n_dev, n_upper, ticket,
-                                                                    ctx->scan_status.as<unsigned long long>(), epoch, total_out);
+                                                                    ctx->scan_status.as<unsigned long long>(), epoch, total_out, run_if);
     ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
