@@ -77,6 +77,7 @@ namespace csv {
 int launch_prep(csv_ctx* ctx, csv_batch* b, uint32_t min_mapq);
 int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1);
 int launch_chunk_bounds(csv_ctx* ctx, csv_batch* b);
+int launch_tile_hi(csv_ctx* ctx, csv_batch* b);
 int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t chunk);
 int launch_depth_begin(csv_ctx* ctx, csv_batch* b);
 int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t chunk);

@@ -423,6 +423,8 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_fork, 0));
         TileScope ts(ctx);
         CSV_TRY(launch_depth_begin(ctx, b));
+        StageTimer t(ctx, ST_TILE_RANGES);
+        CSV_TRY(launch_tile_hi(ctx, b));                                 // beside the walk
     }
     for (uint32_t c = 0; c < nc; c++) {
         { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1)); }

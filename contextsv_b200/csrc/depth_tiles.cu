@@ -137,23 +137,37 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
 }
 
 // ------------------------------------------------------------ tile -> event slice
-__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t t_begin, uint32_t t_end, const unsigned long long* __restrict__ key,
-                              const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
-                              uint32_t* scalars, const uint32_t* bounds, uint2* tile_ev, uint4* tile_q, uint32_t* wide_list)
+// Static half: r_hi = first record with (tid, pos0 + 1) >= (tid, T1) only depends on the sort keys, so it runs on the
+// tile stream while the walk is busy; it is parked in tile_ev[t].y.
+__global__ void k_tile_hi(const uint4* __restrict__ tile_desc, uint32_t t_begin, uint32_t t_end, const unsigned long long* __restrict__ key,
+                          const uint32_t* scalars, uint2* tile_ev)
 {
-    const uint32_t n = scalars[SC_N_NONEMPTY], kb = bounds[0];
+    const uint32_t n = scalars[SC_N_NONEMPTY];
     for (uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x; t < t_end; t += gridDim.x * blockDim.x) {
         const uint4 d = tile_desc[t];            // {region, positions, T0, tid}
         const unsigned long long key_hi = ((unsigned long long)d.w << 32) | (unsigned long long)(d.z + d.y);   // (tid, T1)
-        const unsigned long long key_lo = ((unsigned long long)d.w << 32) | (unsigned long long)d.z;           // (tid, T0)
-        uint32_t lo = kb, hi = n;
-        while (lo < hi) {                        // r_hi: first record with (tid, pos0 + 1) >= (tid, T1)
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
             const uint32_t mid = lo + ((hi - lo) >> 1);
             if (key[mid] < key_hi) lo = mid + 1; else hi = mid;
         }
-        const uint32_t r_hi = lo;
-        lo = kb; hi = r_hi;
-        while (lo < hi) {                        // r_lo: first record with running max (tid, ref_end) > (tid, T0)
+        tile_ev[t] = make_uint2(0u, lo);
+    }
+}
+
+// After the walk: r_lo = first record whose running max (tid, ref_end) exceeds (tid, T0); the records [r_lo, r_hi) are
+// the ones that can touch the tile, their events one contiguous slice.
+__global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t t_begin, uint32_t t_end,
+                              const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
+                              uint32_t* scalars, const uint32_t* bounds, uint2* tile_ev, uint4* tile_q, uint32_t* wide_list)
+{
+    const uint32_t kb = bounds[0];
+    for (uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x; t < t_end; t += gridDim.x * blockDim.x) {
+        const uint4 d = tile_desc[t];
+        const unsigned long long key_lo = ((unsigned long long)d.w << 32) | (unsigned long long)d.z;           // (tid, T0)
+        const uint32_t r_hi = tile_ev[t].y;
+        uint32_t lo = kb < r_hi ? kb : r_hi, hi = r_hi;
+        while (lo < hi) {
             const uint32_t mid = lo + ((hi - lo) >> 1);
             if (pmax[mid] <= key_lo) lo = mid + 1; else hi = mid;
         }
@@ -192,6 +206,18 @@ int launch_chunk_bounds(csv_ctx* ctx, csv_batch* b)
     return CSV_OK;
 }
 
+// static half of the tile ranges, all tiles: needs the sort keys only (prep)
+int launch_tile_hi(csv_ctx* ctx, csv_batch* b)
+{
+    if (b->n_tiles == 0) return CSV_OK;
+    const uint32_t grid_t = (b->n_tiles + 255) / 256;
+    k_tile_hi<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), 0u, b->n_tiles, b->d_key.as<unsigned long long>(), b->d_scalars.as<uint32_t>(),
+                                              b->d_tile_ev.as<uint2>());
+    ctx->launches++;
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
 // event slices of the tiles of pipeline chunk c (needs the walk of chunk c + 1: see csv_scan_run)
 int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
 {
@@ -213,7 +239,7 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
     }
     for (const auto& tr : ch.tiles) {
         const uint32_t grid_t = (tr.second - tr.first + 255) / 256;
-        k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), tr.first, tr.second, meta, pmax, b->d_ev_start.as<uint32_t>(),
+        k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), tr.first, tr.second, pmax, b->d_ev_start.as<uint32_t>(),
                                                       scalars, bounds, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_wide_list.as<uint32_t>());
         ctx->launches++;
     }

@@ -1,7 +1,7 @@
 // cnv_caller_gpu.cpp -- drop-in definition of CNVCaller::calculateMeanChromosomeCoverage
 // (include/cnv_caller.h:104, src/cnv_caller.cpp:415-556): same signature, same messages, same
 // containers filled; the per-base loop and the two reductions run on the GPU through the C ABI.
-// One decode of the BAM feeds every chromosome in one batch (the reference iterates per chromosome).
+// Chromosomes are scanned one after the other, each in as many shards as its CIGAR ops need.
 #include "cnv_caller.h"
 
 #include <htslib/sam.h>
@@ -28,10 +28,6 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
     bam1_t* bam_record = bam_init1();
     if (!bam_record) { bam_hdr_destroy(bam_header); sam_close(bam_file); printError("ERROR: Could not initialize BAM record."); return; }
 
-    // pack every requested chromosome (file order == coordinate order inside a chromosome)
-    csvhost::PackedReads reads;
-    std::vector<csv_region> regions;
-    std::vector<std::string> region_chr;
     int current_chr = 0;
     const int total_chr_count = (int)chromosomes.size();
     std::vector<std::pair<int, std::string>> by_tid;
@@ -51,39 +47,51 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
         by_tid.emplace_back(tid, chr);
         hts_itr_destroy(bam_iter);
     }
-    // the batch must be coordinate-sorted across contigs: visit the contigs in header order
+    // Contigs in header order.  Records stream into a shard; whenever the shard would exceed the ops one batch may hold
+    // (a batch takes < 2^31: 60x ONT is ~3.7e10 over the genome), the depth slice up to the current position is
+    // scanned, and only the records that reach past the cut stay as the halo of the next shard -- the region sharding
+    // of SURVEY 8e, in time instead of across GPUs, with bounded host memory.
     std::sort(by_tid.begin(), by_tid.end());
+    csv_ctx* ctx = csvhost::thread_context();
+    const uint64_t max_ops = csvhost::max_ops_per_batch();
+    bool failed = false;
     for (const auto& tc : by_tid) {
         hts_itr_t* it = sam_itr_querys(bam_index, bam_header, tc.second.c_str());
         if (!it) continue;
-        csvhost::pack_iterator(bam_file, it, bam_record, reads, false);
-        hts_itr_destroy(it);
+        std::vector<uint32_t>& depth = chr_pos_depth_map[tc.second];
         const uint32_t size = bam_header->target_len[tc.first] + 1;
-        regions.push_back(csv_region{tc.first, 0u, size, size});
-        region_chr.push_back(tc.second);
-    }
-
-    if (!regions.empty()) {
-        csv_ctx* ctx = csvhost::thread_context();
-        const csv_reads view = reads.view();
-        csv_batch* batch = nullptr;
-        const csv_scan_params params = {50, 20, 1, 0, 0};
-        std::vector<uint64_t> sums(regions.size());
-        std::vector<uint32_t> nonzero(regions.size());
-        int rc = csv_batch_upload(ctx, &view, (uint32_t)regions.size(), regions.data(), &batch);
-        if (rc == CSV_OK) rc = csv_scan_run(ctx, batch, &params);
-        if (rc == CSV_OK) rc = csv_depth_stats(ctx, batch, sums.data(), nonzero.data());
-        for (size_t i = 0; rc == CSV_OK && i < regions.size(); i++)
-            rc = csv_depth_fetch(ctx, batch, (uint32_t)i, chr_pos_depth_map[region_chr[i]].data());
-        csv_batch_free(ctx, batch);
-        if (rc != CSV_OK) printError(std::string("ERROR: GPU depth pass failed: ") + csv_last_error());
-        else for (size_t i = 0; i < regions.size(); i++) {
-            const uint64_t cum_depth = sums[i];
-            const uint32_t pos_count = nonzero[i];
-            const double mean_chr_cov = (pos_count > 0) ? static_cast<double>(cum_depth) / static_cast<double>(pos_count) : 0.0;
-            printMessage("Mean coverage for chromosome " + region_chr[i] + ": " + std::to_string(mean_chr_cov));
-            if (mean_chr_cov != 0.0) chr_mean_cov_map[region_chr[i]] = mean_chr_cov;
+        uint64_t cum_depth = 0;
+        uint32_t pos_count = 0, beg = 0;
+        csvhost::PackedReads reads;
+        auto flush = [&](uint32_t end) {                       // depth slice [beg, end) from the records packed so far
+            if (end <= beg || failed) { beg = std::max(beg, end); return; }
+            const csv_region reg = {tc.first, beg, end, size};
+            const csv_reads view = reads.view();
+            uint64_t sum = 0; uint32_t nz = 0;
+            if (csv_depth(ctx, &view, &reg, depth.data() + beg, &sum, &nz) != CSV_OK) {
+                printError(std::string("ERROR: GPU depth pass failed: ") + csv_last_error());
+                failed = true;
+            }
+            cum_depth += sum; pos_count += nz;
+            beg = end;
+        };
+        int32_t last_pos = -2;
+        while (sam_itr_next(bam_file, it, bam_record) >= 0) {
+            const int32_t pos = (int32_t)bam_record->core.pos;
+            if (reads.ops() + bam_record->core.n_cigar > max_ops && pos != last_pos && reads.size() > 0) {
+                const uint32_t cut = std::min<uint32_t>((uint32_t)pos + 1u, size);       // records from here on start at or after the cut
+                flush(cut);
+                reads.keep_reaching(cut);
+            }
+            reads.append(bam_record, false);
+            last_pos = pos;
         }
+        hts_itr_destroy(it);
+        flush(size);
+        if (failed) break;
+        const double mean_chr_cov = (pos_count > 0) ? static_cast<double>(cum_depth) / static_cast<double>(pos_count) : 0.0;
+        printMessage("Mean coverage for chromosome " + tc.second + ": " + std::to_string(mean_chr_cov));
+        if (mean_chr_cov != 0.0) chr_mean_cov_map[tc.second] = mean_chr_cov;
     }
 
     printMessage("Closing BAM file " + bam_filepath);

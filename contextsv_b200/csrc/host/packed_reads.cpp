@@ -1,5 +1,6 @@
 #include "packed_reads.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace csvhost {
@@ -14,16 +15,49 @@ void PackedReads::append(const bam1_t* b, bool keep_seq)
     const uint32_t* c = bam_get_cigar(b);
     const uint32_t n = b->core.n_cigar;
     bool want_seq = false;
+    uint32_t rlen = 0;
     for (uint32_t i = 0; i < n; i++) {
         cigar.push_back(c[i]);
         const uint32_t op = bam_cigar_op(c[i]), len = bam_cigar_oplen(c[i]);
         if (len == 50 && (op == BAM_CINS || op == BAM_CSOFT_CLIP)) want_seq = true;
+        if (op == BAM_CMATCH || op == BAM_CDEL || op == BAM_CREF_SKIP || op == BAM_CEQUAL || op == BAM_CDIFF) rlen += len;
     }
     cig_off.push_back(cigar.size());
+    ref_end.push_back((uint32_t)b->core.pos + 1u + rlen);
     if (keep_seq && want_seq) {
         const uint8_t* s = bam_get_seq(b);
         seq4[idx].assign(s, s + ((size_t)b->core.l_qseq + 1) / 2);
     }
+}
+
+void PackedReads::clear()
+{
+    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); seq4.clear();
+    cig_off.assign(1, 0);
+}
+
+void PackedReads::keep_reaching(uint32_t cut)
+{
+    PackedReads k;
+    for (size_t i = 0; i < pos0.size(); i++) {
+        if (ref_end[i] <= cut) continue;
+        k.tid.push_back(tid[i]); k.pos0.push_back(pos0[i]); k.flag.push_back(flag[i]); k.mapq.push_back(mapq[i]); k.ref_end.push_back(ref_end[i]);
+        k.cigar.insert(k.cigar.end(), cigar.begin() + (ptrdiff_t)cig_off[i], cigar.begin() + (ptrdiff_t)cig_off[i + 1]);
+        k.cig_off.push_back(k.cigar.size());
+    }
+    *this = std::move(k);
+}
+
+uint64_t max_ops_per_batch()
+{
+    static const uint64_t v = [] {
+        const char* e = std::getenv("CONTEXTSV_MAX_OPS");
+        const uint64_t hard = (1ull << 31) - (1ull << 20);
+        if (!e) return hard;
+        const uint64_t x = std::strtoull(e, nullptr, 10);
+        return x == 0 || x > hard ? hard : x;
+    }();
+    return v;
 }
 
 csv_reads PackedReads::view() const

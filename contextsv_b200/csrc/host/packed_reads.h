@@ -21,6 +21,7 @@ struct PackedReads {
     std::vector<uint8_t> mapq;
     std::vector<uint64_t> cig_off{0};
     std::vector<uint32_t> cigar;
+    std::vector<uint32_t> ref_end;   // pos0 + 1 + reference bases consumed: depth index one past the last covered base
     // 4-bit bases of the few records that carry an I / S op of exactly 50 bases: the only place the
     // reference looks at the sequence on this path (literal ALT allele, src/sv_caller.cpp:572-591)
     std::unordered_map<uint32_t, std::vector<uint8_t>> seq4;
@@ -28,7 +29,14 @@ struct PackedReads {
     void append(const bam1_t* b, bool keep_seq);
     csv_reads view() const;
     size_t size() const { return pos0.size(); }
+    uint64_t ops() const { return cigar.size(); }
+    void clear();
+    // keeps only the records that reach past depth index `cut` (the halo of the next shard), in order
+    void keep_reaching(uint32_t cut);
 };
+
+// CIGAR ops one batch may hold: the C ABI takes < 2^31; CONTEXTSV_MAX_OPS lowers it (tests, small GPUs)
+uint64_t max_ops_per_batch();
 
 // Every record an iterator yields, in file order.
 void pack_iterator(samFile* fp, hts_itr_t* itr, bam1_t* scratch, PackedReads& out, bool keep_seq);
