@@ -351,7 +351,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_tile_sum.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_nz.ensure(nt * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_sum.ensure(n_regions * 8, &ctx->pool)); CSV_TRY(b->d_nz.ensure(n_regions * 4, &ctx->pool));
     CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));
-    CSV_TRY(b->d_sig_qpos.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
     CSV_TRY(b->d_out_start.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_end.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_kind.ensure(sc, &ctx->pool));
     CSV_TRY(b->d_out_read.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_op.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_qpos.ensure(sc * 4, &ctx->pool));
     CSV_TRY(b->d_out_seg.ensure(sc * 4, &ctx->pool));

@@ -107,7 +107,6 @@ __device__ __forceinline__ ThreadOps load_ops(const uint32_t* __restrict__ cigar
 // Class bit of a CIGAR word without isolating its op nibble: the per-op bit masks are replicated in both
 // 16-bit halves, so a funnel shift by (w & 31) lands on the right bit whatever the length's low bit is.
 constexpr uint32_t kRefLut = kRefMask | (kRefMask << 16);
-constexpr uint32_t kQryLut = kQryMask | (kQryMask << 16);
 constexpr uint32_t kGapLut = kGapMask | (kGapMask << 16);
 constexpr uint32_t kSigLut = kSigMask | (kSigMask << 16);
 __device__ __forceinline__ uint32_t class_bit(uint32_t lut, uint32_t w) { return __funnelshift_r(lut, lut, w) & 1u; }
@@ -498,7 +497,6 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     P.sig.key_hi = b->d_sig_hi.as<unsigned long long>();
     P.sig.key_lo = b->d_sig_lo.as<unsigned long long>();
     P.sig.k = b->d_sig_k.as<uint32_t>();
-    P.sig.qpos = b->d_sig_qpos.as<uint32_t>();
     P.sig.kind = b->d_sig_kind.as<uint8_t>();
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
