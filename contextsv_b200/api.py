@@ -251,6 +251,28 @@ class DBSCAN1D:
         return out[:m]
 
 
+class DBSCAN:
+    """include/dbscan.h:11-33: the 2-D DBSCAN mergeSVs runs on SV calls (intervals, reciprocal-overlap distance).
+    fit() takes the calls' (start, end) columns instead of a vector<SVCall>."""
+
+    def __init__(self, epsilon, minPts, ctx=None):
+        self.epsilon = float(epsilon)
+        self.minPts = int(minPts)
+        self.clusters = np.zeros(0, np.int32)
+        self._ctx = ctx
+
+    def fit(self, start, end):
+        ctx = self._ctx or default_context()
+        s = np.ascontiguousarray(start, np.uint32); e = np.ascontiguousarray(end, np.uint32)
+        assert len(s) == len(e)
+        lab = np.zeros(len(s), np.int32)
+        check(lib().csv_dbscan2d(ctx.h, ptr(s), ptr(e), len(s), self.epsilon, self.minPts, ptr(lab)))
+        self.clusters = lab
+
+    def getClusters(self):
+        return self.clusters
+
+
 def dbscan1d_segments(points, seg_id, n_seg, eps, min_pts, ctx=None):
     """Many independent DBSCAN1D fits in one launch sequence (csv_dbscan1d_seg)."""
     ctx = ctx or default_context()

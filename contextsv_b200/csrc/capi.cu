@@ -162,6 +162,7 @@ void csv_ctx_destroy(csv_ctx* ctx)
     ctx->tickets.release(); ctx->scan_status.release();
     for (auto& b : ctx->sort_tmp) b.release();
     for (auto& b : ctx->db) b.release();
+    for (auto& b : ctx->db2) b.release();
     if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -611,6 +612,25 @@ int csv_dbscan1d_seg(csv_ctx* ctx, const int32_t* pts, const uint32_t* seg_id, u
 int csv_dbscan1d(csv_ctx* ctx, const int32_t* pts, uint64_t n, double eps, int min_pts, int32_t* labels_out, int32_t* n_clusters_out)
 {
     return csv_dbscan1d_seg(ctx, pts, nullptr, n, 1, eps, min_pts, labels_out, n_clusters_out);
+}
+
+int csv_dbscan2d(csv_ctx* ctx, const uint32_t* start, const uint32_t* end, uint64_t n, double eps, int min_pts, int32_t* labels_out)
+{
+    if (!ctx || (n && (!start || !end || !labels_out))) { set_error("csv_dbscan2d: null argument"); return CSV_ERR_ARG; }
+    if (n == 0) return CSV_OK;
+    if (n >= (1ull << 30)) { set_error("csv_dbscan2d: %llu intervals exceed the 2^30 limit", (unsigned long long)n); return CSV_ERR_LIMIT; }
+    CSV_CUDA(cudaSetDevice(ctx->device));
+    CSV_TRY(side_join(ctx));
+    DevBuf& d_in = ctx->sort_tmp[4]; DevBuf& d_lab = ctx->sort_tmp[5];
+    CSV_TRY(d_in.ensure(n * 8)); CSV_TRY(d_lab.ensure(n * 4));
+    cudaStream_t st = ctx->stream;
+    uint32_t* d_start = d_in.as<uint32_t>(); uint32_t* d_end = d_start + n;
+    CSV_CUDA(cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
+    CSV_CUDA(cudaMemcpyAsync(d_end, end, n * 4, cudaMemcpyHostToDevice, st));
+    CSV_TRY(dbscan2d_device(ctx, d_start, d_end, n, eps, min_pts, d_lab.as<int32_t>()));
+    CSV_CUDA(cudaMemcpyAsync(labels_out, d_lab.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CSV_CUDA(cudaStreamSynchronize(st));
+    return CSV_OK;
 }
 
 uint64_t csv_largest_cluster(const int32_t* pts, const int32_t* labels, uint64_t n, int32_t* out)

@@ -127,6 +127,7 @@ struct csv_ctx {
     csv::DevBuf scan_status;            // u64 status words for chained scans / radix passes
     csv::DevBuf sort_tmp[6];            // radix sort ping-pong buffers + histograms
     csv::DevBuf db[16];                 // DBSCAN scratch
+    csv::DevBuf db2[14];                // 2-D DBSCAN scratch
     void* pinned_small = nullptr;       // 4 KB pinned staging for tiny D2H reads
     int sm_count = csv::kSMs;
     csv::DevPool pool;                  // parked batch buffers

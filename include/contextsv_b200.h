@@ -184,6 +184,13 @@ int csv_dbscan1d_seg(csv_ctx* ctx, const int32_t* pts, const uint32_t* seg_id, u
                      uint32_t n_seg, double eps, int min_pts, int32_t* labels_out,
                      int32_t* n_clusters_out /* [n_seg] or NULL */);
 
+/* DBSCAN::fit + getClusters (include/dbscan.h:11-33, src/dbscan.cpp:9-81): the 2-D clustering mergeSVs
+ * (src/sv_object.cpp:45-269) runs on the SV calls of one type -- points are intervals (start, end), the distance is
+ * the minimum reciprocal overlap.  labels: cluster id >= 0, -2 noise (-1 only in the reference's own degenerate
+ * min_pts <= 0 cases), exactly as the reference assigns them for this input order. */
+int csv_dbscan2d(csv_ctx* ctx, const uint32_t* start, const uint32_t* end, uint64_t n, double eps, int min_pts,
+                 int32_t* labels_out);
+
 /* DBSCAN1D::getLargestCluster (dbscan1d.cpp:72-90) on labels from a fit: host-side
  * helper, no device work.  Returns the number of points written to out. */
 uint64_t csv_largest_cluster(const int32_t* pts, const int32_t* labels, uint64_t n, int32_t* out);

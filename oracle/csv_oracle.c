@@ -247,6 +247,52 @@ void orc_dbscan1d(const int32_t* pts, uint64_t n, double eps, int min_pts, int32
     free(seeds.v); free(result.v);
 }
 
+/* ---- DBSCAN::fit, 2-D (src/dbscan.cpp:9-81): the clustering mergeSVs runs on the signatures ("next" row 8f-1) */
+static double db2_distance(uint32_t s1, uint32_t e1, uint32_t s2, uint32_t e2)   /* :69-81 */
+{
+    int me = (int)e1 < (int)e2 ? (int)e1 : (int)e2, ms = (int)s1 > (int)s2 ? (int)s1 : (int)s2;
+    int overlap = me - ms > 0 ? me - ms : 0;
+    int length1 = (int)(e1 - s1), length2 = (int)(e2 - s2);
+    double a = (double)overlap / (double)length1, b = (double)overlap / (double)length2;
+    double m = (b < a) ? b : a;                                    /* std::min(a, b) */
+    return 1.0 - m;
+}
+static void region_query2(const uint32_t* st, const uint32_t* en, uint64_t n, size_t q, double eps, idxvec* out)   /* :59-67 */
+{
+    out->n = 0;
+    for (size_t i = 0; i < n; i++) if (db2_distance(st[q], en[q], st[i], en[i]) <= eps) iv_push(out, i);
+}
+void orc_dbscan2d(const uint32_t* start, const uint32_t* end, uint64_t n, double eps, int min_pts, int32_t* labels)
+{
+    int cluster_id = 0;
+    for (uint64_t i = 0; i < n; i++) labels[i] = -1;               /* :11 */
+    idxvec seeds = {0, 0, 0}, result = {0, 0, 0};
+    for (size_t i = 0; i < n; i++) {                               /* :13 */
+        if (labels[i] != -1) continue;
+        region_query2(start, end, n, i, eps, &seeds);              /* expandCluster :27-57 */
+        if ((int)seeds.n < min_pts) { labels[i] = -2; continue; }
+        for (size_t s = 0; s < seeds.n; s++) labels[seeds.v[s]] = cluster_id;   /* :33-35 */
+        size_t w = 0;                                              /* :37 erase(remove(i)) */
+        for (size_t s = 0; s < seeds.n; s++) if (seeds.v[s] != i) seeds.v[w++] = seeds.v[s];
+        seeds.n = w;
+        while (seeds.n) {
+            size_t cur = seeds.v[--seeds.n];                       /* :40-41 back(), pop_back() */
+            region_query2(start, end, n, cur, eps, &result);
+            if ((int)result.n >= min_pts) {
+                for (size_t q = 0; q < result.n; q++) {
+                    size_t p = result.v[q];
+                    if (labels[p] == -1 || labels[p] == -2) {
+                        if (labels[p] == -1) iv_push(&seeds, p);
+                        labels[p] = cluster_id;
+                    }
+                }
+            }
+        }
+        ++cluster_id;
+    }
+    free(seeds.v); free(result.v);
+}
+
 typedef struct { int32_t v; uint64_t i; } vi_t;
 static int vi_cmp(const void* a, const void* b)
 {

@@ -77,6 +77,9 @@ void orc_dbscan1d(const int32_t* pts, uint64_t n, double eps, int min_pts,
 void orc_dbscan1d_fast(const int32_t* pts, uint64_t n, double eps, int min_pts,
                        int32_t* labels);
 
+/* dbscan.cpp:9-81 (2-D DBSCAN::fit over intervals, reciprocal-overlap distance), literal sequential O(N^2). */
+void orc_dbscan2d(const uint32_t* start, const uint32_t* end, uint64_t n, double eps, int min_pts, int32_t* labels);
+
 /* dbscan1d.cpp:72-90: points of the first cluster id >= 0 with the strictly
  * largest size, in input order.  Returns their count; with no cluster id >= 0 the reference returns cluster_map[-1]. */
 uint64_t orc_largest_cluster(const int32_t* pts, const int32_t* labels,

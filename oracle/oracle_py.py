@@ -115,6 +115,12 @@ class Oracle:
         fn(_p(pts), C.c_uint64(len(pts)), C.c_double(eps), C.c_int(min_pts), _p(lab))
         return lab
 
+    def dbscan2d(self, start, end, eps, min_pts):
+        start = np.ascontiguousarray(start, np.uint32); end = np.ascontiguousarray(end, np.uint32)
+        lab = np.zeros(len(start), np.int32)
+        self.lib.orc_dbscan2d(_p(start), _p(end), C.c_uint64(len(start)), C.c_double(eps), C.c_int(min_pts), _p(lab))
+        return lab
+
     def largest_cluster(self, pts, labels):
         pts = np.ascontiguousarray(pts, np.int32); labels = np.ascontiguousarray(labels, np.int32)
         out = np.zeros(max(len(pts), 1), np.int32)

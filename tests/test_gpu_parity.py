@@ -265,6 +265,34 @@ def test_dbscan1d_fuzz_and_large(ctx, oracle):
         assert np.array_equal(db.getClusters(), want)
 
 
+def test_dbscan2d_golden_fuzz_and_large(ctx, oracle):
+    """DBSCAN::fit over intervals (SURVEY 8f-1): golden vectors of the compiled reference (closed-form AND literal
+    path: eps >= 1, eps < 0, zero lengths), a fuzz against the oracle, and signature-shaped sets the closed form
+    handles at sizes where the O(N^2) oracle still finishes."""
+    for i, st, en, eps, mp, want in util.golden_db2_cases():
+        db = api.DBSCAN(eps, mp, ctx); db.fit(st, en)
+        assert np.array_equal(db.getClusters(), want), (i, eps, mp)
+    rng = np.random.default_rng(12)
+    for it in range(150):
+        n = int(rng.integers(0, 400))
+        centers = rng.integers(0, 20000, max(1, n // 8 + 1))
+        st = (rng.choice(centers, n) + rng.integers(0, 30, n)).astype(np.uint32)
+        en = (st + rng.choice([1, 49, 50, 80, 300, 5000], n) + rng.integers(0, 5, n)).astype(np.uint32)
+        eps = float(rng.choice([0, 0.02, 0.1, 0.25, 0.5, 0.8, 0.999])); mp = int(rng.choice([0, 1, 2, 3, 5, 10]))
+        db = api.DBSCAN(eps, mp, ctx); db.fit(st, en)
+        assert np.array_equal(db.getClusters(), oracle.dbscan2d(st, en, eps, mp)), (it, n, eps, mp)
+    for n, eps, mp in ((6000, 0.1, 2), (20000, 0.1, 3), (20000, 0.3, 5)):
+        centers = rng.integers(0, 40_000_000, n // 20)
+        lens = rng.integers(50, 5000, n // 20)
+        pick = rng.integers(0, n // 20, n)
+        st = (centers[pick] + np.rint(rng.normal(0, 8, n)).astype(np.int64)).astype(np.uint32)
+        en = (st + lens[pick] + np.rint(rng.normal(0, 6, n)).astype(np.int64) + 1).astype(np.uint32)
+        order = np.lexsort((en, st))                       # mergeSVs sees the calls in vector order
+        st, en = st[order], en[order]
+        db = api.DBSCAN(eps, mp, ctx); db.fit(st, en)
+        assert np.array_equal(db.getClusters(), oracle.dbscan2d(st, en, eps, mp)), (n, eps, mp)
+
+
 def test_dbscan1d_segments(ctx, oracle):
     rng = np.random.default_rng(4)
     n, n_seg = 5000, 7

@@ -88,3 +88,22 @@ def test_reference_depth_map_resize(oracle, reference):
     d, s, nz, mean = reference.depth(r, 0, [30000], alloc_size=1234)
     d2, s2, nz2 = oracle.depth(r, 0, 30001)
     assert np.array_equal(d, d2) and s == s2 and nz == nz2
+
+
+def test_dbscan2d_restatement_against_golden_and_reference():
+    """orc_dbscan2d (dbscan.cpp:9-81 restated) vs the committed outputs of the compiled reference, and live where
+    oracle/_ref exists -- degenerate eps / min_pts / zero lengths included."""
+    from oracle.oracle_py import Oracle, ref_available, Reference
+    O = Oracle()
+    for i, st, en, eps, mp, want in util.golden_db2_cases():
+        assert np.array_equal(O.dbscan2d(st, en, eps, mp), want), i
+    if not ref_available():
+        return
+    R = Reference()
+    rng = np.random.default_rng(8)
+    for it in range(150):
+        n = int(rng.integers(0, 100))
+        st = rng.integers(0, 800, n).astype(np.uint32)
+        en = (st + rng.choice([0, 1, 20, 50, 200], n)).astype(np.uint32)
+        eps = float(rng.choice([-0.5, 0, 0.1, 0.4, 0.99, 1.0, 2.0])); mp = int(rng.choice([-2, 0, 1, 2, 4]))
+        assert np.array_equal(O.dbscan2d(st, en, eps, mp), R.dbscan2d(st, en, eps, mp)), (it, eps, mp)

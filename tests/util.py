@@ -124,3 +124,14 @@ def golden_cg_answer(i, tid):
     if q + "_l2" in g.files:
         ans["l2par"] = [int(x) for x in g[q + "_l2par"]]; ans["l2pos"] = g[q + "_l2pos"]; ans["l2"] = g[q + "_l2"]
     return ans
+
+
+GOLDEN_DB2 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_db2_v1.npz")
+
+
+def golden_db2_cases():
+    """2-D DBSCAN::fit cases: (start, end, eps, min_pts, labels of the compiled reference)."""
+    g = np.load(GOLDEN_DB2)
+    for i in range(int(g["n"][0])):
+        eps, mp = g["c%d_par" % i]
+        yield i, g["c%d_start" % i], g["c%d_end" % i], float(eps), int(mp), g["c%d_labels" % i]
