@@ -33,7 +33,20 @@ METRIC = "aligned reads/sec (CIGAR scan+depth+DBSCAN1D)"
 DB_EPS, DB_MIN_PTS = 100.0, 5        # the reference's own DBSCAN1D parameters (sv_caller.cpp:270)
 
 
+SYNTH_KW = {
+    # BASELINE configs[2] in small: one chromosome of 60x ONT ultra-long reads (N50 50 kb, ~10 % indel rate => ~0.2 CIGAR
+    # ops per aligned base; the whole genome at this depth is ~3.7e10 ops and is scanned as a stream of such shards)
+    "ont60x_chr20": dict(profile=1, coverage=60.0, read_len_mean=50000.0, indel_rate=0.10, indel_len_max=4),
+    # BASELINE configs[4] in small: SV-rich set with per-read breakpoint jitter (100k SVs over the genome ~ 8.5k on chr1)
+    "svrich_chr1": dict(sv_jitter_sd=10.0),
+}
+
+
 def workload_contigs(name):
+    if name == "ont60x_chr20":
+        return [shard.GRCH38[19][1]], 500
+    if name == "svrich_chr1":
+        return [shard.GRCH38[0][1]], 8500
     if name == "wgs30x":
         return [l for _, l in shard.GRCH38], 25000
     if name == "chr1_5":
@@ -46,7 +59,9 @@ def workload_contigs(name):
 
 
 def workload_name(name):
-    return {"wgs30x": "synthetic whole-genome 30x HiFi GRCh38-shaped (24 contigs, 15 kb reads, 25k SVs) [BASELINE configs[1]]",
+    return {"ont60x_chr20": "synthetic 60x ONT ultra-long chr20 (N50 50 kb, dense CIGAR) [BASELINE configs[2], one shard of the stream]",
+            "svrich_chr1": "synthetic 30x HiFi chr1, SV-rich (8.5k SVs, breakpoint jitter) [BASELINE configs[4], one chromosome]",
+            "wgs30x": "synthetic whole-genome 30x HiFi GRCh38-shaped (24 contigs, 15 kb reads, 25k SVs) [BASELINE configs[1]]",
             "chr1_5": "synthetic 30x HiFi chr1-chr5 (1.06 Gb; profiling workload)",
             "chr21": "synthetic 30x HiFi chr21 [BASELINE configs[0]]",
             "small": "synthetic 30x HiFi, 2 contigs of 5+3 Mb (debug)"}[name]
@@ -233,11 +248,11 @@ def main_ours(args):
     t_gen = time.perf_counter()
     if args.scaling == "weak" or world == 1:
         # every rank scans its own sample of the workload (different seed per rank)
-        reads = synth.generate(contig_len, alloc=_capi.pinned_empty, seed=args.seed + rank, n_sv=n_sv)
+        reads = synth.generate(contig_len, alloc=_capi.pinned_empty, seed=args.seed + rank, n_sv=n_sv, **SYNTH_KW.get(args.workload, {}))
         regions = api.whole_contig_regions(contig_len)
     else:
         # config 4: one genome, region-sharded by cumulative length, halo reads included
-        full = synth.generate(contig_len, seed=args.seed, n_sv=n_sv)
+        full = synth.generate(contig_len, seed=args.seed, n_sv=n_sv, **SYNTH_KW.get(args.workload, {}))
         regions = shard.plan_regions(contig_len, world)[rank]
         sub, _ = shard.select_reads(full, regions)
         reads = {}
@@ -382,7 +397,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr1_5", "chr21", "small"])
+    ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr1_5", "chr21", "small", "ont60x_chr20", "svrich_chr1"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--seed", type=int, default=20261018 + 2)
     ap.add_argument("--e2e-steps", type=int, default=3)

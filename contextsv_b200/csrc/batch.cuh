@@ -56,7 +56,7 @@ struct csv_batch {
     // depth
     csv::DevBuf d_events;    // uint32 depth-map indices, sign = slot parity
     csv::DevBuf d_ev_start, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
-    csv::DevBuf d_depth, d_sum, d_nz, d_tile_desc, d_tile_ev, d_tile_sum, d_tile_nz, d_wide_list, d_tile_q;
+    csv::DevBuf d_depth, d_sum, d_nz, d_tile_desc, d_tile_ev, d_tile_sum, d_tile_nz, d_wide_list, d_tile_q, d_tile_r;
     // signatures
     csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_kind, d_sig_payload;
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
@@ -64,7 +64,7 @@ struct csv_batch {
     void release(csv::DevPool* pool = nullptr) {
         csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
                               &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds,
-                              &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_sig_hi, &d_sig_lo, &d_sig_k,
+                              &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r, &d_sig_hi, &d_sig_lo, &d_sig_k,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
         for (auto* b : all) b->release(pool);

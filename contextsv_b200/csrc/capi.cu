@@ -348,7 +348,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pmax.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_pmax_part.ensure((nr / 2048 + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_tile_desc.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_ev.ensure(nt * 8 + 16, &ctx->pool));
-    CSV_TRY(b->d_wide_list.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_q.ensure(nt * 16 + 16, &ctx->pool));
+    CSV_TRY(b->d_wide_list.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_q.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_r.ensure(nt * 8 + 16, &ctx->pool));
     CSV_TRY(b->d_tile_sum.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_nz.ensure(nt * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_sum.ensure(n_regions * 8, &ctx->pool)); CSV_TRY(b->d_nz.ensure(n_regions * 4, &ctx->pool));
     CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));

@@ -33,7 +33,29 @@
 
 namespace csv {
 
-constexpr uint32_t kNarrowMaxPairs = 32767;     // a 16-bit counter cannot overflow below this many pairs per slice
+// A record's events alternate +,-,+,- in position order, so its net contribution to any position (and to any run of
+// consecutive positions) is -1, 0 or +1: a 16-bit counter cannot overflow while at most this many records overlap the tile.
+constexpr uint32_t kNarrowMaxRecords = 32767;
+// Slices longer than this many pairs (long reads: a 50 kb ONT record owns ~5000 events, 70 of them overlap a tile) are
+// not streamed whole: the events of a record are sorted, so two binary searches per record find the pairs that can
+// touch the tile.
+constexpr uint32_t kSearchMinPairs = 4096;
+constexpr uint32_t kSearchShortRecord = 64;     // events; shorter records are taken whole
+
+// pair range [a, b) of record k that can touch [T0, T1): everything before a is an even number of events left of the
+// tile (net zero), everything from b on lies at or beyond T1
+__device__ __forceinline__ uint2 record_pair_range(const uint32_t* __restrict__ events, const uint32_t* __restrict__ ev_start, uint32_t k,
+                                                  uint32_t T0, uint32_t T1)
+{
+    const uint32_t es = ev_start[k], ee = ev_start[k + 1];
+    if (ee - es <= kSearchShortRecord) return make_uint2(es >> 1, ee >> 1);
+    uint32_t lo = es, hi = ee;
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(events + mid) < T0) lo = mid + 1; else hi = mid; }
+    const uint32_t lb0 = lo;
+    hi = ee;
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(events + mid) < T1) lo = mid + 1; else hi = mid; }
+    return make_uint2(lb0 >> 1, (lo + 1u) >> 1);
+}
 
 // ------------------------------------------------------- prefix max over records
 constexpr int kPmThreads = 256, kPmItems = 8, kPmTile = kPmThreads * kPmItems;
@@ -159,7 +181,7 @@ __global__ void k_tile_hi(const uint4* __restrict__ tile_desc, uint32_t t_begin,
 // the ones that can touch the tile, their events one contiguous slice.
 __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t t_begin, uint32_t t_end,
                               const unsigned long long* __restrict__ pmax, const uint32_t* __restrict__ ev_start,
-                              uint32_t* scalars, const uint32_t* bounds, uint2* tile_ev, uint4* tile_q, uint32_t* wide_list)
+                              uint32_t* scalars, const uint32_t* bounds, uint2* tile_ev, uint4* tile_q, uint2* tile_r, uint32_t* wide_list)
 {
     const uint32_t kb = bounds[0];
     for (uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x; t < t_end; t += gridDim.x * blockDim.x) {
@@ -175,7 +197,8 @@ __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t t_be
         const uint2 er = r_lo < r_hi ? make_uint2(ev_start[r_lo], ev_start[r_hi]) : make_uint2(0u, 0u);
         tile_ev[t] = er;
         tile_q[t] = make_uint4(d.z, d.y, er.x, er.y);
-        if (((er.y - er.x) >> 1) > kNarrowMaxPairs) wide_list[atomicAdd(&scalars[SC_N_WIDE], 1u)] = t;   // rare: 32-bit counters
+        tile_r[t] = make_uint2(r_lo, r_hi);
+        if (r_hi - r_lo > kNarrowMaxRecords && r_lo < r_hi) wide_list[atomicAdd(&scalars[SC_N_WIDE], 1u)] = t;   // rare: 32-bit counters
     }
 }
 
@@ -240,7 +263,7 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
     for (const auto& tr : ch.tiles) {
         const uint32_t grid_t = (tr.second - tr.first + 255) / 256;
         k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), tr.first, tr.second, pmax, b->d_ev_start.as<uint32_t>(),
-                                                      scalars, bounds, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_wide_list.as<uint32_t>());
+                                                      scalars, bounds, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_tile_r.as<uint2>(), b->d_wide_list.as<uint32_t>());
         ctx->launches++;
     }
     CSV_CUDA(cudaGetLastError());
@@ -252,6 +275,8 @@ struct TileParams {
     const uint4* tile_desc;          // static per tile: {region, positions in tile, T0, tid}
     const uint2* tile_ev;            // event slice [x, y)
     const uint4* tile_q;             // {T0, positions, x, y}: all the 16-bit kernel needs, one 128-bit load
+    const uint2* tile_r;             // records [r_lo, r_hi) that can touch the tile
+    const uint32_t* ev_start;
     const uint32_t* events;
     uint32_t ev_cap;
     uint32_t* depth;                 // n_tiles * kTile words
@@ -283,6 +308,7 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 4 : 2)) k_depth_tiles_
     static_assert(kWarps <= 32, "one lane per warp in the offset reduction");
     __shared__ __align__(16) int s_diff[kThreads * kPadW];
     __shared__ int s_wtot[kWarps], s_wcar[kWarps];
+    __shared__ uint2 s_rng[kThreads];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(P.events);
     const uint32_t pair_cap = P.ev_cap >> 1;
@@ -323,6 +349,21 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 4 : 2)) k_depth_tiles_
             if (q0 < n_here) atomicAdd(&s_diff[q0 + (q0 >> kShift) * 4u], 1);
             if (q1 < n_here) atomicAdd(&s_diff[q1 + (q1 >> kShift) * 4u], -1);
         };
+        if (pe - pb > kSearchMinPairs) {
+            // long records (or a pile-up): per record, only the pairs that can touch the tile
+            const uint2 rr = __ldg(P.tile_r + t);
+            for (uint32_t rb = rr.x; rb < rr.y; rb += kThreads) {
+                const uint32_t cnt = rr.y - rb < (uint32_t)kThreads ? rr.y - rb : (uint32_t)kThreads;
+                __syncthreads();
+                if (tid < cnt) s_rng[tid] = record_pair_range(P.events, P.ev_start, rb + tid, T0, T0 + n_here);
+                __syncthreads();
+                for (uint32_t r = warp; r < cnt; r += kWarps) {
+                    const uint2 g2 = s_rng[r];
+                    const uint32_t pend = g2.y < pair_cap ? g2.y : pair_cap;
+                    for (uint32_t q = g2.x + lane; q < pend; q += 32) apply(__ldg(pairs + q));
+                }
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < kPP; u++) apply(pf[u]);
         for (uint32_t base = pb + kThreads * kPP; base < pe; base += kThreads * kPP) {      // rare: > 2048 events
@@ -331,6 +372,7 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 4 : 2)) k_depth_tiles_
             for (int u = 0; u < kPP; u++) { const uint32_t i = base + tid + u * kThreads; p[u] = i < pe ? __ldg(pairs + i) : make_uint2(kNone, kNone); }
 #pragma unroll
             for (int u = 0; u < kPP; u++) apply(p[u]);
+        }
         }
         // first batch of the next tile: in flight while this tile is scanned and written
 #pragma unroll
@@ -420,6 +462,36 @@ __device__ __forceinline__ int scan_step(int x, int d)
     return x;
 }
 
+// Searched path of the 16-bit kernel (long records): per record only the pairs that can touch the tile.  Returns the
+// thread's share of the tile's carry-in.  Out of line on purpose: the streaming path keeps its registers.
+__device__ __noinline__ int tile16_searched(const uint32_t* __restrict__ events, const uint32_t* __restrict__ ev_start, const uint32_t pair_cap,
+                                           const uint2 rr, const uint32_t T0, const uint32_t n_here, const uint32_t sbase, uint2* s_rng)
+{
+    constexpr int kThreads = 256, kWarps = 8;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(events);
+    int mycarry = 0;
+    for (uint32_t rb = rr.x; rb < rr.y; rb += kThreads) {
+        const uint32_t cnt = rr.y - rb < (uint32_t)kThreads ? rr.y - rb : (uint32_t)kThreads;
+        __syncthreads();
+        if (tid < cnt) s_rng[tid] = record_pair_range(events, ev_start, rb + tid, T0, T0 + n_here);
+        __syncthreads();
+        for (uint32_t r = warp; r < cnt; r += kWarps) {
+            const uint2 g2 = s_rng[r];
+            const uint32_t pend = g2.y < pair_cap ? g2.y : pair_cap;
+            for (uint32_t q = g2.x + lane; q < pend; q += 32) {
+                const uint2 pr = __ldg(pairs + q);
+                const uint32_t q0 = pr.x - T0, q1 = pr.y - T0;
+                mycarry += (pr.x < T0) ? 1 : 0;
+                mycarry -= (pr.y < T0) ? 1 : 0;
+                red_shared_if_lt(q0, n_here, (sbase + 2u * q0) & ~3u, (q0 & 1u) * 0x0000ffffu + 1u);
+                red_shared_if_lt(q1, n_here, (sbase + 2u * q1) & ~3u, (q1 & 1u) * 0xffff0001u + 0xffffffffu);
+            }
+        }
+    }
+    return mycarry;
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
 {
@@ -427,6 +499,7 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
     static_assert(kTile == kWarps * 1024, "a warp owns 1024 positions: 4 rows of 32 chunks of 8");
     __shared__ __align__(16) uint32_t s_d[kTile / 2];
     __shared__ int s_wtot[kWarps], s_wcar[kWarps];
+    __shared__ uint2 s_rng[kThreads];                                    // searched path: pair range of 256 records at a time
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(P.events);
     const uint32_t pair_cap = P.ev_cap >> 1;
@@ -452,7 +525,11 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
         const uint4 nn = t + 2 * g < P.t_end ? __ldg(P.tile_q + t + 2 * g) : zero4;
         const uint32_t T0 = cur.x, n_here = cur.y;
         const uint32_t pb = cur.z >> 1, pe = min(cur.w >> 1, pair_cap);
-        const bool narrow = ((cur.w - cur.z) >> 1) <= kNarrowMaxPairs;    // CTA-uniform; wide tiles belong to k_depth_tiles_wide
+        const uint32_t np_slice = (cur.w - cur.z) >> 1;
+        const bool searched = np_slice > kSearchMinPairs;                // CTA-uniform
+        uint2 rr = make_uint2(0, 0);
+        if (searched) rr = __ldg(P.tile_r + t);
+        const bool narrow = !searched || rr.y - rr.x <= kNarrowMaxRecords;   // CTA-uniform; wide tiles belong to k_depth_tiles_wide
         // ---- stretches of the records that overlap the tile (every counter is at its bias here)
         int mycarry = 0;
         auto apply = [&](const uint2 pr) {
@@ -462,7 +539,9 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
             red_shared_if_lt(q0, n_here, (sbase + 2u * q0) & ~3u, (q0 & 1u) * 0x0000ffffu + 1u);             // +1 in its half
             red_shared_if_lt(q1, n_here, (sbase + 2u * q1) & ~3u, (q1 & 1u) * 0xffff0001u + 0xffffffffu);     // -1 in its half
         };
-        if (narrow) {
+        if (searched && narrow) {
+            mycarry = tile16_searched(P.events, P.ev_start, pair_cap, rr, T0, n_here, sbase, s_rng);  // long records: kept out of line, the streaming path stays lean
+        } else if (narrow) {
 #pragma unroll
             for (int u = 0; u < kPP; u++) apply(pf[u]);
             for (uint32_t base = pb + kThreads * kPP; base < pe; base += kThreads * kPP) {      // > 2048 events
@@ -578,6 +657,8 @@ static TileParams tile_params(csv_batch* b)
     P.tile_desc = b->d_tile_desc.as<uint4>();
     P.tile_ev = b->d_tile_ev.as<uint2>();
     P.tile_q = b->d_tile_q.as<uint4>();
+    P.tile_r = b->d_tile_r.as<uint2>();
+    P.ev_start = b->d_ev_start.as<uint32_t>();
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.depth = b->d_depth.as<uint32_t>();

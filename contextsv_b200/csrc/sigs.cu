@@ -76,37 +76,34 @@ __global__ void k_sig_gather(const GatherParams P)
         const uint32_t read = P.ne_idx[k];
         const unsigned long long c0 = P.cig_off[read];
         const uint8_t kr = P.raw_kind[slot];
-        uint32_t qpos;
-        if (!(kr & 0x80u)) {
-            // query offset of the op (sv_caller.cpp:547,653-655): the pre-pass knows it at the start of the op's
-            // span; the ops between the span start (or the record head, if later) and g are summed here
-            const uint32_t sp = g / (uint32_t)kWalkSpan;
-            unsigned long long from = c0;
-            uint32_t q = 0;
-            if (c0 < (unsigned long long)sp * kWalkSpan) {
-                const WalkAgg ch = P.chunk_agg[sp / (uint32_t)kSpanChunk], pr = P.span_pre[sp];
+        // query offset of the op (sv_caller.cpp:547,653-655): the pre-pass knows it (and the reference offset) at the
+        // start of the op's span; the ops between the span start (or the record head, if later) and g are summed here.
+        // Records that reach the end of their contig need the reference's own sequence of steps from there on: a soft
+        // clip of >= min_len at pos + 1 >= map_size skips the query advance (sv_caller.cpp:602-604).  Positions never
+        // decrease along a record, so the prefix is still valid as long as the record was inside the contig at the
+        // span start; only a record that already left it before falls back to its head.
+        const uint32_t sp = g / (uint32_t)kWalkSpan;
+        const unsigned long long span_op0 = (unsigned long long)sp * kWalkSpan;
+        const bool exact = kr & 0x80u;
+        const uint4 m = P.meta[k];
+        unsigned long long from = c0;
+        uint32_t q = 0, pos = m.x;
+        if (c0 < span_op0) {
+            const WalkAgg ch = P.chunk_agg[sp / (uint32_t)kSpanChunk], pr = P.span_pre[sp];
+            const uint32_t ref_pre = pr.heads ? pr.ref : ch.ref + pr.ref;
+            if (!exact || m.x + ref_pre + 1u < m.y) {
                 q = pr.heads ? pr.qry : ch.qry + pr.qry;
-                from = (unsigned long long)sp * kWalkSpan;
+                pos = m.x + ref_pre;
+                from = span_op0;
             }
-            for (unsigned long long o = from; o < (unsigned long long)g; o++) {
-                const uint32_t w = P.cigar[o];
-                if ((kQryMask >> (w & 15u)) & 1u) q += w >> 4;
-            }
-            qpos = q;
-        } else {
-            // exact sequential restatement (sv_caller.cpp:563-655) for the rare records that reach or
-            // pass the end of their contig: a soft clip there skips the query advance (:602-604)
-            const uint4 m = P.meta[k];
-            const uint32_t map_size = m.y;
-            uint32_t pos = m.x, q = 0;
-            for (unsigned long long o = c0; o < (unsigned long long)g; o++) {
-                const uint32_t w = P.cigar[o], op = w & 15u, len = w >> 4;
-                if (len >= P.min_len && op == 4u && (uint32_t)(pos + 1u) >= map_size) continue;
-                if ((kRefMask >> op) & 1u) pos += len;
-                if ((kQryMask >> op) & 1u) q += len;
-            }
-            qpos = q;
         }
+        for (unsigned long long o = from; o < (unsigned long long)g; o++) {
+            const uint32_t w = P.cigar[o], op = w & 15u, len = w >> 4;
+            if (exact && len >= P.min_len && op == 4u && (uint32_t)(pos + 1u) >= m.y) continue;
+            if ((kRefMask >> op) & 1u) pos += len;
+            if ((kQryMask >> op) & 1u) q += len;
+        }
+        const uint32_t qpos = q;
         const uint32_t kind = kr & 0x7fu;
         const uint32_t region = (uint32_t)(hi >> 32);
         P.o_start[i] = (uint32_t)hi;
