@@ -479,13 +479,18 @@ __device__ __noinline__ int tile16_searched(const uint32_t* __restrict__ events,
         for (uint32_t r = warp; r < cnt; r += kWarps) {
             const uint2 g2 = s_rng[r];
             const uint32_t pend = g2.y < pair_cap ? g2.y : pair_cap;
-            for (uint32_t q = g2.x + lane; q < pend; q += 32) {
-                const uint2 pr = __ldg(pairs + q);
-                const uint32_t q0 = pr.x - T0, q1 = pr.y - T0;
-                mycarry += (pr.x < T0) ? 1 : 0;
-                mycarry -= (pr.y < T0) ? 1 : 0;
-                red_shared_if_lt(q0, n_here, (sbase + 2u * q0) & ~3u, (q0 & 1u) * 0x0000ffffu + 1u);
-                red_shared_if_lt(q1, n_here, (sbase + 2u * q1) & ~3u, (q1 & 1u) * 0xffff0001u + 0xffffffffu);
+            for (uint32_t q = g2.x + lane; q < pend; q += 32 * 8) {        // 8 loads in flight per lane
+                uint2 pr[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) pr[u] = q + 32 * u < pend ? __ldg(pairs + q + 32 * u) : make_uint2(kNone, kNone);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t q0 = pr[u].x - T0, q1 = pr[u].y - T0;
+                    mycarry += (pr[u].x < T0) ? 1 : 0;
+                    mycarry -= (pr[u].y < T0) ? 1 : 0;
+                    red_shared_if_lt(q0, n_here, (sbase + 2u * q0) & ~3u, (q0 & 1u) * 0x0000ffffu + 1u);
+                    red_shared_if_lt(q1, n_here, (sbase + 2u * q1) & ~3u, (q1 & 1u) * 0xffff0001u + 0xffffffffu);
+                }
             }
         }
     }
