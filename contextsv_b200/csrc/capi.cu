@@ -477,6 +477,7 @@ int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth
     if (!ctx || !b || !depth_out) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_fetch: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
     if (region >= b->n_regions) { set_error("region %u out of range", region); return CSV_ERR_ARG; }
+    CSV_TRY(side_join(ctx));             // the tiles run on their own stream
     const size_t len = b->regions[region].end - b->regions[region].beg;
     const uint32_t* src = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
     CSV_CUDA(cudaMemcpyAsync(depth_out, src, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -487,6 +488,7 @@ int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth
 int csv_depth_device_ptr(csv_ctx* ctx, csv_batch* b, uint32_t region, const uint32_t** dptr_out)
 {
     if (!ctx || !b || !dptr_out || region >= b->n_regions) { set_error("bad argument"); return CSV_ERR_ARG; }
+    CSV_TRY(side_join(ctx));             // work the caller enqueues on the context's stream after this call sees the finished map
     *dptr_out = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
     return CSV_OK;
 }
