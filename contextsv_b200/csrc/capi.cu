@@ -249,6 +249,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     if (r->n_ops && !r->cigar) { set_error("csv_batch_upload: cigar is NULL"); return CSV_ERR_ARG; }
     if (r->n_reads && r->cig_off[r->n_reads] != r->n_ops) { set_error("csv_batch_upload: cig_off[n_reads] != n_ops"); return CSV_ERR_ARG; }
     if (r->n_ops >= (1ull << 31)) { set_error("batch of %llu CIGAR ops exceeds the 2^31 per-batch limit: split it", (unsigned long long)r->n_ops); return CSV_ERR_LIMIT; }
+    if (r->n_ops + (uint64_t)r->n_reads >= (1ull << 31)) { set_error("batch of %llu ops + %u records exceeds the 2^31 event-slot limit: split it", (unsigned long long)r->n_ops, r->n_reads); return CSV_ERR_LIMIT; }
     if (n_regions >= (1u << 30)) { set_error("too many regions"); return CSV_ERR_LIMIT; }
     CSV_CUDA(cudaSetDevice(ctx->device));
 

@@ -76,7 +76,7 @@ int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, doubl
  * asynchronous but is not required. */
 typedef struct {
     uint32_t        n_reads;
-    uint64_t        n_ops;     /* == cig_off[n_reads]; must be < 2^32                 */
+    uint64_t        n_ops;     /* == cig_off[n_reads]; n_ops + n_reads must be < 2^31 per batch (larger inputs: shards) */
     const int32_t*  tid;       /* [n_reads] contig id, or NULL (all reads on contig 0) */
     const int32_t*  pos0;      /* [n_reads] 0-based leftmost position                  */
     const uint16_t* flag;      /* [n_reads] BAM FLAG                                   */
