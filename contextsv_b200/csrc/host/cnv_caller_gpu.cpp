@@ -78,7 +78,7 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
         int32_t last_pos = -2;
         while (sam_itr_next(bam_file, it, bam_record) >= 0) {
             const int32_t pos = (int32_t)bam_record->core.pos;
-            if (reads.ops() + bam_record->core.n_cigar > max_ops && pos != last_pos && reads.size() > 0) {
+            if (reads.ops() + reads.size() + bam_record->core.n_cigar + 1 > max_ops && pos != last_pos && reads.size() > 0) {   // ops + records: a batch counts both
                 const uint32_t cut = std::min<uint32_t>((uint32_t)pos + 1u, size);       // records from here on start at or after the cut
                 flush(cut);
                 reads.keep_reaching(cut);

@@ -71,7 +71,7 @@ void SVCaller::findCIGARSVs(samFile* fp_in, hts_idx_t* idx, bam_hdr_t* bamHdr, c
         reads.clear();
     };
     while (readNextAlignment(fp_in, itr, bam1) >= 0) {
-        if (reads.ops() + bam1->core.n_cigar > max_ops && reads.size() > 0) flush();
+        if (reads.ops() + reads.size() + bam1->core.n_cigar + 1 > max_ops && reads.size() > 0) flush();   // ops + records: a batch counts both
         reads.append(bam1, true);
     }
     hts_itr_destroy(itr);

@@ -82,8 +82,8 @@ def select_reads(reads, regions, ends=None):
 def plan_by_ops(reads, contig_len, max_ops, ends=None):
     """Shards for ONE device when the records hold more CIGAR ops than a batch takes (csv_batch_upload: < 2^31;
     BASELINE config 3, 60x ONT, is ~3.7e10): the same region sharding as across GPUs, in time instead of space.
-    Walks the records in order and cuts a region whenever the next record would push the ops of the slice
-    [first halo record, record] past max_ops.  Cuts fall between records with different pos0, so every record is
+    Walks the records in order and cuts a region whenever the next record would push the ops + records of the slice
+    [first halo record, record] past max_ops (a batch counts both: its event slots are 32-bit).  Cuts fall between records with different pos0, so every record is
     owned by exactly one shard.  Returns a list of region lists [(tid, beg, end, map_size), ...] in genome order."""
     n = int(reads["n_reads"])
     sizes = [int(l) + 1 for l in contig_len]
@@ -104,7 +104,7 @@ def plan_by_ops(reads, contig_len, max_ops, ends=None):
         j = i + 1
         while j < n and tid[j] == tid[i] and idx[j] == idx[i]:
             j += 1
-        if off[j] - off[i_first] > max_ops and i > i_first and (tid[i] > cur_tid or idx[i] > cur_beg):
+        if off[j] - off[i_first] + (j - i_first) > max_ops and i > i_first and (tid[i] > cur_tid or idx[i] > cur_beg):
             t, cut = int(tid[i]), int(min(idx[i], sizes[int(tid[i])]))
             # close the open shard at (t, cut): whole contigs up to t, then [.., cut) of t
             while cur_tid < t:
@@ -120,7 +120,7 @@ def plan_by_ops(reads, contig_len, max_ops, ends=None):
             lo_t = int(np.searchsorted(tid, t, side="left"))
             h = np.nonzero(ends[lo_t:i] > cut)[0]
             i_first = lo_t + int(h[0]) if len(h) else i
-            if off[j] - off[i_first] > max_ops:
+            if off[j] - off[i_first] + (j - i_first) > max_ops:
                 raise ValueError("max_ops=%d is too small: the records overlapping index %d of contig %d alone hold %d ops"
                                  % (max_ops, cut, t, off[j] - off[i_first]))
         i = j

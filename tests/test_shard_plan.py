@@ -14,7 +14,7 @@ def _check_plan(r, clen, plans, max_ops):
     tid = r["tid"].astype(np.int64)
     for regions in plans:
         sub, base = shard.select_reads(r, regions, ends)
-        assert int(sub["n_ops"]) <= max_ops
+        assert int(sub["n_ops"]) + int(sub["n_reads"]) <= max_ops
         for (t, b, e, m) in regions:
             assert m == clen[t] + 1 and 0 <= b < e <= m
             cov[t].append((b, e))
@@ -33,10 +33,10 @@ def _check_plan(r, clen, plans, max_ops):
 def test_plan_by_ops_tiles_the_genome_and_respects_the_budget():
     clen = [700_000, 90_000, 400_000]
     r = util.synth_reads(clen, seed=3, profile=1, coverage=10.0, read_len_mean=20000, indel_rate=0.05, n_sv=30)
-    for max_ops in (int(r["n_ops"]) + 1, 400_000, 150_000):
+    for max_ops in (int(r["n_ops"]) + int(r["n_reads"]) + 1, 400_000, 150_000):
         plans = shard.plan_by_ops(r, clen, max_ops)
         _check_plan(r, clen, plans, max_ops)
-    assert len(shard.plan_by_ops(r, clen, int(r["n_ops"]) + 1)) == 1
+    assert len(shard.plan_by_ops(r, clen, int(r["n_ops"]) + int(r["n_reads"]) + 1)) == 1
     assert len(shard.plan_by_ops(r, clen, 150_000)) > 5
 
 
