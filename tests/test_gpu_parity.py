@@ -92,6 +92,30 @@ def test_long_reads_spanning_many_spans(ctx, oracle):
     check_contigs(ctx, oracle, r, [3_000_000])
 
 
+def test_inputs_the_path_refuses(ctx):
+    """Not silently wrong: unsorted records (the reference needs an indexed = sorted BAM) and a record that consumes
+    2^31 reference bases (BAM positions are int32) are reported when results are fetched."""
+    from oracle.oracle_py import make_reads
+    from contextsv_b200._capi import CsvError
+    r = make_reads([500, 100, 900], [[(50, M)], [(60, M)], [(10, M)]])
+    b = run_batch(ctx, r, api.whole_contig_regions([2000]))
+    with pytest.raises(CsvError, match="sorted"):
+        b.depth_stats()
+    b.free()
+    big = (1 << 28) - 1
+    r = make_reads([10, 20], [[(big, M)] * 9, [(30, M)]])
+    b = run_batch(ctx, r, api.whole_contig_regions([5000]))
+    with pytest.raises(CsvError, match="2\\^31"):
+        b.depth_stats()
+    b.free()
+    # the same record one op shorter is fine (and clipped to the map like any read running off the contig end)
+    r = make_reads([10, 20], [[(big, M)] * 7, [(30, M)]])
+    b = run_batch(ctx, r, api.whole_contig_regions([5000]))
+    d = b.depth(0)
+    assert d[10] == 0 and d[11] == 1 and d[21] == 2 and d[50] == 2 and d[51] == 1 and d[5000] == 1
+    b.free()
+
+
 def test_pileups_deep_coverage(ctx, oracle):
     """Thousands of records starting / ending / deleting at the same base: tiles whose slice holds more than
     32767 pairs take the 32-bit-counter kernel, the others run the 16-bit one close to its bound."""
