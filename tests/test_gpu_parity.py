@@ -92,6 +92,74 @@ def test_long_reads_spanning_many_spans(ctx, oracle):
     check_contigs(ctx, oracle, r, [3_000_000])
 
 
+def test_full_size_whole_genome_properties(ctx, oracle):
+    """BASELINE configs[1] at full size (6.2 M reads, 375 M CIGAR ops, 3.1 G depth positions, one batch): exact parity with
+    the oracle on two whole contigs taken out of the full-size run, and size-independent properties on everything --
+    sum(depth) == covered bases counted from the CIGARs, INS / DEL signature counts == qualifying ops counted from the CIGARs, every
+    region's signature list sorted the way addSVCall leaves it, DBSCAN1D labels dense per group, and a second pass over the
+    resident batch reproducing the first bit for bit."""
+    from contextsv_b200 import shard
+    clen = [l for _, l in shard.GRCH38]
+    r = util.synth_reads(clen, seed=20261019, n_sv=25000)
+    regions = api.whole_contig_regions(clen)
+    b = run_batch(ctx, r, regions)
+    sums, nzs = b.depth_stats()
+    sg = b.sigs()
+    lab = b.sigs_dbscan1d(100.0, 5)
+    # ---- properties from the CIGARs alone (numpy, no oracle)
+    cig = r["cigar"]; off = r["cig_off"].astype(np.int64); n = int(r["n_reads"])
+    op = cig & 15; ln = (cig >> 4).astype(np.int64)
+    rec = np.repeat(np.arange(n), np.diff(off))
+    flag = r["flag"]; tid = r["tid"]
+    depth_ok = (flag & (0x4 | 0x100 | 0x200 | 0x400)) == 0
+    sig_ok = ((flag & (0x4 | 0x100 | 0x200 | 0x400 | 0x800)) == 0) & (r["mapq"] >= 20)
+    ends = shard.ref_end(r)
+    inside = ends <= np.asarray(clen, np.int64)[tid] + 1
+    assert inside.all(), "the generator keeps reads inside their contig; the property below relies on it"
+    covered = np.bincount(tid[rec], weights=(ln * np.isin(op, (0, 7, 8)) * depth_ok[rec]).astype(np.float64), minlength=len(clen))
+    assert np.array_equal(sums.astype(np.int64), covered.astype(np.int64))
+    # I and D of >= 50 bases from records that pass the filter (soft clips also depend on the position: sv_caller.cpp:602)
+    for kind, opv in ((0, 1), (1, 2)):
+        want = np.bincount(tid[rec], weights=((op == opv) & (ln >= 50) & sig_ok[rec]).astype(np.float64), minlength=len(clen)).astype(np.int64)
+        seg = np.repeat(np.arange(len(clen)), np.diff(sg["region_off"].astype(np.int64)))
+        got = np.bincount(seg[sg["kind"] == kind], minlength=len(clen))
+        assert np.array_equal(got, want), kind
+    clips = np.bincount(tid[rec], weights=((op == 4) & (ln >= 50) & sig_ok[rec]).astype(np.float64), minlength=len(clen)).astype(np.int64)
+    seg = np.repeat(np.arange(len(clen)), np.diff(sg["region_off"].astype(np.int64)))
+    assert np.all(np.bincount(seg[sg["kind"] == 2], minlength=len(clen)) <= clips)
+    for t in range(len(clen)):
+        lo, hi = int(sg["region_off"][t]), int(sg["region_off"][t + 1])
+        key = sg["start"][lo:hi].astype(np.int64) * (1 << 32) + sg["end"][lo:hi]
+        assert np.all(np.diff(key) >= 0)
+        seq = sg["read_idx"][lo:hi].astype(np.int64) * (1 << 20) + sg["op_idx"][lo:hi]
+        tie = np.diff(key) == 0
+        assert np.all(np.diff(seq)[tie] < 0)                       # equal keys: reverse insertion order
+        for is_del in (True, False):
+            l = lab[lo:hi][(sg["kind"][lo:hi] == 1) == is_del]
+            ids = np.unique(l[l >= 0])
+            assert np.all((l >= 0) | (l == -2)) and np.array_equal(ids, np.arange(len(ids)))
+    # ---- exact parity on two whole contigs out of the full-size run
+    for t in (20, 21):
+        d, s_, nz_ = oracle.depth(r, t, clen[t] + 1)
+        assert np.array_equal(b.depth(t), d) and int(sums[t]) == s_ and int(nzs[t]) == nz_
+        o = oracle.cigar_scan(r, t, clen[t] + 1)
+        lo, hi = int(sg["region_off"][t]), int(sg["region_off"][t + 1])
+        for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+            assert np.array_equal(sg[f][lo:hi], o[f]), f
+        for is_del in (True, False):
+            m = (sg["kind"][lo:hi] == 1) == is_del
+            assert np.array_equal(lab[lo:hi][m], oracle.dbscan1d(sg["start"][lo:hi][m].astype(np.int32), 100.0, 5, fast=True))
+    # ---- idempotence: the second pass over the resident batch gives the same bits
+    d21 = b.depth(21).copy()
+    b.scan(want_depth=True, want_sigs=True)
+    sums2, nzs2 = b.depth_stats()
+    sg2 = b.sigs()
+    assert np.array_equal(sums, sums2) and np.array_equal(nzs, nzs2) and np.array_equal(b.depth(21), d21)
+    for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+        assert np.array_equal(sg[f], sg2[f])
+    b.free()
+
+
 def test_inputs_the_path_refuses(ctx):
     """Not silently wrong: unsorted records (the reference needs an indexed = sorted BAM) and a record that consumes
     2^31 reference bases (BAM positions are int32) are reported when results are fetched."""
