@@ -304,7 +304,7 @@ def main_ours(args):
     # ---- roofline of the dominant kernel and of the whole path (algorithmic bytes)
     peak, peak_src = measured_peak_gbs()
     b_alg = 15 * n_reads + 4 * n_ops + 4 * depth_words + 21 * n_sig + 8 * n_sig
-    tile_ms = stages["depth_tiles"][0] / args.steps      # all chunk launches of one step
+    tile_ms = stages["k_depth_tiles16"][0] / args.steps  # the dominant kernel alone: CUDA events around its launch(es) on its stream
     tile_bytes = 4 * depth_words
     achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
     path_gbs = b_alg / (ms / args.steps * 1e-3) / 1e9

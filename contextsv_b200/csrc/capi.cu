@@ -219,7 +219,7 @@ int csv_profile_enable(csv_ctx* ctx, int on)
 
 int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, double* ms_out, uint32_t* calls_out, int reset)
 {
-    static const char* kNames[ST_COUNT] = {"prep", "walk", "tile_ranges", "depth_tiles", "sig_sort", "dbscan1d"};
+    static const char* kNames[ST_COUNT] = {"prep", "walk", "tile_ranges", "depth_tiles", "sig_sort", "dbscan1d", "k_depth_tiles16"};
     if (!ctx) { set_error("null context"); return -CSV_ERR_ARG; }
     if (side_join(ctx) != CSV_OK || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("csv_profile_read: stream synchronisation failed"); return -CSV_ERR_CUDA; }
     for (int s = 0; s < ST_COUNT; s++) {

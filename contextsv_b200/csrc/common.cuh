@@ -92,7 +92,7 @@ struct DevBuf {
 };
 
 // Per-stage device timing (CUDA events on the context's stream), for bench.py's roofline.
-enum Stage { ST_PREP = 0, ST_WALK, ST_TILE_RANGES, ST_DEPTH_TILES, ST_SIG_SORT, ST_DBSCAN, ST_COUNT };
+enum Stage { ST_PREP = 0, ST_WALK, ST_TILE_RANGES, ST_DEPTH_TILES, ST_SIG_SORT, ST_DBSCAN, ST_TILE_KERNEL /* k_depth_tiles16 alone, inside ST_DEPTH_TILES */, ST_COUNT };
 
 // Region tables (device copies live in the batch)
 struct RegionDev {       // sorted by (tid, beg)

@@ -697,6 +697,7 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t c)
         P.t_begin = tr.first; P.t_end = tr.second;
         const uint32_t nt = tr.second - tr.first;
         const uint32_t grid = nt < (uint32_t)ctx->sm_count * mult ? nt : (uint32_t)ctx->sm_count * mult;
+        StageTimer tk(ctx, ST_TILE_KERNEL);                                                 // the dominant kernel alone (bench.py's roofline)
         if (minb == 5) k_depth_tiles16<5><<<grid, 256, 0, ctx->stream>>>(P);
         else if (minb == 6) k_depth_tiles16<6><<<grid, 256, 0, ctx->stream>>>(P);
         else k_depth_tiles16<4><<<grid, 256, 0, ctx->stream>>>(P);
