@@ -14,17 +14,19 @@
 //   owns an even number of events, so slots (2i, 2i+1) are the two ends [p0, p1) of one covered stretch of a
 //   record: +1 at p0, -1 at p1.  The CTA streams the pairs of the slice with 64-bit loads: an end left of the
 //   tile moves the tile's carry-in (depth at T0), an end inside goes into a shared-memory difference array,
-//   the rest is skipped.  No inter-tile dependency, no global atomics.
+//   the rest is skipped.  No inter-tile dependency, no global atomics.  Slices of long reads (> 4096 pairs)
+//   are not streamed whole: two binary searches per record find the pairs that can touch the tile.
 //   The difference array holds 16-bit counters, two per word, biased by 0x8000 so that no borrow ever crosses
-//   the halves: 16 KB per tile, a quarter of the shared-memory traffic of 32-bit counters.  A tile whose slice
-//   holds more than 32767 pairs (local coverage in the thousands) could overflow them: those tiles go to
-//   k_depth_tiles_wide (32-bit counters) through a list k_tile_ranges builds.
+//   the halves: 16 KB per tile, a quarter of the shared-memory traffic of 32-bit counters.  A record moves any
+//   counter (and any run of them) by -1, 0 or +1 in total, so only a tile that more than 32767 records overlap
+//   (local coverage in the tens of thousands) could overflow them: those tiles go to k_depth_tiles_wide
+//   (32-bit counters) through a list k_tile_ranges builds.
 //   Thread ownership is chosen for the memory system, not for the scan: lane l of warp w owns the four
 //   8-position chunks l, l+32, l+64, l+96 of the warp's 1024 positions, so every 128-bit shared-memory access
 //   and every 256-bit global store of a warp covers one contiguous kilobyte.  The prefix sum is IDP.2A
 //   (dot product of the two halves with {1,0} / {1,1}, accumulate in the running depth): one FMA-pipe
-//   instruction per position, beside the ALU-pipe reductions (sum, min).  Four warp scans (one per chunk row)
-//   + one redux per row order the chunks.  sum(depth) / count(depth > 0) are reduced per tile and summed per
+//   instruction per position, beside the ALU-pipe reductions (sum, min).  Two packed warp scans (two chunk rows
+//   each) order the chunks.  sum(depth) / count(depth > 0) are reduced per tile and summed per
 //   region by k_region_stats.
 #include "batch.cuh"
 #include "scan.cuh"
@@ -579,8 +581,8 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
             w[4 * i] = x.x ^ kBias2; w[4 * i + 1] = x.y ^ kBias2; w[4 * i + 2] = x.z ^ kBias2; w[4 * i + 3] = x.w ^ kBias2;
             tot[i] = dp2(w[4 * i + 3], 0x0101, dp2(w[4 * i + 2], 0x0101, dp2(w[4 * i + 1], 0x0101, dp2(w[4 * i], 0x0101, 0))));
         }
-        // Two rows per scan: every partial sum of counters is bounded by the pairs of the slice (<= 32767), so the
-        // integer a + 65536 b carries both exactly
+        // Two rows per scan: every partial sum of counters is bounded by the records overlapping the tile (<= 32767),
+        // so the integer a + 65536 b carries both exactly
         int s01 = tot[0] + (tot[1] << 16), s23 = tot[2] + (tot[3] << 16);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { s01 = scan_step(s01, d); s23 = scan_step(s23, d); }
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
         base[1] = woff + R[0] + inc[1] - tot[1];
         base[2] = woff + R[0] + R[1] + inc[2] - tot[2];
         base[3] = woff + R[0] + R[1] + R[2] + inc[3] - tot[3];
-        // depths never exceed carry-in + pairs <= 65534 here: 32-bit sums of 32 of them cannot overflow
+        // depths never exceed the records overlapping the tile (<= 32767) here: 32-bit sums of 32 of them cannot overflow
         const uint32_t q_first = warp * 1024u + lane * 8u;                 // my chunk of row 0; row i is 256 positions further
         uint32_t* out = P.depth + (size_t)t * kTile + q_first;
         uint32_t sum32 = 0, mn = 0xffffffffu;
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
                     if (qc + k < n_here) { if (!full) out[256 * i + k] = (uint32_t)v[k]; sum32 += (uint32_t)v[k]; nz += v[k] != 0; }
             }
         }
-        // warp totals with the redux unit: thread sums <= 32 * 65534 < 2^21, so the warp sum fits 32 bits
+        // warp totals with the redux unit: thread sums <= 32 * 32767 < 2^20, so the warp sum fits 32 bits
         sum32 = __reduce_add_sync(0xffffffffu, sum32);
         nz = __reduce_add_sync(0xffffffffu, nz);
         if (lane == 0 && (sum32 | nz)) { atomicAdd(&P.tile_sum[t], (unsigned long long)sum32); atomicAdd(&P.tile_nz[t], nz); }
