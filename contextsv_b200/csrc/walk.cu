@@ -41,7 +41,7 @@ struct WalkParams {
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
-    uint32_t* ref_end;      // [n_nonempty] one past the last covered index, clipped to the map; 0 = takes no part in the depth
+    uint32_t* ref_end;      // [n_nonempty] one past the last covered index (may lie beyond the map); 0 = takes no part in the depth
     uint32_t n_meta;        // entries allocated in meta
     uint32_t min_len, sig_lut;
     uint32_t* scalars;
@@ -449,12 +449,11 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const WalkParams P)
                     const uint32_t slot = T_ev + __popc((hbv & low) | ((tails & low) << 9)) + 2u * __popc(gm & low);   // after the tail event of op b-1
                     if (b) {
                         const uint32_t kt = k_first + klb;
-                        const uint4 m = __ldg(P.meta + kt);
-                        const bool live = ((m.z >> 30) & 1u) && m.x + 1u < m.y;
+                        const uint32_t p1 = s_pos1[klb];
                         const uint32_t ie = cb + biasb;                      // one past the last covered index
-                        if (ie - s_pos1[klb] >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
+                        if (ie - p1 >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
                         P.events[slot - 1u] = ie;
-                        P.ref_end[kt] = live ? (ie < m.y ? ie : m.y) : 0u;
+                        P.ref_end[kt] = p1 != kDeadPos ? ie : 0u;            // not clipped to the map: only compared with tile starts
                         P.ev_start[kt + 1u] = slot;
                     }
                     if (b < t.n_valid) {
