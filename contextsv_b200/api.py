@@ -183,6 +183,13 @@ class Batch:
         check(lib().csv_sigs_dbscan1d(self.ctx.h, self.h, float(eps), int(min_pts), ptr(lab), max(n, 1)))
         return lab[:n]
 
+    def depth_at(self, region, positions):
+        """SVCaller::getReadDepth for many positions, from the device-resident map (0 beyond it)."""
+        pos = np.ascontiguousarray(positions, np.uint32)
+        out = np.zeros(len(pos), np.uint32)
+        check(lib().csv_depth_at(self.ctx.h, self.h, region, len(pos), ptr(pos), ptr(out)))
+        return out
+
     def window_sums(self, region, start_pos, end_pos, sample_size):
         s = np.ascontiguousarray(start_pos, np.uint32); e = np.ascontiguousarray(end_pos, np.uint32)
         su = np.zeros(len(s) * sample_size, np.uint64); cn = np.zeros(len(s) * sample_size, np.uint32)

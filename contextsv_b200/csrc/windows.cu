@@ -36,9 +36,41 @@ __global__ void k_window_sums(const uint32_t* __restrict__ depth, uint32_t map_s
     }
 }
 
+// depth at arbitrary positions (SVCaller::getReadDepth, sv_caller.cpp:1332-1344): 0 beyond the map, like the caught
+// std::out_of_range there
+__global__ void k_depth_at(const uint32_t* __restrict__ depth, uint32_t map_size, uint64_t n, const uint32_t* __restrict__ pos, uint32_t* out)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = pos[i] < map_size ? depth[pos[i]] : 0u;
+}
+
 }  // namespace csv
 
 using namespace csv;
+
+extern "C" int csv_depth_at(csv_ctx* ctx, csv_batch* b, uint32_t region, uint64_t n, const uint32_t* positions, uint32_t* depth_out)
+{
+    if (!ctx || !b || (n && (!positions || !depth_out))) { set_error("csv_depth_at: bad argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_depth) { set_error("csv_depth_at: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    if (region >= b->n_regions) { set_error("region %u out of range", region); return CSV_ERR_ARG; }
+    const csv_region& g = b->regions[region];
+    if (g.beg != 0 || g.end != g.map_size) { set_error("csv_depth_at needs a whole-contig region"); return CSV_ERR_ARG; }
+    if (n == 0) return CSV_OK;
+    CSV_TRY(side_join(ctx));
+    DevBuf& io = ctx->sort_tmp[4];
+    CSV_TRY(io.ensure((size_t)n * 8));
+    uint32_t* d_pos = io.as<uint32_t>(); uint32_t* d_out = d_pos + n;
+    cudaStream_t st = ctx->stream;
+    CSV_CUDA(cudaMemcpyAsync(d_pos, positions, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t* depth = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    k_depth_at<<<grid, 256, 0, st>>>(depth, g.map_size, n, d_pos, d_out);
+    ctx->launches++;
+    CSV_CUDA(cudaGetLastError());
+    CSV_CUDA(cudaMemcpyAsync(depth_out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CSV_CUDA(cudaStreamSynchronize(st));
+    return CSV_OK;
+}
 
 extern "C" int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv, const uint32_t* start_pos,
                                const uint32_t* end_pos, int sample_size, uint64_t* sum_out, uint32_t* count_out)

@@ -203,6 +203,12 @@ int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv,
                     const uint32_t* start_pos, const uint32_t* end_pos, int sample_size,
                     uint64_t* sum_out /* [n_sv*sample_size] */, uint32_t* count_out);
 
+/* SVCaller::getReadDepth (sv_caller.cpp:1332-1344) for many positions at once, read from a whole-contig region's
+ * device-resident depth: depth_out[i] == map[positions[i]], 0 beyond the map (the reference catches the out_of_range
+ * and adds nothing).  With csv_window_sums this serves every consumer of the depth map -- its size, the log2 windows,
+ * the VCF's DP / SUPPORT -- without the map crossing PCIe. */
+int csv_depth_at(csv_ctx* ctx, csv_batch* b, uint32_t region, uint64_t n, const uint32_t* positions, uint32_t* depth_out);
+
 /* ------------------------------------------------------- synthetic inputs */
 
 /* Seeded generator of coordinate-sorted long-read alignments.

@@ -414,6 +414,20 @@ def test_signature_clustering_on_device(ctx, oracle):
     b.free()
 
 
+def test_depth_at_positions(ctx, oracle):
+    """SVCaller::getReadDepth served from the device-resident map (sv_caller.cpp:1332-1344): 0 beyond the map."""
+    clen = [120_000, 40_000]
+    r = util.synth_reads(clen, seed=29, n_sv=30, coverage=25.0)
+    b = run_batch(ctx, r, api.whole_contig_regions(clen))
+    rng = np.random.default_rng(29)
+    for t in range(2):
+        d, _, _ = oracle.depth(r, t, clen[t] + 1)
+        pos = np.concatenate([rng.integers(0, clen[t] + 1, 5000), [0, clen[t], clen[t] + 1, clen[t] + 500, 2**32 - 1]]).astype(np.uint32)
+        want = np.where(pos <= clen[t], d[np.minimum(pos, clen[t])], 0)
+        assert np.array_equal(b.depth_at(t, pos), want)
+    b.free()
+
+
 def test_mirror_classes(ctx, oracle):
     """The reference-shaped host interface (CNVCaller / SVCaller mirrors in contextsv_b200.api)."""
     clen = [80_000, 20_000]
