@@ -46,17 +46,39 @@ constexpr uint32_t kSearchShortRecord = 64;     // events; shorter records are t
 
 // pair range [a, b) of record k that can touch [T0, T1): everything before a is an even number of events left of the
 // tile (net zero), everything from b on lies at or beyond T1
+// first slot in [lo, hi) whose event is >= x.  The events of a long record are spread almost evenly over its span, so the
+// slot is guessed by interpolation and bracketed with a doubling step before the binary search: ~3 + 5 probes, most of
+// them in one or two cache lines, instead of 13 scattered ones.
+__device__ __forceinline__ uint32_t event_lower_bound(const uint32_t* __restrict__ events, uint32_t lo, uint32_t hi, uint32_t x)
+{
+    if (lo >= hi) return lo;
+    const uint32_t first = __ldg(events + lo), last = __ldg(events + hi - 1u);
+    if (x <= first) return lo;
+    if (x > last) return hi;
+    // first < x <= last: the answer is in (lo, hi - 1]
+    uint32_t g = lo + (uint32_t)(((unsigned long long)(x - first) * (hi - 1u - lo)) / (last - first));
+    uint32_t a, b;                                          // invariant: events[a] < x <= events[b]
+    if (__ldg(events + g) < x) {
+        a = g; uint32_t step = 16;
+        for (;;) { b = a + step < hi - 1u ? a + step : hi - 1u; if (b == hi - 1u || __ldg(events + b) >= x) break; a = b; step <<= 1; }
+    } else {
+        b = g; uint32_t step = 16;
+        for (;;) { a = b > lo + step ? b - step : lo; if (a == lo || __ldg(events + a) < x) break; b = a; step <<= 1; }
+    }
+    while (b - a > 1u) { const uint32_t mid = a + ((b - a) >> 1); if (__ldg(events + mid) < x) a = mid; else b = mid; }
+    return b;
+}
+
+// pair range [a, b) of record k that can touch [T0, T1): everything before a is an even number of events left of the
+// tile (net zero), everything from b on lies at or beyond T1
 __device__ __forceinline__ uint2 record_pair_range(const uint32_t* __restrict__ events, const uint32_t* __restrict__ ev_start, uint32_t k,
                                                   uint32_t T0, uint32_t T1)
 {
     const uint32_t es = ev_start[k], ee = ev_start[k + 1];
     if (ee - es <= kSearchShortRecord) return make_uint2(es >> 1, ee >> 1);
-    uint32_t lo = es, hi = ee;
-    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(events + mid) < T0) lo = mid + 1; else hi = mid; }
-    const uint32_t lb0 = lo;
-    hi = ee;
-    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(events + mid) < T1) lo = mid + 1; else hi = mid; }
-    return make_uint2(lb0 >> 1, (lo + 1u) >> 1);
+    const uint32_t lb0 = event_lower_bound(events, es, ee, T0);
+    const uint32_t lb1 = event_lower_bound(events, lb0, ee, T1);
+    return make_uint2(lb0 >> 1, (lb1 + 1u) >> 1);
 }
 
 // ------------------------------------------------------- prefix max over records
