@@ -44,7 +44,7 @@ EXPORTS = [
     "csv_ctx_create", "csv_ctx_destroy", "csv_ctx_sync", "csv_last_error", "csv_version", "csv_host_alloc", "csv_host_free",
     "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_ctx_set_pipeline_chunks", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
     "csv_depth_stats", "csv_depth_fetch", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
-    "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at",
+    "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at", "csv_record_summary",
 ]
 SYNTH_EXPORTS = ["csv_synth_default_params", "csv_synth_num_reads", "csv_synth_reads", "csv_synth_cigar"]
 
@@ -87,6 +87,7 @@ def lib():
         L.csv_cigar_scan.argtypes = [C.c_void_p, C.POINTER(CsvReads), C.POINTER(CsvRegion), C.c_uint32, C.c_uint8, C.POINTER(CsvSigs),
                                      C.c_uint64, C.POINTER(C.c_uint64)]
         L.csv_dbscan1d.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.csv_record_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.csv_depth_at.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
         L.csv_dbscan2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_void_p]
         L.csv_dbscan1d_seg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p]

@@ -183,6 +183,13 @@ class Batch:
         check(lib().csv_sigs_dbscan1d(self.ctx.h, self.h, float(eps), int(min_pts), ptr(lab), max(n, 1)))
         return lab[:n]
 
+    def record_summary(self):
+        """(bam_endpos, query_start, query_end) of every record: what the split-read pass reads off each alignment
+        (sv_caller.cpp:150-162, 663-690)."""
+        e = np.zeros(self.n_reads, np.int32); s = np.zeros(self.n_reads, np.int32); q = np.zeros(self.n_reads, np.int32)
+        check(lib().csv_record_summary(self.ctx.h, self.h, ptr(e), ptr(s), ptr(q)))
+        return e, s, q
+
     def depth_at(self, region, positions):
         """SVCaller::getReadDepth for many positions, from the device-resident map (0 beyond it)."""
         pos = np.ascontiguousarray(positions, np.uint32)

@@ -17,7 +17,7 @@ INC = os.path.join(ROOT, "include")
 LIB_CUDA = os.path.join(PKG, "libcontextsv_b200.so")
 LIB_SYNTH = os.path.join(PKG, "libcsvsynth.so")
 
-CUDA_SOURCES = ["capi.cu", "prep.cu", "walk.cu", "depth_tiles.cu", "radix_sort.cu", "sigs.cu", "dbscan1d.cu", "dbscan2d.cu", "windows.cu"]
+CUDA_SOURCES = ["capi.cu", "prep.cu", "walk.cu", "depth_tiles.cu", "radix_sort.cu", "sigs.cu", "dbscan1d.cu", "dbscan2d.cu", "windows.cu", "records.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",

@@ -209,6 +209,11 @@ int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv,
  * the VCF's DP / SUPPORT -- without the map crossing PCIe. */
 int csv_depth_at(csv_ctx* ctx, csv_batch* b, uint32_t region, uint64_t n, const uint32_t* positions, uint32_t* depth_out);
 
+/* Per-record summaries the split-read pass starts from (SVCaller::detectSVsFromSplitReads, sv_caller.cpp:150-162):
+ * bam_endpos(b) and SVCaller::getAlignmentReadPositions(b) (sv_caller.cpp:663-690) for every record of the batch, in
+ * csv_reads order.  Any output may be NULL.  The batch needs no scan first. */
+int csv_record_summary(csv_ctx* ctx, csv_batch* b, int32_t* endpos_out, int32_t* query_start_out, int32_t* query_end_out);
+
 /* ------------------------------------------------------- synthetic inputs */
 
 /* Seeded generator of coordinate-sorted long-read alignments.

@@ -247,6 +247,26 @@ void orc_dbscan1d(const int32_t* pts, uint64_t n, double eps, int min_pts, int32
     free(seeds.v); free(result.v);
 }
 
+/* ---- per-record summaries of the split-read pass ("next" row 8f-3): SVCaller::getAlignmentReadPositions
+ * (src/sv_caller.cpp:663-690) and htslib's bam_endpos (pos + max(1, reference length), 0 reference bases if unmapped) */
+void orc_record_summary(const orc_reads* r, int32_t* endpos, int32_t* qstart, int32_t* qend)
+{
+    for (uint64_t i = 0; i < r->n_reads; i++) {
+        int query_start = -1, query_end = 0;                       /* :665-666 */
+        uint32_t rlen = 0;
+        for (uint64_t o = r->cig_off[i]; o < r->cig_off[i + 1]; o++) {
+            int op_len = (int)(r->cigar[o] >> 4), op = (int)(r->cigar[o] & 15u);
+            if (query_start == -1 && (op == 0 || op == 1 || op == 7 || op == 8)) query_start = query_end;   /* :674-676 */
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) query_end += op_len;                    /* :680-682 */
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += (uint32_t)op_len;
+        }
+        if (query_start == -1) query_start = 0;                    /* :685-687 */
+        if (r->flag[i] & 0x4) rlen = 0;
+        endpos[i] = (int32_t)((uint32_t)r->pos0[i] + (rlen ? rlen : 1u));
+        qstart[i] = query_start; qend[i] = query_end;
+    }
+}
+
 /* ---- DBSCAN::fit, 2-D (src/dbscan.cpp:9-81): the clustering mergeSVs runs on the signatures ("next" row 8f-1) */
 static double db2_distance(uint32_t s1, uint32_t e1, uint32_t s2, uint32_t e2)   /* :69-81 */
 {

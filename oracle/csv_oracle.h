@@ -77,6 +77,9 @@ void orc_dbscan1d(const int32_t* pts, uint64_t n, double eps, int min_pts,
 void orc_dbscan1d_fast(const int32_t* pts, uint64_t n, double eps, int min_pts,
                        int32_t* labels);
 
+/* sv_caller.cpp:663-690 (getAlignmentReadPositions) + htslib bam_endpos, per record (split-read pass, sv_caller.cpp:150-162). */
+void orc_record_summary(const orc_reads* r, int32_t* endpos, int32_t* qstart, int32_t* qend);
+
 /* dbscan.cpp:9-81 (2-D DBSCAN::fit over intervals, reciprocal-overlap distance), literal sequential O(N^2). */
 void orc_dbscan2d(const uint32_t* start, const uint32_t* end, uint64_t n, double eps, int min_pts, int32_t* labels);
 

@@ -108,6 +108,14 @@ class Oracle:
         fn(*args, _p(out), C.c_uint64(n))
         return out[:n]
 
+    def record_summary(self, r):
+        r = norm_reads(r)
+        st = _orc_struct(r)
+        n = int(r["n_reads"])
+        e = np.zeros(n, np.int32); s = np.zeros(n, np.int32); q = np.zeros(n, np.int32)
+        self.lib.orc_record_summary(C.byref(st), _p(e), _p(s), _p(q))
+        return e, s, q
+
     def dbscan1d(self, pts, eps, min_pts, fast=False):
         pts = np.ascontiguousarray(pts, np.int32)
         lab = np.zeros(len(pts), np.int32)
@@ -185,6 +193,15 @@ class Reference:
             cap = n
         alts = [bytes(alt[64 * i: 64 * i + 64]).split(b"\0")[0].decode() for i in range(n)]
         return st[:n], en[:n], ty[:n], ev[:n], alts
+
+    def record_summary(self, r, tid, contig_len):
+        """(bam_endpos, query_start, query_end) of the records sam_itr_querys yields for contig tid, in file order."""
+        m, keep = self._mem(r, contig_len)
+        cap = int(norm_reads(r)["n_reads"]) + 1
+        e = np.zeros(cap, np.int32); s = np.zeros(cap, np.int32); q = np.zeros(cap, np.int32)
+        self.lib.ref_record_summary.restype = C.c_int64
+        n = int(self.lib.ref_record_summary(C.byref(m), C.c_int32(tid), _p(e), _p(s), _p(q), C.c_uint64(cap)))
+        return e[:n], s[:n], q[:n]
 
     def dbscan1d(self, pts, eps, min_pts):
         pts = np.ascontiguousarray(pts, np.int32)

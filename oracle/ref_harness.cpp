@@ -178,4 +178,35 @@ void ref_dbscan2d(const uint32_t* start, const uint32_t* end, uint64_t n, double
     if (n) memcpy(labels, c.data(), n * sizeof(int));
 }
 
+/* What the split-read pass reads off every record (sv_caller.cpp:150-162): bam_endpos and
+ * SVCaller::getAlignmentReadPositions (sv_caller.cpp:663-690), for the records of one contig in file order. */
+int64_t ref_record_summary(const csvshim_mem* m, int32_t tid, int32_t* endpos_out, int32_t* qstart_out, int32_t* qend_out, uint64_t cap)
+{
+    std::string name = unique_name();
+    csvshim_register_mem(name.c_str(), m);
+    std::string path = "mem:" + name;
+    uint64_t n = 0;
+    {
+        Quiet q(g_quiet);
+        samFile* fp = sam_open(path.c_str(), "r");
+        bam_hdr_t* hdr = sam_hdr_read(fp);
+        hts_idx_t* idx = sam_index_load(fp, path.c_str());
+        hts_itr_t* itr = sam_itr_querys(idx, hdr, m->target_name[tid]);
+        bam1_t* b = bam_init1();
+        SVCaller caller;
+        while (itr && sam_itr_next(fp, itr, b) >= 0) {
+            if (n < cap) {
+                const std::pair<int, int> qp = caller.getAlignmentReadPositions(b);
+                endpos_out[n] = (int32_t)bam_endpos(b); qstart_out[n] = qp.first; qend_out[n] = qp.second;
+            }
+            n++;
+        }
+        bam_destroy1(b);
+        if (itr) hts_itr_destroy(itr);
+        hts_idx_destroy(idx); bam_hdr_destroy(hdr); sam_close(fp);
+    }
+    csvshim_unregister_mem(name.c_str());
+    return (int64_t)n;
+}
+
 }  // extern "C"

@@ -34,6 +34,22 @@ def main():
         out["c%d_labels" % k] = R.dbscan2d(st, en, eps, mp)
         k += 1
     out["n"] = np.array([k])
+    # record summaries of the split-read pass (bam_endpos + getAlignmentReadPositions, sv_caller.cpp:150-162, 663-690)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import util
+    nrs = 0
+    for it in range(12):
+        clen = [int(rng.choice([3000, 40000]))]
+        r = util.random_cigar_reads(rng, int(rng.integers(1, 150)), clen, n_tids=1, weird=False, max_ops=int(rng.choice([1, 4, 12, 40])))
+        keep = np.nonzero(r["pos0"] < clen[0])[0]                    # what sam_itr_querys(contig) yields
+        e, s_, q = R.record_summary(r, 0, clen)
+        assert len(e) == len(keep)
+        p = "rs%d_" % nrs
+        for key in ("pos0", "flag", "mapq", "cig_off", "cigar"):
+            out[p + key] = np.asarray(r[key])
+        out[p + "keep"] = keep; out[p + "endpos"] = e; out[p + "qstart"] = s_; out[p + "qend"] = q
+        nrs += 1
+    out["n_rs"] = np.array([nrs])
     np.savez_compressed(os.path.join(HERE, "golden_db2_v1.npz"), **out)
     print("wrote", k, "cases")
 

@@ -414,6 +414,28 @@ def test_signature_clustering_on_device(ctx, oracle):
     b.free()
 
 
+def test_record_summary(ctx, oracle):
+    """bam_endpos + getAlignmentReadPositions of every record (split-read pass): golden vectors of the compiled
+    reference, adversarial CIGARs (all ops, empty records, unmapped flags), HiFi- and ONT-shaped records."""
+    for i, r, keep, e, s, q in util.golden_record_summary_cases():
+        b = api.Batch(ctx, r, api.whole_contig_regions([50000]))
+        ge, gs, gq = b.record_summary()
+        assert np.array_equal(ge[keep], e) and np.array_equal(gs[keep], s) and np.array_equal(gq[keep], q), i
+        b.free()
+    rng = np.random.default_rng(61)
+    cases = [util.random_cigar_reads(rng, 700, [90000, 5000], n_tids=2, weird=True, max_ops=mo) for mo in (1, 12, 40, 300)]
+    cases.append(util.synth_reads([400_000], seed=3, n_sv=60, frac_softclip=0.3))
+    cases.append(util.synth_reads([900_000], seed=4, profile=1, coverage=5.0, read_len_mean=60000, indel_rate=0.1, n_sv=20))
+    for r in cases:
+        clen = [int(x) for x in r.get("contig_len", [90000, 5000])]
+        b = api.Batch(ctx, r, api.whole_contig_regions(clen))
+        got = b.record_summary()
+        want = oracle.record_summary(r)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        b.free()
+
+
 def test_depth_at_positions(ctx, oracle):
     """SVCaller::getReadDepth served from the device-resident map (sv_caller.cpp:1332-1344): 0 beyond the map."""
     clen = [120_000, 40_000]

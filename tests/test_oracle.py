@@ -107,3 +107,16 @@ def test_dbscan2d_restatement_against_golden_and_reference():
         en = (st + rng.choice([0, 1, 20, 50, 200], n)).astype(np.uint32)
         eps = float(rng.choice([-0.5, 0, 0.1, 0.4, 0.99, 1.0, 2.0])); mp = int(rng.choice([-2, 0, 1, 2, 4]))
         assert np.array_equal(O.dbscan2d(st, en, eps, mp), R.dbscan2d(st, en, eps, mp)), (it, eps, mp)
+
+
+def test_record_summary_restatement_against_golden():
+    """orc_record_summary (getAlignmentReadPositions, sv_caller.cpp:663-690, + bam_endpos) vs the compiled reference's
+    committed outputs."""
+    from oracle.oracle_py import Oracle
+    O = Oracle()
+    n = 0
+    for i, r, keep, e, s, q in util.golden_record_summary_cases():
+        ge, gs, gq = O.record_summary(r)
+        assert np.array_equal(ge[keep], e) and np.array_equal(gs[keep], s) and np.array_equal(gq[keep], q), i
+        n += 1
+    assert n >= 10

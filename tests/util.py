@@ -135,3 +135,13 @@ def golden_db2_cases():
     for i in range(int(g["n"][0])):
         eps, mp = g["c%d_par" % i]
         yield i, g["c%d_start" % i], g["c%d_end" % i], float(eps), int(mp), g["c%d_labels" % i]
+
+
+def golden_record_summary_cases():
+    """(reads, indices the reference's iterator yields, endpos, query_start, query_end of the compiled reference)."""
+    g = np.load(GOLDEN_DB2)
+    for i in range(int(g["n_rs"][0])):
+        p = "rs%d_" % i
+        r = norm_reads({"n_reads": len(g[p + "pos0"]), "tid": None, "pos0": g[p + "pos0"], "flag": g[p + "flag"], "mapq": g[p + "mapq"],
+                        "cig_off": g[p + "cig_off"], "cigar": g[p + "cigar"]})
+        yield i, r, g[p + "keep"], g[p + "endpos"], g[p + "qstart"], g[p + "qend"]
