@@ -25,9 +25,13 @@ const std::vector<int>& DBSCAN::getClusters() const { return clusters; }
 // private helpers of the reference class: kept so that the class definition stays link-complete
 bool DBSCAN::expandCluster(const std::vector<SVCall>&, size_t, int) { return false; }
 std::vector<size_t> DBSCAN::regionQuery(const std::vector<SVCall>&, size_t) const { return {}; }
-double DBSCAN::distance(const SVCall& point1, const SVCall& point2) const
+double DBSCAN::distance(const SVCall& a, const SVCall& b) const
 {
-    const int overlap = std::max(0, std::min(static_cast<int>(point1.end), static_cast<int>(point2.end)) - std::max(static_cast<int>(point1.start), static_cast<int>(point2.start)));
-    const int length1 = static_cast<int>(point1.end - point1.start), length2 = static_cast<int>(point2.end - point2.start);
-    return 1.0 - std::min(static_cast<double>(overlap) / static_cast<double>(length1), static_cast<double>(overlap) / static_cast<double>(length2));
+    // 1 - minimum reciprocal overlap (same value as dbscan.cpp:69-81; unused once fit() runs on the GPU)
+    const int lo = static_cast<int>(a.start) > static_cast<int>(b.start) ? static_cast<int>(a.start) : static_cast<int>(b.start);
+    const int hi = static_cast<int>(a.end) < static_cast<int>(b.end) ? static_cast<int>(a.end) : static_cast<int>(b.end);
+    const double shared = hi > lo ? static_cast<double>(hi - lo) : 0.0;
+    const double fa = shared / static_cast<double>(static_cast<int>(a.end - a.start));
+    const double fb = shared / static_cast<double>(static_cast<int>(b.end - b.start));
+    return 1.0 - (fb < fa ? fb : fa);
 }
