@@ -36,7 +36,7 @@ void set_error(const char* fmt, ...);
 constexpr int kSMs = 148;                       // B200
 constexpr int kTile = 8192;                     // depth positions per tile (32 KB of int32 in smem)
 constexpr int kTileShift = 13;
-constexpr int kWalkThreads = 256;
+constexpr int kWalkThreads = 128;                           // 128 x 8 ops: measured best of 32 / 64 / 128 / 256 threads per span
 constexpr int kWalkOpsPerThread = 8;
 constexpr int kWalkSpan = kWalkThreads * kWalkOpsPerThread;   // CIGAR ops per span
 constexpr int kSpanChunk = 2048;                              // spans per chunk of the two-level span scan (256 threads x 8)

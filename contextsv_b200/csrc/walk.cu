@@ -280,7 +280,7 @@ __device__ __forceinline__ uint32_t sel9(const uint32_t (&c)[kWalkOpsPerThread +
 constexpr uint32_t kDeadPos = 0x80000000u;   // "first index" of a record that takes no part in the depth: every event
                                              // of such a record lands at or beyond 2^31 >= any map_size and no tile sees it
 
-// The walk proper.  One CTA per span of 2048 ops, 8 consecutive ops per thread.
+// The walk proper.  Persistent CTAs, one span of kWalkSpan = 1024 ops at a time (next one in flight by TMA), 8 consecutive ops per thread.
 //   A. thread-local exclusive prefix c[0..8] of reference consumption (NOT reset at record heads), bit masks of
 //      the D/N ops and of the signature candidates.
 //   B. warp scans with SHFL + predicated add: one packed scan for (record heads, event counts), one plain scan of
@@ -294,7 +294,7 @@ constexpr uint32_t kDeadPos = 0x80000000u;   // "first index" of a record that t
 //   D. record boundaries (about one per warp and pass for long reads) are handled in a sparse loop: the last
 //      event, ref_end and ev_start of the record that ends, the first event of the record that begins.
 template <bool DEPTH, bool SIGS, int MINB>
-__global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const WalkParams P)
+__global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_walk(const WalkParams P)
 {
     __shared__ __align__(128) uint32_t s_ops[2][kWalkSpan];                  // CIGAR words of the span in hand and of the next one
     __shared__ __align__(16) uint8_t s_hb[2][kWalkSpan / 8 + 16];            // their head bits (+ the byte that follows)
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const WalkParams P)
         const int lh = 31 - __clz(hbv);
         const uint32_t reftail = c[kWalkOpsPerThread] - (lh < 0 ? 0u : sel9(c, (uint32_t)lh));
         // ---- B
-        const uint32_t he = (heads << 16) | evn;                             // a span holds <= 2048 heads and <= 8192 events
+        const uint32_t he = (heads << 16) | evn;                             // a span holds <= kWalkSpan heads and <= 4 kWalkSpan events: 16 bits each
         const uint32_t he_inc = warp_incl_scan_fast(he);
         const uint32_t S = warp_incl_scan_fast(c[kWalkOpsPerThread]);
         const uint32_t hm = __ballot_sync(0xffffffffu, heads != 0u);
@@ -507,7 +507,7 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, sc0, sc1, b->d_scan_carry.as<WalkAgg>());
     k_span_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P);
     static const int minb = getenv("CSV_WALK_MINB") ? atoi(getenv("CSV_WALK_MINB")) : 4;    // tuning knob: CTAs per SM the compiler targets
-    static const int gmul = getenv("CSV_WALK_GRID") ? atoi(getenv("CSV_WALK_GRID")) : 8;    // persistent CTAs per SM in the grid (4 resident)
+    static const int gmul = getenv("CSV_WALK_GRID") ? atoi(getenv("CSV_WALK_GRID")) : 128;   // CTAs per SM in the grid (8 resident): each walks ~10-20 spans, the next one prefetched
     const uint32_t per_sm = (uint32_t)(minb == 5 || minb == 6 ? minb : 4);
     const uint32_t cap = (uint32_t)ctx->sm_count * (gmul > 0 ? (uint32_t)gmul : per_sm);
     const uint32_t grid = n < cap ? n : cap;

@@ -86,7 +86,7 @@ def test_random_adversarial_cigars(ctx, oracle):
 
 
 def test_long_reads_spanning_many_spans(ctx, oracle):
-    """ONT-like records: thousands of ops per record, so records straddle many 2048-op spans."""
+    """ONT-like records: thousands of ops per record, so records straddle many spans of the walk (1024 ops each)."""
     r = util.synth_reads([3_000_000], seed=21, profile=1, coverage=6.0, read_len_mean=50000, indel_rate=0.1, indel_len_max=4, n_sv=60)
     assert (np.diff(r["cig_off"]).max()) > 5000
     check_contigs(ctx, oracle, r, [3_000_000])
@@ -213,8 +213,9 @@ def test_pipelined_chunks_of_contigs(ctx, oracle):
     the chunked two-stream pass must give what the serial pass gives."""
     clen = [45_000_000, 40_000_000, 42_000_000]
     r = util.synth_reads(clen, seed=31, n_sv=200, coverage=30.0)
-    first_span = [int(r["cig_off"][int(np.searchsorted(r["tid"], t))]) // 2048 for t in (1, 2)]
-    assert first_span[0] // 2048 == 1 and first_span[1] // 2048 == 2 and int(r["n_ops"]) // 2048 >= 3 * 2048     # three chunks
+    # cuts fall on multiples of 2048 spans of 1024 ops: each contig must start in a later 2 M-op block than the one before
+    block = [int(r["cig_off"][int(np.searchsorted(r["tid"], t))]) // (1024 * 2048) for t in (1, 2)]
+    assert 0 < block[0] < block[1] and int(r["n_ops"]) // (1024 * 2048) >= block[1] + 1
     ctx.set_pipeline_chunks(4)
     try:
         check_contigs(ctx, oracle, r, clen)
