@@ -80,11 +80,12 @@ def select_reads(reads, regions, ends=None):
 
 
 def plan_by_ops(reads, contig_len, max_ops, ends=None):
-    """Shards for ONE device when the records hold more CIGAR ops than a batch takes (csv_batch_upload: < 2^31;
-    BASELINE config 3, 60x ONT, is ~3.7e10): the same region sharding as across GPUs, in time instead of space.
-    Walks the records in order and cuts a region whenever the next record would push the ops + records of the slice
-    [first halo record, record] past max_ops (a batch counts both: its event slots are 32-bit).  Cuts fall between records with different pos0, so every record is
-    owned by exactly one shard.  Returns a list of region lists [(tid, beg, end, map_size), ...] in genome order."""
+    """Shards for ONE device when the records hold more CIGAR ops than a batch takes (csv_batch_upload: ops + records
+    < 2^31; BASELINE config 3, 60x ONT, is ~3.7e10 ops): the same region sharding as across GPUs, in time instead of
+    space.  A shard is the slice [first halo record, last own record]; it is closed right before the first record that
+    would push its ops + records past max_ops.  Cuts fall between records with different pos0, so every record is owned
+    by exactly one shard.  One searchsorted per shard, no loop over records.
+    Returns a list of region lists [(tid, beg, end, map_size), ...] in genome order."""
     n = int(reads["n_reads"])
     sizes = [int(l) + 1 for l in contig_len]
     if n == 0:
@@ -93,37 +94,39 @@ def plan_by_ops(reads, contig_len, max_ops, ends=None):
     idx = np.asarray(reads["pos0"]).astype(np.int64) + 1
     off = np.asarray(reads["cig_off"]).astype(np.int64)
     ends = ref_end(reads) if ends is None else ends
-    # first record each record's shard would have to start with if a region began at this record:
-    # the earliest record of the same contig that still reaches idx (running max of ends, per contig)
+    weight = off + np.arange(n + 1)                              # ops + records before record j
+    key = tid * (1 << 33) + idx
+    new_group = np.concatenate([[True], key[1:] != key[:-1]])    # records sharing (tid, pos0) are never split
+    group_start = np.maximum.accumulate(np.where(new_group, np.arange(n), 0))
     shards, cur = [], []
-    cur_tid, cur_beg = 0, 0                   # open region starts at (cur_tid, cur_beg)
+    cur_tid, cur_beg = 0, 0                   # the open region starts at (cur_tid, cur_beg)
     i_first = 0                               # first record (halo included) of the open shard
-    i = 0
-    while i < n:
-        # group of records sharing (tid, pos0): never split
-        j = i + 1
-        while j < n and tid[j] == tid[i] and idx[j] == idx[i]:
-            j += 1
-        if off[j] - off[i_first] + (j - i_first) > max_ops and i > i_first and (tid[i] > cur_tid or idx[i] > cur_beg):
-            t, cut = int(tid[i]), int(min(idx[i], sizes[int(tid[i])]))
-            # close the open shard at (t, cut): whole contigs up to t, then [.., cut) of t
-            while cur_tid < t:
-                if cur_beg < sizes[cur_tid]:
-                    cur.append((cur_tid, cur_beg, sizes[cur_tid], sizes[cur_tid]))
-                cur_tid += 1; cur_beg = 0
-            if cut > cur_beg:
-                cur.append((t, cur_beg, cut, sizes[t]))
-                cur_beg = cut
-            if cur:
-                shards.append(cur); cur = []
-            # halo of the next shard: records of contig t before i that reach past cut
-            lo_t = int(np.searchsorted(tid, t, side="left"))
-            h = np.nonzero(ends[lo_t:i] > cut)[0]
-            i_first = lo_t + int(h[0]) if len(h) else i
-            if off[j] - off[i_first] + (j - i_first) > max_ops:
-                raise ValueError("max_ops=%d is too small: the records overlapping index %d of contig %d alone hold %d ops"
-                                 % (max_ops, cut, t, off[j] - off[i_first]))
-        i = j
+    while True:
+        # first record that does not fit any more (its whole group must fit)
+        j = int(np.searchsorted(weight, weight[i_first] + max_ops, side="right")) - 1      # records [i_first, j) fit
+        if j >= n:
+            break
+        i = int(group_start[j])               # cut before the group that contains record j
+        if i <= i_first or not (tid[i] > cur_tid or idx[i] > cur_beg):
+            # the group at the start of the shard alone is too much, or the cut would not advance the open region
+            g_end = int(np.searchsorted(key, key[j], side="right"))
+            raise ValueError("max_ops=%d is too small: the records overlapping index %d of contig %d alone hold %d ops + records"
+                             % (max_ops, int(idx[j]), int(tid[j]), int(weight[g_end] - weight[i_first])))
+        t, cut = int(tid[i]), int(min(idx[i], sizes[int(tid[i])]))
+        # close the open shard at (t, cut): whole contigs up to t, then [.., cut) of t
+        while cur_tid < t:
+            if cur_beg < sizes[cur_tid]:
+                cur.append((cur_tid, cur_beg, sizes[cur_tid], sizes[cur_tid]))
+            cur_tid += 1; cur_beg = 0
+        if cut > cur_beg:
+            cur.append((t, cur_beg, cut, sizes[t]))
+            cur_beg = cut
+        if cur:
+            shards.append(cur); cur = []
+        # halo of the next shard: records of contig t before i that reach past cut
+        lo_t = int(np.searchsorted(tid, t, side="left"))
+        h = np.nonzero(ends[lo_t:i] > cut)[0]
+        i_first = lo_t + int(h[0]) if len(h) else i
     while cur_tid < len(sizes):
         if cur_beg < sizes[cur_tid]:
             cur.append((cur_tid, cur_beg, sizes[cur_tid], sizes[cur_tid]))
