@@ -43,7 +43,7 @@ class CsvSigs(C.Structure):
 EXPORTS = [
     "csv_ctx_create", "csv_ctx_destroy", "csv_ctx_sync", "csv_last_error", "csv_version", "csv_host_alloc", "csv_host_free",
     "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_ctx_set_pipeline_chunks", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
-    "csv_depth_stats", "csv_depth_fetch", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
+    "csv_depth_stats", "csv_depth_fetch", "csv_depth_fetch_all", "csv_ctx_set_fetch", "csv_ctx_fetch_stats", "csv_host_widen_u8", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
     "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at", "csv_record_summary",
 ]
 SYNTH_EXPORTS = ["csv_synth_default_params", "csv_synth_num_reads", "csv_synth_reads", "csv_synth_cigar"]
@@ -80,6 +80,11 @@ def lib():
         L.csv_scan_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CsvScanParams)]
         L.csv_depth_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.csv_depth_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.csv_depth_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.csv_ctx_set_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64]
+        L.csv_ctx_fetch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.csv_host_widen_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.csv_host_widen_u8.restype = None
         L.csv_sigs_count.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.csv_sigs_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CsvSigs), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
         L.csv_sigs_dbscan1d.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_uint64]

@@ -63,6 +63,17 @@ class Context:
         """Batches uploaded from now on are scanned in up to n pipelined chunks of whole contigs."""
         check(lib().csv_ctx_set_pipeline_chunks(self.h, int(n)))
 
+    def set_fetch(self, threads=-1, chunk_positions=-1, exception_slots=-1, min_positions=-1):
+        """How depth maps come back (csv_ctx_set_fetch): `threads` host threads widen a byte-wide transfer into the
+        caller's uint32 array; 0 = plain 32-bit DMA.  -1 keeps a value."""
+        check(lib().csv_ctx_set_fetch(self.h, int(threads), int(chunk_positions), int(exception_slots), int(min_positions)))
+
+    def fetch_stats(self):
+        """(chunks fetched narrow, chunks re-fetched as plain words) since the context was created."""
+        a = C.c_uint64(0); b = C.c_uint64(0)
+        check(lib().csv_ctx_fetch_stats(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def profile_enable(self, on=True):
         check(lib().csv_profile_enable(self.h, int(on)))
 
@@ -153,6 +164,17 @@ class Batch:
             out = np.empty(end - beg, np.uint32)
         assert out.dtype == np.uint32 and out.size == end - beg and out.flags.c_contiguous
         check(lib().csv_depth_fetch(self.ctx.h, self.h, region, ptr(out)))
+        return out
+
+    def depth_all(self, out=None):
+        """Every region's slice through one fetch pipeline (csv_depth_fetch_all).  out: list of uint32 arrays or None."""
+        if out is None:
+            out = [np.empty(e - b, np.uint32) for (_, b, e, _) in self.regions]
+        assert len(out) == len(self.regions)
+        for o, (_, b, e, _) in zip(out, self.regions):
+            assert o.dtype == np.uint32 and o.size == e - b and o.flags.c_contiguous
+        ptrs = (C.c_void_p * len(out))(*[o.ctypes.data for o in out])
+        check(lib().csv_depth_fetch_all(self.ctx.h, self.h, ptrs))
         return out
 
     def sigs_count(self):

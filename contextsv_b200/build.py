@@ -17,7 +17,8 @@ INC = os.path.join(ROOT, "include")
 LIB_CUDA = os.path.join(PKG, "libcontextsv_b200.so")
 LIB_SYNTH = os.path.join(PKG, "libcsvsynth.so")
 
-CUDA_SOURCES = ["capi.cu", "prep.cu", "walk.cu", "depth_tiles.cu", "radix_sort.cu", "sigs.cu", "dbscan1d.cu", "dbscan2d.cu", "windows.cu", "records.cu"]
+CUDA_SOURCES = ["capi.cu", "prep.cu", "walk.cu", "depth_tiles.cu", "radix_sort.cu", "sigs.cu", "dbscan1d.cu", "dbscan2d.cu", "windows.cu", "records.cu", "fetch.cu"]
+HOST_SOURCES = ["widen.cpp"]          # plain g++ (AVX2 selected at run time)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",
@@ -51,7 +52,7 @@ def build_synth(force=False):
 
 
 def cuda_sources():
-    return [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+    return [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES]
 
 
 def build_cuda(force=False):
@@ -69,7 +70,11 @@ def build_cuda(force=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ["-I" + INC, "-I" + CSRC, "-c", s, "-o", o]
+        if s.endswith(".cu"):
+            cmd = [nvcc] + NVCC_FLAGS + ["-I" + INC, "-I" + CSRC, "-c", s, "-o", o]
+        else:
+            o = os.path.join(objdir, os.path.basename(s)[:-4] + ".o"); objs[-1] = o
+            cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-Wall", "-I" + INC, "-c", s, "-o", o]
         procs.append((cmd, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True
     for cmd, o, p in procs:

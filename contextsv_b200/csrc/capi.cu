@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <memory>
 #include <stdarg.h>
+#include <thread>
 
 namespace csv {
 
@@ -142,6 +143,9 @@ int csv_ctx_create(int device, csv_ctx** out)
     CSV_CUDA(cudaEventCreate(&ctx->ev0));
     CSV_CUDA(cudaEventCreate(&ctx->ev1));
     CSV_CUDA(cudaHostAlloc(&ctx->pinned_small, 4096, cudaHostAllocDefault));
+    // narrow depth fetch: on by default, one widening thread per host core up to 16 (fetch.cu)
+    ctx->fetch.threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (getenv("CSV_FETCH_THREADS")) ctx->fetch.threads = std::max(0, atoi(getenv("CSV_FETCH_THREADS")));
     *out = ctx;
     return CSV_OK;
 }
@@ -154,6 +158,7 @@ void csv_ctx_destroy(csv_ctx* ctx)
     cudaStreamSynchronize(ctx->tile_stream);
     cudaStreamSynchronize(ctx->main_stream);
     ctx->pool.trim();
+    fetch_release(ctx);
     for (auto e : ctx->ev_chunk) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_tile_join);
     cudaStreamDestroy(ctx->tile_stream);
@@ -207,6 +212,27 @@ int csv_ctx_set_pipeline_chunks(csv_ctx* ctx, int n_chunks)
 {
     if (!ctx || n_chunks < 1) { set_error("csv_ctx_set_pipeline_chunks: need a context and n_chunks >= 1"); return CSV_ERR_ARG; }
     ctx->pipe_chunks = n_chunks;
+    return CSV_OK;
+}
+
+int csv_ctx_set_fetch(csv_ctx* ctx, int threads, int64_t chunk_positions, int64_t exception_slots, int64_t min_positions)
+{
+    if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
+    if (chunk_positions >= 0 && (chunk_positions < 512 || chunk_positions % 512 || chunk_positions > (1 << 28))) {
+        set_error("csv_ctx_set_fetch: chunk_positions must be a multiple of 512 in [512, 2^28]"); return CSV_ERR_ARG;
+    }
+    if (exception_slots > (1 << 24) || min_positions > 0xffffffffll) { set_error("csv_ctx_set_fetch: value out of range"); return CSV_ERR_ARG; }
+    if (threads >= 0) ctx->fetch.threads = std::min(threads, 256);
+    if (chunk_positions >= 0) ctx->fetch.chunk = (uint32_t)chunk_positions;
+    if (exception_slots >= 0) ctx->fetch.exc_cap = (uint32_t)exception_slots;
+    if (min_positions >= 0) ctx->fetch.min_len = (uint32_t)min_positions;
+    return CSV_OK;
+}
+int csv_ctx_fetch_stats(const csv_ctx* ctx, uint64_t* narrow_chunks_out, uint64_t* fallback_chunks_out)
+{
+    if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
+    if (narrow_chunks_out) *narrow_chunks_out = ctx->fetch.narrow_chunks;
+    if (fallback_chunks_out) *fallback_chunks_out = ctx->fetch.fallback_chunks;
     return CSV_OK;
 }
 
@@ -481,9 +507,20 @@ int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth
     CSV_TRY(side_join(ctx));             // the tiles run on their own stream
     const size_t len = b->regions[region].end - b->regions[region].beg;
     const uint32_t* src = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
-    CSV_CUDA(cudaMemcpyAsync(depth_out, src, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
-    return CSV_OK;
+    return fetch_depth_segments(ctx, {FetchSeg{src, depth_out, len}});
+}
+
+int csv_depth_fetch_all(csv_ctx* ctx, csv_batch* b, uint32_t* const* depth_out)
+{
+    if (!ctx || !b || !depth_out) { set_error("null argument"); return CSV_ERR_ARG; }
+    if (!b->scanned || !b->have_depth) { set_error("csv_depth_fetch_all: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_TRY(side_join(ctx));
+    std::vector<FetchSeg> segs;
+    for (uint32_t r = 0; r < b->n_regions; r++) {
+        if (!depth_out[r]) continue;                           // regions the caller does not want
+        segs.push_back(FetchSeg{b->d_depth.as<uint32_t>() + (size_t)b->tile_base[r] * kTile, depth_out[r], (size_t)(b->regions[r].end - b->regions[r].beg)});
+    }
+    return fetch_depth_segments(ctx, segs);
 }
 
 int csv_depth_device_ptr(csv_ctx* ctx, csv_batch* b, uint32_t region, const uint32_t** dptr_out)

@@ -102,6 +102,23 @@ struct RegionDev {       // sorted by (tid, beg)
 };
 struct TidDev { uint32_t first, count, map_size, pad; };
 
+// Narrow depth fetch (fetch.cu): the map crosses PCIe as bytes (+ a short list of the values that do not fit) and
+// host threads widen it into the caller's uint32 array.
+struct FetchState {
+    int threads = 0;                 // host threads that widen; 0 = plain 32-bit DMA
+    uint32_t chunk = 2u << 20;       // positions per pipeline chunk (multiple of 512)
+    uint32_t exc_cap = 2048;         // exception slots per chunk (values >= 255)
+    uint32_t min_len = 1u << 18;     // shorter fetches use the plain DMA
+    int slots = 0;                   // staging ring (allocated lazily)
+    size_t slot_bytes = 0;
+    uint8_t* h = nullptr;            // pinned
+    uint8_t* d = nullptr;            // device
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> ev_narrow, ev_copy;
+    uint64_t narrow_chunks = 0, fallback_chunks = 0;     // statistics since context creation
+};
+struct FetchSeg { const uint32_t* src; uint32_t* dst; size_t len; };
+
 // Look-back scan state of the walk: record heads and depth events are plain sums,
 // (ref, qry) consumption is segmented: it restarts at every record head.
 struct WalkAgg { uint32_t heads, ref, qry, ev; };
@@ -136,6 +153,7 @@ struct csv_ctx {
     std::vector<cudaEvent_t> spare_events;
     double stage_ms[csv::ST_COUNT] = {0};
     uint32_t stage_calls[csv::ST_COUNT] = {0};
+    csv::FetchState fetch;
 };
 
 namespace csv {
@@ -156,6 +174,9 @@ struct TileScope {                      // ... to the tile stream
     explicit TileScope(csv_ctx* c) : ctx(c) { ctx->stream = ctx->tile_stream; ctx->tile_busy = true; }
     ~TileScope() { ctx->stream = ctx->main_stream; }
 };
+// Depth slices device -> host (fetch.cu).  Blocks until every segment is in host memory.
+int fetch_depth_segments(csv_ctx* ctx, const std::vector<FetchSeg>& segs);
+void fetch_release(csv_ctx* ctx);
 // RAII stage timer: records an event pair around a pipeline stage when profiling is on.
 struct StageTimer {
     csv_ctx* ctx; int stage; cudaEvent_t e1 = nullptr;

@@ -1,0 +1,40 @@
+// widen.cpp -- host half of the narrow depth fetch (fetch.cu): u8 -> u32 with non-temporal stores.
+// Plain g++ translation unit (no CUDA): the AVX2 body is selected at run time.
+#include <cstddef>
+#include <cstdint>
+#include <immintrin.h>
+
+#include "contextsv_b200.h"
+
+namespace {
+
+void widen_scalar(const uint8_t* src, uint32_t* dst, size_t n)
+{
+    for (size_t i = 0; i < n; i++) dst[i] = src[i];
+}
+
+// The destination is 12 GB that nobody reads back soon: streaming stores skip the read-for-ownership
+// (measured on the B200 host, 16 threads: 125-140 GB/s written against 72-76 GB/s with ordinary stores).
+__attribute__((target("avx2"))) void widen_avx2(const uint8_t* src, uint32_t* dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; i++; }     // dst is 4-byte aligned: at most 7 steps
+    for (; i + 32 <= n; i += 32) {
+        __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+        __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+        _mm256_stream_si256((__m256i*)(dst + i), _mm256_cvtepu8_epi32(a));
+        _mm256_stream_si256((__m256i*)(dst + i + 8), _mm256_cvtepu8_epi32(_mm_srli_si128(a, 8)));
+        _mm256_stream_si256((__m256i*)(dst + i + 16), _mm256_cvtepu8_epi32(b));
+        _mm256_stream_si256((__m256i*)(dst + i + 24), _mm256_cvtepu8_epi32(_mm_srli_si128(b, 8)));
+    }
+    for (; i < n; i++) dst[i] = src[i];
+    _mm_sfence();
+}
+
+}  // namespace
+
+extern "C" void csv_host_widen_u8(const uint8_t* src, uint32_t* dst, size_t n)
+{
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) widen_avx2(src, dst, n); else widen_scalar(src, dst, n);
+}

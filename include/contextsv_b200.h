@@ -57,6 +57,18 @@ int csv_timer_end(csv_ctx* ctx, float* ms_out);  /* synchronises the end event  
  * Default 1 (also settable with the environment variable CSV_CHUNKS): on B200 both kernels are limited by the warps
  * a register file holds, so running them side by side buys nothing today. */
 int csv_ctx_set_pipeline_chunks(csv_ctx* ctx, int n_chunks);
+/* How csv_depth_fetch / csv_depth_fetch_all / csv_depth bring the map back.  The reference's container is a uint32 per
+ * base (sv_caller.cpp:788,801); depths are small, so the map crosses PCIe as bytes plus a short list of the values
+ * >= 255 and `threads` host threads widen it into the caller's array -- bit-identical to a plain copy, and the
+ * destination need not be pinned.  threads = 0 selects the plain 32-bit DMA.  Default: min(host cores, 16), or the
+ * environment variable CSV_FETCH_THREADS.  A negative argument keeps the current value.  chunk_positions (multiple of
+ * 512, default 2 Mi) is the pipeline granule, exception_slots (default 2048) the list length per chunk (a chunk that
+ * overflows it is fetched again as plain words), min_positions (default 256 Ki) the shortest fetch that takes this path. */
+int csv_ctx_set_fetch(csv_ctx* ctx, int threads, int64_t chunk_positions, int64_t exception_slots, int64_t min_positions);
+/* Chunks fetched narrow / re-fetched plain since the context was created. */
+int csv_ctx_fetch_stats(const csv_ctx* ctx, uint64_t* narrow_chunks_out, uint64_t* fallback_chunks_out);
+/* Host helper of the narrow fetch: dst[i] = src[i] for i < n, streaming stores (no device needed). */
+void csv_host_widen_u8(const uint8_t* src, uint32_t* dst, size_t n);
 /* Kernels launched by this context since creation. */
 uint64_t csv_ctx_launch_count(const csv_ctx* ctx);
 /* Per-stage device time of the scan pipeline (event pairs around each stage while
@@ -134,6 +146,8 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p);
 int csv_depth_stats(csv_ctx* ctx, csv_batch* b, uint64_t* sum_out, uint32_t* nonzero_out);
 /* Depth slice of one region: depth_out[i] == reference map[beg + i]. */
 int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth_out);
+/* All regions in one pipeline: depth_out[r] receives region r (NULL = skip it). */
+int csv_depth_fetch_all(csv_ctx* ctx, csv_batch* b, uint32_t* const* depth_out);
 /* Device address of a region's depth slice (for device-side consumers). */
 int csv_depth_device_ptr(csv_ctx* ctx, csv_batch* b, uint32_t region, const uint32_t** dptr_out);
 

@@ -54,3 +54,19 @@ def test_no_silent_cpu_fallback():
     with pytest.raises(_capi.CsvError) as e:
         Context(0)
     assert e.value.status == 1 and "no CPU fallback" in str(e.value)
+
+
+def test_host_widen_helper():
+    """csv_host_widen_u8 (host half of the narrow depth fetch): every length / alignment, nothing written outside."""
+    import numpy as np
+    L = _capi.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 8, 31, 32, 33, 100, 4097, 1 << 18):
+        for off in range(9):
+            for soff in (0, 1, 3):
+                src = rng.integers(0, 256, n + soff + 16, dtype=np.uint8)[soff:soff + n]
+                buf = np.full(n + off + 16, 0xdeadbeef, np.uint32)
+                dst = buf[off:off + n]
+                L.csv_host_widen_u8(src.ctypes.data, dst.ctypes.data, n)
+                assert np.array_equal(dst, src), (n, off, soff)
+                assert (buf[:off] == 0xdeadbeef).all() and (buf[off + n:] == 0xdeadbeef).all()

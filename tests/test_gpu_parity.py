@@ -202,6 +202,61 @@ def test_pileups_deep_coverage(ctx, oracle):
         check_contigs(ctx, oracle, r, [L])
 
 
+def test_narrow_depth_fetch(oracle):
+    """csv_depth_fetch / csv_depth_fetch_all bring the map back as bytes + a list of the values >= 255 and widen it on
+    host threads.  Must equal the plain 32-bit DMA and the oracle for: many chunks through a short ring, values that
+    need the list (a pile-up in the thousands), a list that overflows (chunk re-fetched plain), odd lengths,
+    unaligned and pageable destinations."""
+    from oracle.oracle_py import make_reads
+    c = api.Context(0)
+    rng = np.random.default_rng(99)
+    clen = [40_001, 9_999, 513]
+    pos0, tid, cig = [], [], []
+    for t, L in enumerate(clen):
+        n = {0: 3000, 1: 600, 2: 400}[t]
+        p = np.sort(rng.integers(0, max(L - 300, 1), n))
+        if t == 0:
+            p = np.sort(np.concatenate([p, np.full(2500, 20_000), np.full(300, 33_000)]))    # depth > 2500 around 20 000, ~300 at 33 000
+        for x in p:
+            pos0.append(int(x)); tid.append(t)
+            cig.append([(int(rng.integers(20, 200)), M), (int(rng.integers(1, 9)), D), (int(rng.integers(1, 60)), EQ)])
+    r = make_reads(np.array(pos0, np.int32), cig, tid=np.array(tid, np.int32))
+    regions = api.whole_contig_regions(clen)
+    b = run_batch(c, r, regions, want_sigs=False)
+    want = [oracle.depth(r, t, clen[t] + 1)[0] for t in range(len(clen))]
+    assert want[0].max() > 2500
+    c.set_fetch(threads=0)
+    for t in range(len(clen)):
+        assert np.array_equal(b.depth(t), want[t])
+    n0 = c.fetch_stats()
+    assert n0 == (0, 0)
+    for threads, chunk, slots in ((3, 512, 64), (16, 1024, 2048), (2, 512, 4), (1, 4096, 0), (5, 1 << 20, 2048)):
+        c.set_fetch(threads=threads, chunk_positions=chunk, exception_slots=slots, min_positions=0)
+        before = c.fetch_stats()
+        for t in range(len(clen)):
+            buf = np.full(clen[t] + 1 + 3, 0xabababab, np.uint32)           # unaligned view into a pageable array
+            got = b.depth(t, out=buf[3:])
+            assert np.array_equal(got, want[t]), "narrow fetch tid %d (threads %d chunk %d slots %d): first diff at %s" % (
+                t, threads, chunk, slots, np.nonzero(got != want[t])[0][:5])
+            assert (buf[:3] == 0xabababab).all()
+        outs = b.depth_all()
+        for t in range(len(clen)):
+            assert np.array_equal(outs[t], want[t])
+        after = c.fetch_stats()
+        assert after[0] > before[0]
+        if slots <= 4:
+            assert after[1] > before[1], "the pile-up chunks must have overflowed the exception list"
+    # the one-shot entry point takes the same path
+    c.set_fetch(threads=4, chunk_positions=2048, exception_slots=16, min_positions=0)
+    rs, keep = reads_struct(r)
+    out = np.zeros(clen[0] + 1, np.uint32); s = C.c_uint64(0); nz = C.c_uint32(0)
+    reg = CsvRegion(0, 0, clen[0] + 1, clen[0] + 1)
+    check(lib().csv_depth(c.h, C.byref(rs), C.byref(reg), ptr(out), C.byref(s), C.byref(nz)))
+    assert np.array_equal(out, want[0]) and int(s.value) == int(want[0].astype(np.uint64).sum())
+    b.free()
+    c.close()
+
+
 def test_synthetic_hifi_multi_contig(ctx, oracle):
     clen = [1_500_000, 700_000, 50_000]
     r = util.synth_reads(clen, seed=5, n_sv=300, coverage=30.0, frac_len50=0.1)
