@@ -332,10 +332,11 @@ def main_ours(args):
 
     # The depth maps come back through csv_depth_fetch_all: bytes over PCIe + host threads that widen them into the
     # caller's uint32 arrays (fetch.cu).  The host cores are shared by the ranks of one box.
-    fetch_threads = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+    fetch_threads = max(1, min(16, (os.cpu_count() or 1) // max(world, 1) - (2 if world == 1 else 0)))
     ctx.set_fetch(threads=fetch_threads)
 
     def step_e2e():
+        """One batch: upload everything, scan, fetch everything."""
         bt = api.Batch(ctx, reads, regions)                       # H2D of the packed SoA
         bt.scan(want_depth=True, want_sigs=True)
         lab = bt.sigs_dbscan1d(DB_EPS, DB_MIN_PTS)                # D2H labels
@@ -343,13 +344,13 @@ def main_ours(args):
         bt.depth_all(out_depth)                                   # D2H depth maps (uint32 per base in host memory)
         sg = bt.sigs()                                            # D2H signatures
         bt.free()
-        return len(lab), sg, sums, nzs
+        return len(lab), len(sg["start"]), int(sums.sum()), int(nzs.sum())
 
-    def timed_e2e(n_steps):
+    def timed(step, n_steps):
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_steps):
-            r = step_e2e()
+            r = step()
         ctx.sync()
         dt = time.perf_counter() - t0
         barrier()
@@ -362,14 +363,14 @@ def main_ours(args):
         for _ in range(min(args.warmup, 2)):
             step_e2e()
         st0 = ctx.fetch_stats()
-        dt_max, (nl, sg, sums, nzs) = timed_e2e(e2e_steps)
-        e2e_value = total_reads * e2e_steps / dt_max
+        dt_max, _ = timed(step_e2e, e2e_steps)
         st1 = ctx.fetch_stats()
         narrow_chunks, fallback_chunks = (st1[0] - st0[0]) // e2e_steps, (st1[1] - st0[1]) // e2e_steps     # per step
+        e2e_value = total_reads * e2e_steps / dt_max
         # the same step with the plain 32-bit DMA of the map (csv_ctx_set_fetch threads = 0), for comparison
         ctx.set_fetch(threads=0)
         step_e2e()
-        dt_plain, _ = timed_e2e(e2e_steps)
+        dt_plain, _ = timed(step_e2e, e2e_steps)
         ctx.set_fetch(threads=fetch_threads)
     # ---- the same step when the consumers of the depth map query the device (csv_depth_at = getReadDepth for every
     # signature start, csv_window_sums for the log2 windows) instead of the 12 GB map crossing PCIe.  Extra information:

@@ -143,8 +143,10 @@ int csv_ctx_create(int device, csv_ctx** out)
     CSV_CUDA(cudaEventCreate(&ctx->ev0));
     CSV_CUDA(cudaEventCreate(&ctx->ev1));
     CSV_CUDA(cudaHostAlloc(&ctx->pinned_small, 4096, cudaHostAllocDefault));
-    // narrow depth fetch: on by default, one widening thread per host core up to 16 (fetch.cu)
-    ctx->fetch.threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    // narrow depth fetch: on by default; widening threads = host cores - 2 (the thread that feeds the pipeline and the
+    // CUDA driver want the rest), at most 16 (fetch.cu)
+    const unsigned hw = std::thread::hardware_concurrency();
+    ctx->fetch.threads = (int)std::min(16u, hw > 3 ? hw - 2 : 1u);
     if (getenv("CSV_FETCH_THREADS")) ctx->fetch.threads = std::max(0, atoi(getenv("CSV_FETCH_THREADS")));
     *out = ctx;
     return CSV_OK;

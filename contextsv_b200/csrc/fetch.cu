@@ -7,11 +7,15 @@
 //
 //   device   k_depth_narrow: u32 -> u8, values >= 255 stored as 255 and appended to a short (index, value) list
 //   PCIe     one cudaMemcpyAsync per chunk (header + list + bytes) into a pinned staging ring, own copy stream
-//   host     worker threads widen u8 -> u32 straight into the caller's array with streaming stores (widen.cpp), then
-//            patch the listed values; a chunk whose list overflowed is fetched again as plain 32-bit words
+//   host     worker threads widen u8 -> u32 straight into the caller's array with streaming stores (widen.cpp), 256 Ki
+//            positions at a time, then patch the listed values; a chunk whose list overflowed is fetched again as
+//            plain 32-bit words
 //
 // The result is bit-identical to the plain copy for every input; the plain copy stays for short fetches and for
-// threads == 0.  B200 host (16 cores): 12.4 GB in ~100 ms instead of 216 ms (pinned) / 590 ms (pageable).
+// threads == 0.  B200 host (16 cores, scripts/fetch_sweep.py): the 12.4 GB of a genome in 101-108 ms (14 threads,
+// 118 GB/s into host memory; widening alone peaks at 125-140 GB/s, scripts/fetch_probe.cu) instead of 216 ms into
+// pinned / 576 ms into pageable memory.  The hosts of the pool differ and are shared: the same call took 200-240 ms on a
+// busy box, where the plain copy took 269 / 724 ms.
 #include "batch.cuh"
 
 #include <algorithm>
@@ -84,13 +88,16 @@ static int ensure_ring(csv_ctx* ctx, int slots)
 }
 
 namespace {
-struct Chunk { const uint32_t* src; uint32_t* dst; uint32_t n; };
+constexpr uint32_t kPart = 256u << 10;      // positions one worker widens at a time: a chunk is shared by chunk / kPart workers
+struct Chunk { const uint32_t* src; uint32_t* dst; uint32_t n; uint32_t first_task, parts; };
 struct Job {
     std::mutex m;
     std::condition_variable cv_issue, cv_done;
-    size_t issued = 0, next = 0;
+    size_t issued = 0, next = 0;             // tasks (parts of chunks) whose bytes are on their way / handed to a worker
     bool closed = false;
-    std::vector<uint8_t> done;
+    std::vector<uint32_t> task_chunk;
+    std::vector<uint32_t> remaining;         // parts of the chunk still being widened
+    std::vector<uint8_t> done;               // chunk has left its staging slot
     std::vector<size_t> fallback;
     cudaError_t error = cudaSuccess;
 };
@@ -103,42 +110,59 @@ int fetch_depth_segments(csv_ctx* ctx, const std::vector<FetchSeg>& segs)
     for (auto& s : segs) total += s.len;
     if (f.threads <= 0 || total < f.min_len) return fetch_plain(ctx, segs);
 
+    // A chunk is widened by several workers (kPart positions each), so the staging ring stays at a few slots (12 MB by
+    // default) whatever the thread count: what the copy engine writes is then still in the host's last-level cache when
+    // a worker reads it, and only the 4 bytes per base of the result go to DRAM.  With one worker per chunk and a ring of
+    // threads + 6 slots, 1 / 2 / 4 Mi-position chunks took 198 / 229 / 245 ms on the same box.
+    Job job;
     std::vector<Chunk> chunks;
     for (auto& s : segs)
-        for (size_t o = 0; o < s.len; o += f.chunk) chunks.push_back({s.src + o, s.dst + o, (uint32_t)std::min<size_t>(f.chunk, s.len - o)});
-    const int n_threads = (int)std::min<size_t>(f.threads, chunks.size());
-    const int slots = n_threads + 6;            // every worker holds one chunk while the copy engine fills the rest
+        for (size_t o = 0; o < s.len; o += f.chunk) {
+            const uint32_t n = (uint32_t)std::min<size_t>(f.chunk, s.len - o), parts = (n + kPart - 1) / kPart;
+            chunks.push_back({s.src + o, s.dst + o, n, (uint32_t)job.task_chunk.size(), parts});
+            for (uint32_t p = 0; p < parts; p++) job.task_chunk.push_back((uint32_t)(chunks.size() - 1));
+            job.remaining.push_back(parts);
+        }
+    const size_t n_tasks = job.task_chunk.size();
+    const int n_threads = (int)std::min<size_t>(f.threads, n_tasks);
+    const uint32_t parts_per_chunk = (f.chunk + kPart - 1) / kPart;
+    const int slots = (n_threads + (int)parts_per_chunk - 1) / (int)parts_per_chunk + 4;   // chunks being widened + chunks in flight
     CSV_TRY(ensure_ring(ctx, slots));
 
-    Job job;
     job.done.assign(chunks.size(), 0);
     const int device = ctx->device;
     auto worker = [&]() {
         cudaSetDevice(device);
         for (;;) {
-            size_t c;
+            size_t t;
             {
                 std::unique_lock<std::mutex> lk(job.m);
                 job.cv_issue.wait(lk, [&] { return job.next < job.issued || job.closed; });
                 if (job.next >= job.issued) return;
-                c = job.next++;
+                t = job.next++;
             }
+            const size_t c = job.task_chunk[t];
+            const Chunk& ch = chunks[c];
             const int slot = (int)(c % (size_t)slots);
             const uint8_t* h = f.h + (size_t)slot * f.slot_bytes;
-            cudaError_t e = cudaEventSynchronize(f.ev_copy[slot]);
-            bool overflow = false;
-            if (e == cudaSuccess) {
-                const uint32_t* hdr = (const uint32_t*)h;
-                const uint32_t cnt = hdr[0];
-                overflow = cnt > f.exc_cap;
-                if (!overflow) {
-                    csv_host_widen_u8(h + 16 + (size_t)f.exc_cap * 8, chunks[c].dst, chunks[c].n);
-                    for (uint32_t i = 0; i < cnt; i++) chunks[c].dst[hdr[4 + 2 * i]] = hdr[5 + 2 * i];
-                }
+            const uint32_t* hdr = (const uint32_t*)h;
+            const cudaError_t e = cudaEventSynchronize(f.ev_copy[slot]);
+            const bool overflow = e == cudaSuccess && hdr[0] > f.exc_cap;
+            if (e == cudaSuccess && !overflow) {
+                const size_t o = (size_t)(t - ch.first_task) * kPart;
+                csv_host_widen_u8(h + 16 + (size_t)f.exc_cap * 8 + o, ch.dst + o, std::min<size_t>(kPart, ch.n - o));
             }
+            bool last;
             {
                 std::lock_guard<std::mutex> lk(job.m);
                 if (e != cudaSuccess && job.error == cudaSuccess) job.error = e;
+                last = --job.remaining[c] == 0;
+            }
+            if (!last) continue;
+            if (e == cudaSuccess && !overflow)                       // every part is in place: the values that did not fit a byte
+                for (uint32_t i = 0; i < hdr[0]; i++) ch.dst[hdr[4 + 2 * i]] = hdr[5 + 2 * i];
+            {
+                std::lock_guard<std::mutex> lk(job.m);
                 if (overflow) job.fallback.push_back(c);
                 job.done[c] = 1;
             }
@@ -172,9 +196,9 @@ int fetch_depth_segments(csv_ctx* ctx, const std::vector<FetchSeg>& segs)
         if ((err = cudaEventRecord(f.ev_copy[slot], f.copy_stream)) != cudaSuccess) break;
         {
             std::lock_guard<std::mutex> lk(job.m);
-            job.issued = c + 1;
+            job.issued = chunks[c].first_task + chunks[c].parts;
         }
-        job.cv_issue.notify_one();
+        job.cv_issue.notify_all();
     }
     {
         std::lock_guard<std::mutex> lk(job.m);

@@ -54,15 +54,18 @@ def select_reads(reads, regions, ends=None):
         return dict(reads), 0
     tid = np.zeros(n, np.int64) if reads.get("tid") is None else np.asarray(reads["tid"]).astype(np.int64)
     idx = np.asarray(reads["pos0"]).astype(np.int64) + 1
-    ends = ref_end(reads) if ends is None else ends
     t0, b0, _, _ = regions[0]
     t1, _, e1, m1 = regions[-1]
     key = tid * (1 << 33) + idx
     i_own = int(np.searchsorted(key, t0 * (1 << 33) + b0, side="left"))
-    # halo: records of contig t0 that start before b0 and reach past it
+    # halo: records of contig t0 that start before b0 and reach past it (none when the region starts the contig)
     lo_t = int(np.searchsorted(key, t0 * (1 << 33), side="left"))
-    halo = np.nonzero(ends[lo_t:i_own] > b0)[0]
-    i0 = lo_t + int(halo[0]) if len(halo) else i_own
+    i0 = i_own
+    if lo_t < i_own:
+        ends = ref_end(reads) if ends is None else ends
+        halo = np.nonzero(ends[lo_t:i_own] > b0)[0]
+        if len(halo):
+            i0 = lo_t + int(halo[0])
     if e1 == m1:
         i1 = int(np.searchsorted(key, (t1 + 1) * (1 << 33), side="left"))     # last region also owns records beyond the contig end
     else:

@@ -60,7 +60,7 @@ int csv_ctx_set_pipeline_chunks(csv_ctx* ctx, int n_chunks);
 /* How csv_depth_fetch / csv_depth_fetch_all / csv_depth bring the map back.  The reference's container is a uint32 per
  * base (sv_caller.cpp:788,801); depths are small, so the map crosses PCIe as bytes plus a short list of the values
  * >= 255 and `threads` host threads widen it into the caller's array -- bit-identical to a plain copy, and the
- * destination need not be pinned.  threads = 0 selects the plain 32-bit DMA.  Default: min(host cores, 16), or the
+ * destination need not be pinned.  threads = 0 selects the plain 32-bit DMA.  Default: host cores - 2 (at most 16), or the
  * environment variable CSV_FETCH_THREADS.  A negative argument keeps the current value.  chunk_positions (multiple of
  * 512, default 2 Mi) is the pipeline granule, exception_slots (default 2048) the list length per chunk (a chunk that
  * overflows it is fetched again as plain words), min_positions (default 256 Ki) the shortest fetch that takes this path. */
