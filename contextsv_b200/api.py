@@ -348,6 +348,7 @@ class CNVCaller:
         batch = Batch(ctx, alignments.reads, regions)
         batch.scan(want_depth=True, want_sigs=False)
         sums, nzs = batch.depth_stats()
+        outs = []
         for i, chrom in enumerate(chroms):
             size = regions[i][3]
             cur = chr_pos_depth_map.get(chrom)
@@ -355,7 +356,10 @@ class CNVCaller:
                 err("ERROR: Chromosome length mismatch for %s: expected %d, found %d, resizing to %d"
                     % (chrom, size, 0 if cur is None else len(cur), size))
                 cur = np.zeros(size, np.uint32)
-            chr_pos_depth_map[chrom] = batch.depth(i, out=np.ascontiguousarray(cur, np.uint32))
+            outs.append(np.ascontiguousarray(cur, np.uint32))
+        batch.depth_all(outs)                                                 # one fetch pipeline over all contigs
+        for i, chrom in enumerate(chroms):
+            chr_pos_depth_map[chrom] = outs[i]
             mean = float(sums[i]) / float(nzs[i]) if nzs[i] > 0 else 0.0     # :538  (uint64 -> double, uint32 -> double)
             if mean != 0.0:
                 chr_mean_cov_map[chrom] = mean
