@@ -17,6 +17,8 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
                                                 std::unordered_map<std::string, double>& chr_mean_cov_map,
                                                 const std::string& bam_filepath, int thread_count) const
 {
+    csvhost::StatTimer st_all(csvhost::STAT_DEPTH, chromosomes.size());
+    csvhost::warm_up_async();
     printMessage("Opening BAM file: " + bam_filepath);
     samFile* bam_file = sam_open(bam_filepath.c_str(), "r");
     if (!bam_file) { printError("ERROR: Could not open BAM file: " + bam_filepath); return; }
@@ -52,7 +54,7 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
     // scanned, and only the records that reach past the cut stay as the halo of the next shard -- the region sharding
     // of SURVEY 8e, in time instead of across GPUs, with bounded host memory.
     std::sort(by_tid.begin(), by_tid.end());
-    csv_ctx* ctx = csvhost::thread_context();
+    csv_ctx* ctx = nullptr;                                    // created at the first flush: CUDA start-up runs beside the decoding
     const uint64_t max_ops = csvhost::max_ops_per_batch();
     bool failed = false;
     for (const auto& tc : by_tid) {
@@ -68,6 +70,8 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
             const csv_region reg = {tc.first, beg, end, size};
             const csv_reads view = reads.view();
             uint64_t sum = 0; uint32_t nz = 0;
+            if (!ctx) ctx = csvhost::thread_context();
+            csvhost::StatTimer st(csvhost::STAT_DEPTH_GPU, view.n_reads);
             if (csv_depth(ctx, &view, &reg, depth.data() + beg, &sum, &nz) != CSV_OK) {
                 printError(std::string("ERROR: GPU depth pass failed: ") + csv_last_error());
                 failed = true;
@@ -76,19 +80,22 @@ void CNVCaller::calculateMeanChromosomeCoverage(const std::vector<std::string>& 
             beg = end;
         };
         int32_t last_pos = -2;
+        bool whole = true;                                     // the contig is still one shard
         while (sam_itr_next(bam_file, it, bam_record) >= 0) {
             const int32_t pos = (int32_t)bam_record->core.pos;
             if (reads.ops() + reads.size() + bam_record->core.n_cigar + 1 > max_ops && pos != last_pos && reads.size() > 0) {   // ops + records: a batch counts both
                 const uint32_t cut = std::min<uint32_t>((uint32_t)pos + 1u, size);       // records from here on start at or after the cut
                 flush(cut);
                 reads.keep_reaching(cut);
+                whole = false;
             }
-            reads.append(bam_record, false);
+            reads.append(bam_record, true);                    // with the bases of the few records the CIGAR pass will want them for
             last_pos = pos;
         }
         hts_itr_destroy(it);
         flush(size);
         if (failed) break;
+        if (whole) csvhost::cache_put(bam_filepath, tc.first, std::move(reads));   // the CIGAR pass scans the same records
         const double mean_chr_cov = (pos_count > 0) ? static_cast<double>(cum_depth) / static_cast<double>(pos_count) : 0.0;
         printMessage("Mean coverage for chromosome " + tc.second + ": " + std::to_string(mean_chr_cov));
         if (mean_chr_cov != 0.0) chr_mean_cov_map[tc.second] = mean_chr_cov;

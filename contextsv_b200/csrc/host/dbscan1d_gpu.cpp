@@ -13,6 +13,7 @@ void DBSCAN1D::fit(const std::vector<int>& points)
     clusters.assign(points.size(), -1);
     if (points.empty()) return;
     csv_ctx* ctx = csvhost::thread_context();
+    csvhost::StatTimer st(csvhost::STAT_DBSCAN1D, points.size());
     if (csv_dbscan1d(ctx, points.data(), points.size(), epsilon, minPts, clusters.data(), nullptr) != CSV_OK)
         throw std::runtime_error(std::string("DBSCAN1D::fit (GPU): ") + csv_last_error());   // caught by run() like any std::exception
 }

@@ -16,6 +16,7 @@ void DBSCAN::fit(const std::vector<SVCall>& sv_calls)
     std::vector<uint32_t> start(sv_calls.size()), end(sv_calls.size());
     for (size_t i = 0; i < sv_calls.size(); i++) { start[i] = sv_calls[i].start; end[i] = sv_calls[i].end; }
     csv_ctx* ctx = csvhost::thread_context();
+    csvhost::StatTimer st(csvhost::STAT_DBSCAN2D, start.size());
     if (csv_dbscan2d(ctx, start.data(), end.data(), start.size(), epsilon, minPts, clusters.data()) != CSV_OK)
         throw std::runtime_error(std::string("DBSCAN::fit (GPU): ") + csv_last_error());   // caught by run() like any std::exception
 }

@@ -2,6 +2,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 namespace csvhost {
 
@@ -58,6 +60,51 @@ uint64_t max_ops_per_batch()
         return x == 0 || x > hard ? hard : x;
     }();
     return v;
+}
+
+namespace {
+struct Cache {
+    std::mutex m;
+    std::map<std::pair<std::string, int>, std::unique_ptr<PackedReads>> entries;
+    uint64_t ops = 0;
+    uint64_t budget = [] {
+        const char* e = std::getenv("CONTEXTSV_CACHE_OPS");
+        return e ? std::strtoull(e, nullptr, 10) : (1ull << 30);
+    }();
+};
+Cache g_cache;
+}  // namespace
+
+void cache_put(const std::string& bam_path, int tid, PackedReads&& reads)
+{
+    std::lock_guard<std::mutex> lk(g_cache.m);
+    const uint64_t n = reads.ops() + reads.size();
+    if (g_cache.ops + n > g_cache.budget) return;
+    auto& slot = g_cache.entries[{bam_path, tid}];
+    if (slot) g_cache.ops -= slot->ops() + slot->size();
+    slot.reset(new PackedReads(std::move(reads)));
+    g_cache.ops += n;
+}
+
+std::unique_ptr<PackedReads> cache_take(const char* bam_path, int tid)
+{
+    if (!bam_path) return nullptr;
+    std::lock_guard<std::mutex> lk(g_cache.m);
+    auto it = g_cache.entries.find({std::string(bam_path), tid});
+    if (it == g_cache.entries.end()) return nullptr;
+    std::unique_ptr<PackedReads> r = std::move(it->second);
+    g_cache.entries.erase(it);
+    g_cache.ops -= r->ops() + r->size();
+    return r;
+}
+
+const char* file_name(samFile* fp)
+{
+#ifdef CSVSHIM_HTSLIB
+    return hts_get_fn(fp);
+#else
+    return fp ? fp->fn : nullptr;
+#endif
 }
 
 csv_reads PackedReads::view() const

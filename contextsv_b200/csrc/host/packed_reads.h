@@ -7,6 +7,7 @@
 #include <htslib/sam.h>
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -40,6 +41,16 @@ uint64_t max_ops_per_batch();
 
 // Every record an iterator yields, in file order.
 void pack_iterator(samFile* fp, hts_itr_t* itr, bam1_t* scratch, PackedReads& out, bool keep_seq);
+
+// Single decode: the depth pass packs every record of a contig, and the CIGAR pass of the same contig
+// (src/sv_caller.cpp:692-745, run later from a pool thread) needs exactly the same records -- the reference decodes
+// the BAM again for it.  The depth pass parks the packing of every contig it scanned in one piece here and the CIGAR
+// pass takes it instead of re-reading the file.  Bounded: at most CONTEXTSV_CACHE_OPS CIGAR ops in total (default 2^30,
+// 4 GB; a 30x HiFi genome holds 4e8; 0 disables), beyond that the CIGAR pass decodes as before.
+void cache_put(const std::string& bam_path, int tid, PackedReads&& reads);
+std::unique_ptr<PackedReads> cache_take(const char* bam_path, int tid);      // removes the entry; null if absent
+// Path the file was opened with (htsFile::fn in htslib; an accessor in the shim, whose htsFile is opaque).
+const char* file_name(samFile* fp);
 
 // seq_nt16_str[bam_seqi(seq, i)] with the IUPAC -> N mapping of src/sv_caller.cpp:554-559,576-580
 char base_at(const std::vector<uint8_t>& seq4, uint32_t i);

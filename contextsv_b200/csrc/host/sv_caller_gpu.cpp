@@ -8,6 +8,7 @@
 #include <htslib/sam.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "contextsv_b200.h"
 #include "gpu_context.h"
@@ -16,12 +17,14 @@
 void SVCaller::findCIGARSVs(samFile* fp_in, hts_idx_t* idx, bam_hdr_t* bamHdr, const std::string& region, std::vector<SVCall>& sv_calls,
                             const std::vector<uint32_t>& pos_depth_map)
 {
+    csvhost::StatTimer st_all(csvhost::STAT_CIGAR, 1);
+    csvhost::warm_up_async();
     bam1_t* bam1 = bam_init1();
     if (!bam1) { printError("ERROR: failed to initialize BAM record"); return; }
     hts_itr_t* itr = sam_itr_querys(idx, bamHdr, region.c_str());
     if (!itr) { bam_destroy1(bam1); printError("ERROR: failed to query region " + region); return; }
     const uint32_t map_size = (uint32_t)pos_depth_map.size();       // only the size of the depth map is consulted (sv_caller.cpp:602)
-    csv_ctx* ctx = csvhost::thread_context();
+    csv_ctx* ctx = nullptr;                                         // created at the first flush
     const uint64_t max_ops = csvhost::max_ops_per_batch();
     std::vector<SVCall> found;
     std::vector<std::pair<uint64_t, uint32_t>> seq;                 // insertion order of found[i]: (record, op)
@@ -37,6 +40,8 @@ void SVCaller::findCIGARSVs(samFile* fp_in, hts_idx_t* idx, bam_hdr_t* bamHdr, c
         const csv_region reg = {reads.tid[0], 0u, map_size, map_size};
         const csv_reads view = reads.view();
         uint64_t n = 0, cap = std::max<uint64_t>(start.size(), 1u << 16);
+        if (!ctx) ctx = csvhost::thread_context();
+        csvhost::StatTimer st(csvhost::STAT_CIGAR_GPU, view.n_reads);
         for (;;) {
             start.resize(cap); end.resize(cap); read_idx.resize(cap); op_idx.resize(cap); query_pos.resize(cap); kind.resize(cap);
             csv_sigs out = {start.data(), end.data(), kind.data(), read_idx.data(), op_idx.data(), query_pos.data()};
@@ -70,9 +75,17 @@ void SVCaller::findCIGARSVs(samFile* fp_in, hts_idx_t* idx, bam_hdr_t* bamHdr, c
         read_base += reads.size();
         reads.clear();
     };
-    while (readNextAlignment(fp_in, itr, bam1) >= 0) {
-        if (reads.ops() + reads.size() + bam1->core.n_cigar + 1 > max_ops && reads.size() > 0) flush();   // ops + records: a batch counts both
-        reads.append(bam1, true);
+    // the depth pass has usually packed this contig already (packed_reads.h): no second decode
+    const int whole_tid = sam_hdr_name2tid(bamHdr, region.c_str());
+    std::unique_ptr<csvhost::PackedReads> cached = whole_tid >= 0 ? csvhost::cache_take(csvhost::file_name(fp_in), whole_tid) : nullptr;
+    if (cached && cached->ops() + cached->size() <= max_ops) {
+        reads = std::move(*cached);
+        csvhost::stat_add(csvhost::STAT_CACHE_HIT, 0.0, reads.size());
+    } else {
+        while (readNextAlignment(fp_in, itr, bam1) >= 0) {
+            if (reads.ops() + reads.size() + bam1->core.n_cigar + 1 > max_ops && reads.size() > 0) flush();   // ops + records: a batch counts both
+            reads.append(bam1, true);
+        }
     }
     hts_itr_destroy(itr);
     bam_destroy1(bam1);

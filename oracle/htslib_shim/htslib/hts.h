@@ -23,6 +23,8 @@ typedef struct htsFile htsFile;       /* opaque: defined in shim.cpp */
 typedef struct hts_idx_t hts_idx_t;   /* opaque */
 typedef struct hts_itr_t hts_itr_t;   /* opaque */
 
+#define CSVSHIM_HTSLIB 1               /* lets code written for htslib know its htsFile is opaque here */
+const char* hts_get_fn(htsFile* fp);   /* path the file was opened with (htsFile::fn in htslib) */
 int hts_set_threads(htsFile* fp, int n);
 void hts_idx_destroy(hts_idx_t* idx);
 void hts_itr_destroy(hts_itr_t* itr);

@@ -287,6 +287,7 @@ int sam_close(samFile* fp)
 }
 
 int hts_set_threads(htsFile*, int) { return 0; }
+const char* hts_get_fn(htsFile* fp) { return fp ? fp->path.c_str() : nullptr; }
 
 sam_hdr_t* sam_hdr_read(samFile* fp)
 {

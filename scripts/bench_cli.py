@@ -28,6 +28,8 @@ def run(exe, d, out, threads, env=None):
     t0 = time.perf_counter()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, **(env or {})))
     dt = time.perf_counter() - t0
+    if env:
+        sys.stderr.write("".join(l + "\n" for l in p.stdout.splitlines() if "[contextsv_b200]" in l or "lapsed" in l or "ime" in l.split(":")[0][-6:]))
     if p.returncode != 0 or "ContextSV finished successfully!" not in p.stdout:
         sys.stderr.write(p.stdout[-3000:])
         raise SystemExit("CLI failed: " + exe)
@@ -54,7 +56,7 @@ def main():
                "bam_bytes": os.path.getsize(d + "/x.bam"), "threads": a.threads, "generation_s": round(t_gen, 1)}
         t_ref, t_gpu, vcf_ref, vcf_gpu = [], [], None, None
         for rep in range(a.reps):
-            dt, vcf_gpu = run(os.path.join(REF_DIR, "contextsv_gpu"), d, d + "/out_gpu", a.threads); t_gpu.append(dt)
+            dt, vcf_gpu = run(os.path.join(REF_DIR, "contextsv_gpu"), d, d + "/out_gpu", a.threads, {"CONTEXTSV_B200_STATS": "1"} if rep == 0 else None); t_gpu.append(dt)
             dt, vcf_ref = run(os.path.join(REF_DIR, "contextsv_ref"), d, d + "/out_ref", a.threads); t_ref.append(dt)
         res.update({"contextsv_ref_s": [round(x, 2) for x in t_ref], "contextsv_gpu_s": [round(x, 2) for x in t_gpu],
                     "vcf_identical": vcf_ref == vcf_gpu, "vcf_records": len([l for l in vcf_ref if not l.startswith("#")]),
