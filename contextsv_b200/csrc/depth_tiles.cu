@@ -149,27 +149,40 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
                                                          uint32_t* scalars, const uint32_t* bounds, const unsigned long long* __restrict__ part,
                                                          unsigned long long* pmax)
 {
+    // Global loads and stores are striped (lane-contiguous, one 256-byte row per warp and instruction); the scan wants
+    // kPmItems consecutive records per thread.  The tile changes hands in shared memory, rows padded by one word per
+    // kPmItems so that the blocked accesses spread over the banks.
+    __shared__ unsigned long long s_v[kPmTile + kPmTile / kPmItems];
     __shared__ unsigned long long s_w[kPmThreads / 32];
     const uint32_t kb = bounds[0], n = bounds[1] - kb;
     meta += kb; ref_end += kb; pmax += kb;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
-        // blocked arrangement: thread owns kPmItems consecutive records
-        const uint64_t k0 = (uint64_t)t * kPmTile + (uint64_t)threadIdx.x * kPmItems;
-        unsigned long long v[kPmItems], run = 0;
+        const uint64_t base = (uint64_t)t * kPmTile;
+        bool unsorted = false;
 #pragma unroll
         for (int j = 0; j < kPmItems; j++) {
-            v[j] = (k0 + j < n) ? pm_value(meta, ref_end, (uint32_t)(k0 + j)) : 0ull;
-            // coordinate order check rides along: (tid, pos0 + 1) must not decrease (also across chunk borders)
-            if (k0 + j < n && kb + k0 + j > 0) {
-                if (meta[(long long)(k0 + j) - 1] > meta[k0 + j]) scalars[SC_UNSORTED] = 1;
+            const uint32_t i = j * kPmThreads + threadIdx.x;
+            const uint64_t k = base + i;
+            unsigned long long v = 0ull;
+            if (k < n) {
+                const unsigned long long key = meta[k];
+                v = (key & 0xffffffff00000000ull) | ref_end[k];
+                // coordinate order check rides along: (tid, pos0 + 1) must not decrease (also across chunk borders)
+                if (kb + k > 0 && meta[(long long)k - 1] > key) unsorted = true;
             }
-            run = umax64(run, v[j]);
+            s_v[i + i / kPmItems] = v;
         }
+        if (unsorted) scalars[SC_UNSORTED] = 1;
+        __syncthreads();
+        // blocked arrangement: thread owns kPmItems consecutive records
+        const uint32_t o = threadIdx.x * (kPmItems + 1);
+        unsigned long long v[kPmItems], run = 0;
+#pragma unroll
+        for (int j = 0; j < kPmItems; j++) { v[j] = s_v[o + j]; run = umax64(run, v[j]); }
         unsigned long long inc = run;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { unsigned long long x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc = umax64(inc, x); }
-        __syncthreads();
         if (lane == 31) s_w[warp] = inc;
         __syncthreads();
         unsigned long long pre = part[t];
@@ -178,7 +191,14 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
         if (lane == 0) excl = 0;
         pre = umax64(pre, excl);
 #pragma unroll
-        for (int j = 0; j < kPmItems; j++) { pre = umax64(pre, v[j]); if (k0 + j < n) pmax[k0 + j] = pre; }
+        for (int j = 0; j < kPmItems; j++) { pre = umax64(pre, v[j]); s_v[o + j] = pre; }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPmItems; j++) {
+            const uint32_t i = j * kPmThreads + threadIdx.x;
+            if (base + i < n) pmax[base + i] = s_v[i + i / kPmItems];
+        }
+        __syncthreads();                                        // s_v and s_w are rewritten by the next tile
     }
 }
 
@@ -212,7 +232,15 @@ __global__ void k_tile_ranges(const uint4* __restrict__ tile_desc, uint32_t t_be
         const uint4 d = tile_desc[t];
         const unsigned long long key_lo = ((unsigned long long)d.w << 32) | (unsigned long long)d.z;           // (tid, T0)
         const uint32_t r_hi = tile_ev[t].y;
+        // first record of [kb, r_hi) with pmax > key_lo.  It lies a few dozen records below r_hi (the records that overlap
+        // one tile), so gallop down from r_hi before bisecting: ~12 dependent loads instead of 23 over 6 M records.
         uint32_t lo = kb < r_hi ? kb : r_hi, hi = r_hi;
+        for (uint32_t step = 64; lo < hi; step <<= 2) {
+            const uint32_t probe = hi - lo > step ? hi - step : lo;
+            if (pmax[probe] <= key_lo) { lo = probe + 1; break; }
+            hi = probe;                                          // pmax[probe] > key_lo: the answer is at or below probe
+            if (probe == lo) break;
+        }
         while (lo < hi) {
             const uint32_t mid = lo + ((hi - lo) >> 1);
             if (pmax[mid] <= key_lo) lo = mid + 1; else hi = mid;

@@ -170,7 +170,11 @@ int fetch_depth_segments(csv_ctx* ctx, const std::vector<FetchSeg>& segs)
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
+    try {
+        for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
+    } catch (...) {                                                // out of threads: go on with the ones that started
+    }
+    if (pool.empty()) return fetch_plain(ctx, segs);               // nothing is in flight yet
 
     cudaError_t err = cudaSuccess;
     const uint32_t grid_cap = (uint32_t)ctx->sm_count * 8;

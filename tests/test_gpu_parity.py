@@ -246,6 +246,9 @@ def test_narrow_depth_fetch(oracle):
         assert after[0] > before[0]
         if slots <= 4:
             assert after[1] > before[1], "the pile-up chunks must have overflowed the exception list"
+    for bad in (dict(chunk_positions=100), dict(chunk_positions=513), dict(chunk_positions=1 << 29), dict(exception_slots=1 << 25)):
+        with pytest.raises(api.CsvError):
+            c.set_fetch(**bad)
     # the one-shot entry point takes the same path
     c.set_fetch(threads=4, chunk_positions=2048, exception_slots=16, min_positions=0)
     rs, keep = reads_struct(r)
