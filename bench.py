@@ -270,6 +270,9 @@ def main_ours(args):
     batch = api.Batch(ctx, reads, regions)
 
     def step_resident():
+        if args.depth_only:          # diagnostic: the depth stages without the signature side stream beside them
+            batch.scan(want_depth=True, want_sigs=False)
+            return
         batch.scan(want_depth=True, want_sigs=True)
         batch.sigs_dbscan1d(DB_EPS, DB_MIN_PTS, fetch=False)
 
@@ -281,7 +284,7 @@ def main_ours(args):
     for _ in range(args.warmup):
         step_resident()
     ctx.sync()
-    n_sig = batch.sigs_count()
+    n_sig = 0 if args.depth_only else batch.sigs_count()
     ctx.profile_read(reset=True)
     ctx.profile_enable(True)
     barrier()
@@ -497,6 +500,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--depth-only", action="store_true", help="diagnostic: resident step without signatures / DBSCAN1D (never a reported number)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3        # timing rule: at least 3 warm-up steps
