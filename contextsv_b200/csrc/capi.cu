@@ -130,10 +130,12 @@ int csv_ctx_create(int device, csv_ctx** out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (getenv("CSV_CHUNKS")) ctx->pipe_chunks = std::max(1, atoi(getenv("CSV_CHUNKS")));
+    if (getenv("CSV_SIDE_GRID")) ctx->side_grid = std::max(0, atoi(getenv("CSV_SIDE_GRID")));
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     // the signature kernels are many and tiny: with the highest priority their CTAs take the first slot a tile CTA frees
     int prio_lo = 0, prio_hi = 0;
     CSV_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("CSV_SIDE_PRIO") && atoi(getenv("CSV_SIDE_PRIO")) == 0) prio_hi = prio_lo;     // tuning knob: side stream at normal priority
     CSV_CUDA(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->tile_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->main_stream;

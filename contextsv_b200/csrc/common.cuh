@@ -135,6 +135,7 @@ struct csv_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tile_join = nullptr;
     std::vector<cudaEvent_t> ev_chunk;  // walk of chunk c finished (main stream)
     bool side_busy = false, tile_busy = false;
+    int side_grid = 0;                  // CTAs per SM the side-stream kernels may take beside the tiles (0 = each kernel's own default)
     int pipe_chunks = 1;                // batches uploaded from now on are scanned in up to this many pipelined chunks of contigs
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
@@ -177,6 +178,13 @@ struct TileScope {                      // ... to the tile stream
 // Depth slices device -> host (fetch.cu).  Blocks until every segment is in host memory.
 int fetch_depth_segments(csv_ctx* ctx, const std::vector<FetchSeg>& segs);
 void fetch_release(csv_ctx* ctx);
+// Grid multiplier (CTAs per SM) of a grid-stride / ticket kernel.  On the side stream, beside the HBM-bound tile kernel,
+// every CTA slot a tiny signature kernel holds is taken from the tiles: the context may cap the multiplier there.
+inline uint32_t grid_mult(const csv_ctx* ctx, uint32_t dflt)
+{
+    if (ctx->stream == ctx->side_stream && ctx->side_grid > 0 && (uint32_t)ctx->side_grid < dflt) return (uint32_t)ctx->side_grid;
+    return dflt;
+}
 // RAII stage timer: records an event pair around a pipeline stage when profiling is on.
 struct StageTimer {
     csv_ctx* ctx; int stage; cudaEvent_t e1 = nullptr;

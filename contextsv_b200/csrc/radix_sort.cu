@@ -184,7 +184,7 @@ int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32
     if (tiles == 0) tiles = 1;
     CSV_TRY(ensure_status(ctx, tiles * 256));
     uint32_t grid_h = (uint32_t)((n_upper + 255) / 256);
-    if (grid_h > (uint32_t)ctx->sm_count * 8) grid_h = ctx->sm_count * 8;
+    if (grid_h > (uint32_t)ctx->sm_count * grid_mult(ctx, 8)) grid_h = ctx->sm_count * grid_mult(ctx, 8);
     if (grid_h == 0) grid_h = 1;
     k_sort_hist<<<grid_h, 256, 0, ctx->stream>>>(bufs.hi, bufs.lo, n_dev, n_upper, digit_mask, st);
     k_sort_bases<<<1, 256, 0, ctx->stream>>>(n_dev, n_upper, digit_mask, st);
@@ -193,7 +193,8 @@ int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32
     P.hi[0] = bufs.hi; P.hi[1] = bufs.hi2; P.lo[0] = bufs.lo; P.lo[1] = bufs.lo2; P.val[0] = bufs.val; P.val[1] = bufs.val2;
     P.n_dev = n_dev; P.n_host = n_upper; P.st = st;
     P.status = ctx->scan_status.as<unsigned long long>();
-    uint32_t grid = (uint32_t)(tiles < (uint64_t)ctx->sm_count * 6 ? tiles : (uint64_t)ctx->sm_count * 6);
+    const uint64_t pass_cap = (uint64_t)ctx->sm_count * grid_mult(ctx, 6);
+    uint32_t grid = (uint32_t)(tiles < pass_cap ? tiles : pass_cap);
     for (int d = 0; d < n_digits; d++) {
         if (!((digit_mask >> d) & 1u)) continue;
         P.digit = d;

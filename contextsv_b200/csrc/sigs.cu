@@ -120,7 +120,7 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
 {
     const uint32_t cap = (uint32_t)b->sig_cap;
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
-    uint32_t grid = ctx->sm_count * 4;
+    uint32_t grid = ctx->sm_count * grid_mult(ctx, 4);
     k_sig_clamp<<<1, 1, 0, ctx->stream>>>(scalars, cap);
     k_sig_iota<<<grid, 256, 0, ctx->stream>>>(b->d_sig_payload.as<uint32_t>(), scalars);
     ctx->launches += 2;
