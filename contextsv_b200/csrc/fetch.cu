@@ -19,7 +19,6 @@
 #include "batch.cuh"
 
 #include <algorithm>
-#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
