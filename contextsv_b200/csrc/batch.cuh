@@ -100,6 +100,8 @@ int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32
 int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, uint64_t n_upper, const uint32_t* n_dev,
                     uint32_t n_seg, double eps, int min_pts, int32_t* d_labels, int32_t* d_n_clusters /* [n_seg] or null */,
                     bool value_sorted = false /* points of one segment come in ascending order */);
+// one fit of at most kDbSmallMax host-resident points, eps >= 0: one launch (dbscan_small.h)
+int dbscan1d_small(csv_ctx* ctx, const int32_t* pts, uint32_t n, double eps, int min_pts, int32_t* labels_out, int32_t* n_clusters_out);
 // DBSCAN::fit (2-D, reciprocal-overlap distance) on device-resident intervals
 int dbscan2d_device(csv_ctx* ctx, const uint32_t* d_start, const uint32_t* d_end, uint64_t n, double eps, int min_pts, int32_t* d_labels);
 }  // namespace csv

@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" layer (include/contextsv_b200.h): contexts, uploads,
 // the scan pipeline, result fetches and the one-shot host-to-host wrappers.
 #include "batch.cuh"
+#include "dbscan_small.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -131,6 +132,7 @@ int csv_ctx_create(int device, csv_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (getenv("CSV_CHUNKS")) ctx->pipe_chunks = std::max(1, atoi(getenv("CSV_CHUNKS")));
     if (getenv("CSV_SIDE_GRID")) ctx->side_grid = std::max(0, atoi(getenv("CSV_SIDE_GRID")));
+    if (getenv("CSV_DB_SMALL")) ctx->db_small = atoi(getenv("CSV_DB_SMALL")) != 0;
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     // the signature kernels are many and tiny: with the highest priority their CTAs take the first slot a tile CTA frees
     int prio_lo = 0, prio_hi = 0;
@@ -173,6 +175,7 @@ void csv_ctx_destroy(csv_ctx* ctx)
     for (auto& b : ctx->db) b.release();
     for (auto& b : ctx->db2) b.release();
     if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
+    if (ctx->pinned_db) cudaFreeHost(ctx->pinned_db);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->side_stream);
@@ -655,6 +658,10 @@ int csv_dbscan1d_seg(csv_ctx* ctx, const int32_t* pts, const uint32_t* seg_id, u
 
 int csv_dbscan1d(csv_ctx* ctx, const int32_t* pts, uint64_t n, double eps, int min_pts, int32_t* labels_out, int32_t* n_clusters_out)
 {
+    if (ctx && ctx->db_small && n > 0 && n <= (uint64_t)kDbSmallMax && pts && labels_out && eps >= 0.0) {
+        CSV_CUDA(cudaSetDevice(ctx->device));
+        return dbscan1d_small(ctx, pts, (uint32_t)n, eps, min_pts, labels_out, n_clusters_out);
+    }
     return csv_dbscan1d_seg(ctx, pts, nullptr, n, 1, eps, min_pts, labels_out, n_clusters_out);
 }
 

@@ -147,6 +147,9 @@ struct csv_ctx {
     csv::DevBuf db[16];                 // DBSCAN scratch
     csv::DevBuf db2[14];                // 2-D DBSCAN scratch
     void* pinned_small = nullptr;       // 4 KB pinned staging for tiny D2H reads
+    void* pinned_db = nullptr;          // mapped pinned buffer of the one-launch DBSCAN1D path (points | labels | cluster count)
+    void* pinned_db_dev = nullptr;      // ... as the device sees it
+    bool db_small = false;              // csv_dbscan1d takes the one-launch path for <= kDbSmallMax points (CSV_DB_SMALL=1)
     int sm_count = csv::kSMs;
     csv::DevPool pool;                  // parked batch buffers
     bool profile = false;

@@ -20,9 +20,45 @@
 // atomicMin of input indices -> radix sort of runs by (segment, min index) ->
 // cluster ids -> labels.
 #include "batch.cuh"
+#include "dbscan_small.h"
 #include "scan.cuh"
 
 namespace csv {
+
+// One small fit in one launch: a thread per point, the phases of dbscan_small.h, a block barrier between them.
+__global__ void __launch_bounds__(kDbSmallMax) k_db_small(const int32_t* pts, uint32_t n, long long E, int min_pts, int32_t* labels, int32_t* n_clusters)
+{
+    __shared__ DbSmall S;
+    const uint32_t t = threadIdx.x;
+#pragma unroll 1
+    for (int ph = 0; ph < kDbSmallPhases; ph++) {
+        if (t < n) db_small_phase(S, ph, t, n, E, min_pts, pts, labels, n_clusters);
+        __syncthreads();
+    }
+}
+
+// Host side of the small path: points and labels travel through the context's mapped pinned buffer (no copy engine, no
+// device allocation): one launch and one stream synchronisation per fit.
+int dbscan1d_small(csv_ctx* ctx, const int32_t* pts, uint32_t n, double eps, int min_pts, int32_t* labels_out, int32_t* n_clusters_out)
+{
+    if (!ctx->pinned_db) {
+        CSV_CUDA(cudaHostAlloc(&ctx->pinned_db, 2 * kDbSmallMax * sizeof(int32_t) + 64, cudaHostAllocMapped));
+        CSV_CUDA(cudaHostGetDevicePointer(&ctx->pinned_db_dev, ctx->pinned_db, 0));
+    }
+    int32_t* h_in = (int32_t*)ctx->pinned_db;
+    int32_t* h_lab = h_in + kDbSmallMax;
+    int32_t* h_nc = h_lab + kDbSmallMax;
+    int32_t* d_in = (int32_t*)ctx->pinned_db_dev;
+    memcpy(h_in, pts, (size_t)n * sizeof(int32_t));
+    const long long E = eps >= 4294967296.0 ? 4294967296ll : (long long)eps;      // floor for eps >= 0, as in the general path
+    k_db_small<<<1, (n + 31u) & ~31u, 0, ctx->stream>>>(d_in, n, E, min_pts, d_in + kDbSmallMax, d_in + 2 * kDbSmallMax);
+    ctx->launches++;
+    CSV_CUDA(cudaGetLastError());
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(labels_out, h_lab, (size_t)n * sizeof(int32_t));
+    if (n_clusters_out) *n_clusters_out = *h_nc;
+    return CSV_OK;
+}
 
 struct DbParams {
     const int32_t* pts;

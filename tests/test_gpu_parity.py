@@ -444,6 +444,63 @@ def test_dbscan2d_golden_fuzz_and_large(ctx, oracle):
         assert np.array_equal(db.getClusters(), oracle.dbscan2d(st, en, eps, mp)), (n, eps, mp)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("CSV_TEST_DB_SMALL") != "1",
+                    reason="opt-in path (CSV_DB_SMALL=1), not yet verified on a GPU: run with CSV_TEST_DB_SMALL=1")
+def test_dbscan1d_one_launch_small_path(oracle):
+    """csv_dbscan1d with CSV_DB_SMALL=1: fits of at most 1024 points run as ONE launch (k_db_small, points and labels
+    through mapped pinned memory) instead of the general pipeline's ~20 -- what the split-read pass's per-cluster fits
+    (sv_caller.cpp:270) need.  Same labels as the golden vectors and the oracle; larger inputs and eps < 0 still take
+    the general path."""
+    import os
+    import time
+    old = os.environ.get("CSV_DB_SMALL")
+    os.environ["CSV_DB_SMALL"] = "1"
+    try:
+        c = api.Context(0)
+    finally:
+        if old is None:
+            del os.environ["CSV_DB_SMALL"]
+        else:
+            os.environ["CSV_DB_SMALL"] = old
+    n_small = 0
+    for i, pts, eps, mp, labels, largest in util.golden_db_cases():
+        l0 = c.launches
+        db = api.DBSCAN1D(eps, mp, c)
+        db.fit(pts)
+        assert np.array_equal(db.getClusters(), labels), "case %d eps=%g minPts=%d" % (i, eps, mp)
+        if 0 < len(pts) <= 1024 and eps >= 0:
+            assert c.launches - l0 == 1
+            n_small += 1
+    assert n_small >= 80
+    rng = np.random.default_rng(31)
+    for trial in range(300):
+        n = int(rng.choice([1, 2, 3, 5, 17, 33, 64, 200, 1000, 1024, 1025, 3000]))
+        span = int(rng.choice([5, 50, 1000, 100000]))
+        pts = rng.integers(-span, span, n).astype(np.int32)
+        if trial % 7 == 0:
+            pts[: n // 2] = pts[0]
+        if trial % 11 == 0:
+            pts[0] = np.iinfo(np.int32).max; pts[-1] = np.iinfo(np.int32).min
+        eps = float(rng.choice([0, 0.5, 1, 2.9, 10, 100, 1e5, 5e9, -1.0]))
+        mp = int(rng.choice([-1, 0, 1, 2, 3, 5, 10, 2000]))
+        lab = np.zeros(n, np.int32); nc = np.zeros(1, np.int32)
+        l0 = c.launches
+        check(lib().csv_dbscan1d(c.h, ptr(pts), n, eps, mp, ptr(lab), ptr(nc)))
+        want = oracle.dbscan1d(pts, eps, mp, fast=n > 1024)
+        assert np.array_equal(lab, want), "trial %d n=%d eps=%g minPts=%d" % (trial, n, eps, mp)
+        if eps >= 0:
+            assert (c.launches - l0 == 1) == (n <= 1024)
+            assert int(nc[0]) == (int(want.max()) + 1 if (want >= 0).any() else 0)
+    pts = rng.integers(0, 5000, 40).astype(np.int32)
+    lab = np.zeros(40, np.int32)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        lib().csv_dbscan1d(c.h, ptr(pts), 40, 100.0, 5, ptr(lab), None)
+    us_small = 1e6 * (time.perf_counter() - t0) / 2000
+    print("one-launch DBSCAN1D fit of 40 points: %.1f us per call" % us_small)
+    c.close()
+
+
 def test_dbscan1d_segments(ctx, oracle):
     rng = np.random.default_rng(4)
     n, n_seg = 5000, 7
