@@ -149,7 +149,7 @@ struct csv_ctx {
     void* pinned_small = nullptr;       // 4 KB pinned staging for tiny D2H reads
     void* pinned_db = nullptr;          // mapped pinned buffer of the one-launch DBSCAN1D path (points | labels | cluster count)
     void* pinned_db_dev = nullptr;      // ... as the device sees it
-    bool db_small = false;              // csv_dbscan1d takes the one-launch path for <= kDbSmallMax points (CSV_DB_SMALL=1)
+    bool db_small = true;               // csv_dbscan1d takes the one-launch path for <= kDbSmallMax points (CSV_DB_SMALL=0 turns it off)
     int sm_count = csv::kSMs;
     csv::DevPool pool;                  // parked batch buffers
     bool profile = false;

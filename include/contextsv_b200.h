@@ -187,7 +187,9 @@ int csv_cigar_scan(csv_ctx* ctx, const csv_reads* reads, const csv_region* regio
                    uint32_t min_len, uint8_t min_mapq, csv_sigs* out, uint64_t cap, uint64_t* n_out);
 
 /* DBSCAN1D::fit + getClusters (dbscan1d.h:13-17).  labels: cluster id >= 0,
- * -2 noise, exactly as the reference assigns them.  n_clusters_out may be NULL. */
+ * -2 noise, exactly as the reference assigns them.  n_clusters_out may be NULL.
+ * Inputs of at most 1024 points (eps >= 0) are one kernel launch -- the reference fits one small set per cluster of
+ * split alignments (sv_caller.cpp:270); the environment variable CSV_DB_SMALL=0 sends them through the general path. */
 int csv_dbscan1d(csv_ctx* ctx, const int32_t* pts, uint64_t n, double eps, int min_pts,
                  int32_t* labels_out, int32_t* n_clusters_out);
 

@@ -444,10 +444,8 @@ def test_dbscan2d_golden_fuzz_and_large(ctx, oracle):
         assert np.array_equal(db.getClusters(), oracle.dbscan2d(st, en, eps, mp)), (n, eps, mp)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CSV_TEST_DB_SMALL") != "1",
-                    reason="opt-in path (CSV_DB_SMALL=1), not yet verified on a GPU: run with CSV_TEST_DB_SMALL=1")
 def test_dbscan1d_one_launch_small_path(oracle):
-    """csv_dbscan1d with CSV_DB_SMALL=1: fits of at most 1024 points run as ONE launch (k_db_small, points and labels
+    """csv_dbscan1d (default; CSV_DB_SMALL=0 turns it off): fits of at most 1024 points run as ONE launch (k_db_small, points and labels
     through mapped pinned memory) instead of the general pipeline's ~20 -- what the split-read pass's per-cluster fits
     (sv_caller.cpp:270) need.  Same labels as the golden vectors and the oracle; larger inputs and eps < 0 still take
     the general path."""
