@@ -148,11 +148,11 @@ def reference_sample(cores, seed):
     return r, clen
 
 
-def run_reference_steps(r, clen, steps, warmup):
+def run_reference_steps(r, clen, steps, warmup, o0=False):
     from oracle.oracle_py import Oracle, Reference, ref_available
     import concurrent.futures as cf
     kind = "reference" if ref_available() else "port"
-    eng = Reference() if kind == "reference" else Oracle()
+    eng = Reference(o0=o0) if kind == "reference" else Oracle()
     cores = len(clen)
     subs = []
     ends = shard.ref_end(r)
@@ -210,6 +210,92 @@ def main_reference(args):
 
 # ------------------------------------------------------------------------------------------ our arm
 
+def kernel_source_sha():
+    """Hash of what the dominant kernel is compiled from: profiles/r2_traffic.json is only quoted for the build it was
+    captured on (scripts/make_traffic.py stores the same hash)."""
+    import hashlib
+    from contextsv_b200 import build as _b
+    h = hashlib.sha256()
+    for f in ("depth_tiles.cu", "common.cuh", "batch.cuh", "scan.cuh"):
+        h.update(open(os.path.join(_b.CSRC, f), "rb").read())
+    h.update(" ".join(_b.NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+class ShmBoard:
+    """Host-side gather of the shards' results (the path has no collective: SURVEY 8e).  Every rank owns one
+    shared-memory segment on the box and fetches its results straight into it; rank 0 maps all of them and merges."""
+    U_CAP = 8192          # signature starts per shard that another shard's depth slice has to answer
+
+    def __init__(self, tag, rank, world, n_regions_max, cap_sig):
+        self.rank, self.world, self.R, self.cap = rank, world, n_regions_max, int(cap_sig)
+        self.layout, off = {}, 0
+
+        def field(name, dtype, n):
+            nonlocal off
+            off = (off + 63) & ~63
+            self.layout[name] = (off, np.dtype(dtype), int(n))
+            off += np.dtype(dtype).itemsize * int(n)
+        field("hdr", np.int64, 16); field("region_off", np.uint64, self.R + 1); field("sums", np.uint64, self.R); field("nzs", np.uint32, self.R)
+        for k in ("start", "end", "read_idx", "op_idx", "query_pos", "depth"):
+            field(k, np.uint32, self.cap)
+        field("label", np.int32, self.cap); field("kind", np.uint8, self.cap)
+        field("u_tid", np.int32, self.U_CAP); field("u_pos", np.uint32, self.U_CAP); field("u_idx", np.uint32, self.U_CAP)
+        field("answers", np.uint32, self.U_CAP * world)
+        self.size = off + 64
+        d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        self.path = lambda r: os.path.join(d, "csvb_%s_%d" % (tag, r))
+        self.segs = {rank: np.memmap(self.path(rank), dtype=np.uint8, mode="w+", shape=(self.size,))}
+
+    def attach_all(self):
+        for r in range(self.world):
+            if r not in self.segs:
+                self.segs[r] = np.memmap(self.path(r), dtype=np.uint8, mode="r+", shape=(self.size,))
+
+    def view(self, r, name):
+        off, dt, n = self.layout[name]
+        return self.segs[r][off:off + dt.itemsize * n].view(dt)
+
+    def close(self):
+        self.segs.clear()
+        try:
+            os.unlink(self.path(self.rank))
+        except OSError:
+            pass
+
+
+def digest_results(merged, n_contigs):
+    """(signature digest, label digest, depth-at-start digest) over the per-contig vectors in contig order."""
+    import hashlib
+    hs, hl, hd = hashlib.blake2b(digest_size=8), hashlib.blake2b(digest_size=8), hashlib.blake2b(digest_size=8)
+    for t in range(n_contigs):
+        m = merged.get(t)
+        if m is None:
+            continue
+        for k, dt in (("start", np.uint32), ("end", np.uint32), ("kind", np.uint8), ("read_idx", np.int64), ("op_idx", np.uint32), ("query_pos", np.uint32)):
+            hs.update(np.ascontiguousarray(m[k], dt).tobytes())
+        hl.update(np.ascontiguousarray(m["label"], np.int32).tobytes())
+        hd.update(np.ascontiguousarray(m["depth"], np.uint32).tobytes())
+    return hs.hexdigest(), hl.hexdigest(), hd.hexdigest()
+
+
+def finalize_merge(parts, ctx, api):
+    """Host merge of the shards' results: per-contig signature vectors in the reference's order; contigs
+    that were cut get their DBSCAN1D fits redone over the merged vector (a fit never spans contigs, but it does span a
+    cut), one csv_dbscan1d_seg call for all of them."""
+    merged = shard.merge_signatures(parts, extra=("label", "depth"))
+    split = [t for t, m in sorted(merged.items()) if m["n_parts"] > 1 and len(m["start"])]
+    if split:
+        pts = np.concatenate([merged[t]["start"] for t in split]).astype(np.int32)
+        seg = np.concatenate([2 * j + (merged[t]["kind"] != 1).astype(np.uint32) for j, t in enumerate(split)]).astype(np.uint32)
+        lab, _ = api.dbscan1d_segments(pts, seg, 2 * len(split), DB_EPS, DB_MIN_PTS, ctx)
+        o = 0
+        for t in split:
+            n = len(merged[t]["start"])
+            merged[t]["label"] = lab[o:o + n]; o += n
+    return merged, len(split)
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -222,6 +308,8 @@ def main_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    strong = scaling == "strong" and world > 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,42 +317,45 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+    sum_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x
 
     ctx = api.Context(local_rank)
     contig_len, n_sv = workload_contigs(args.workload)
+    n_contigs = len(contig_len)
     t_gen = time.perf_counter()
-    if args.scaling == "weak" or world == 1:
-        # every rank scans its own sample of the workload (different seed per rank)
+    full = None
+    if not strong:
+        # N == 1, or --scaling weak: every rank scans its own sample of the workload (different seed per rank)
         reads = synth.generate(contig_len, alloc=_capi.pinned_empty, seed=args.seed + rank, n_sv=n_sv, **SYNTH_KW.get(args.workload, {}))
         regions = api.whole_contig_regions(contig_len)
+        read_base, plan = 0, [regions]
     else:
-        # config 4: one genome, region-sharded by cumulative length, halo reads included
+        # BASELINE configs[3]: ONE genome (same seed on every rank), cut into `world` region shards of equal cost
+        # (positions + c * CIGAR ops), every shard with the halo reads that start before it and reach into it
         full = synth.generate(contig_len, seed=args.seed, n_sv=n_sv, **SYNTH_KW.get(args.workload, {}))
-        regions = shard.plan_regions(contig_len, world)[rank]
-        sub, _ = shard.select_reads(full, regions)
+        plan = shard.plan_regions(contig_len, world, full)
+        regions = plan[rank]
+        sub, read_base = shard.select_reads(full, regions)
         reads = {}
         for k, v in sub.items():
             if isinstance(v, np.ndarray):
                 p = _capi.pinned_empty(len(v), v.dtype); p[:] = v; reads[k] = p
             else:
                 reads[k] = v
-        del full, sub
+        del sub
+        if rank != 0:
+            full = None
     t_gen = time.perf_counter() - t_gen
     n_reads, n_ops = int(reads["n_reads"]), int(reads["n_ops"])
     depth_words = sum(e - b for (_, b, e, _) in regions)
+    genome_reads = (sum_over_ranks(n_reads) if not strong else None)
 
     # ---- value: inputs resident in HBM, device time on the library's stream
     batch = api.Batch(ctx, reads, regions)
@@ -285,6 +376,14 @@ def main_ours(args):
         step_resident()
     ctx.sync()
     n_sig = 0 if args.depth_only else batch.sigs_count()
+    own_reads = n_reads
+    if strong:
+        # reads this shard OWNS (halo reads belong to the shard before): they add up to the genome
+        idx = reads["pos0"].astype(np.int64) + 1
+        tid = reads["tid"].astype(np.int64)
+        t0_, b0_ = regions[0][0], regions[0][1]
+        own_reads = int(np.count_nonzero((tid > t0_) | (idx >= b0_))) if n_reads else 0
+        genome_reads = sum_over_ranks(own_reads)
     ctx.profile_read(reset=True)
     ctx.profile_enable(True)
     barrier()
@@ -301,53 +400,120 @@ def main_ours(args):
     ctx.profile_enable(False)
     stages = ctx.profile_read(reset=True)
     ms_max = max_over_ranks(ms)
-    total_reads = sum_over_ranks(n_reads)
-    value = total_reads * args.steps / (ms_max * 1e-3)
+    ms_min = -max_over_ranks(-ms)
+    value = genome_reads * args.steps / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel and of the whole path (algorithmic bytes)
+    # ---- roofline of the dominant kernel and of the whole path (algorithmic bytes); per rank, rank 0's printed
     peak, peak_src = measured_peak_gbs()
-    b_alg = 15 * n_reads + 4 * n_ops + 4 * depth_words + 21 * n_sig + 8 * n_sig
+    b_alg = 15 * n_reads + (4 * n_reads if reads.get("n_gap") is not None else 0) + 4 * n_ops + 4 * depth_words + 21 * n_sig + 8 * n_sig
     tile_ms = stages["k_depth_tiles16"][0] / args.steps  # the dominant kernel alone: CUDA events around its launch(es) on its stream
     tile_bytes = 4 * depth_words
     achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
     path_gbs = b_alg / (ms / args.steps * 1e-3) / 1e9
-    traffic = None          # dram bytes read + written by one launch of the dominant kernel, from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
+    traffic, traffic_note = None, "no capture for this workload / world size"
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tpath) and world == 1:
         tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload and world == 1:
-            traffic = tj["traffic_bytes_per_launch"]
+        if tj.get("workload") != args.workload:
+            traffic_note = "profiles/r2_traffic.json is for workload %s" % tj.get("workload")
+        elif tj.get("kernel_source_sha") != kernel_source_sha():
+            traffic_note = "profiles/r2_traffic.json was captured on other kernel sources (%s): not quoted" % tj.get("kernel_source_sha")
+        else:
+            traffic, traffic_note = tj["traffic_bytes_per_launch"], "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, " + tj.get("capture", "")
     roofline = {
         "bound": "hbm", "kernel": "k_depth_tiles16", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": tile_ms,
-        "path": {"algorithmic_bytes_per_step": b_alg, "achieved": path_gbs, "frac": path_gbs / peak},
+        "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": tile_ms,
+        "path": {"algorithmic_bytes_per_step": b_alg, "achieved": path_gbs, "frac": path_gbs / peak, "note": "this rank's bytes / this rank's step time"},
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
     }
-
-    # ---- e2e: the host-facing calls with host buffers; H2D and D2H inside the timed region
     batch.free()
-    out_depth = []
-    for (_, b, e, _) in regions:
-        try:
-            out_depth.append(_capi.pinned_empty(e - b, np.uint32))
-        except _capi.CsvError:
-            out_depth.append(np.empty(e - b, np.uint32))
 
-    # The depth maps come back through csv_depth_fetch_all: bytes over PCIe + host threads that widen them into the
-    # caller's uint32 arrays (fetch.cu).  The host cores are shared by the ranks of one box.
-    fetch_threads = max(1, min(16, (os.cpu_count() or 1) // max(world, 1) - (2 if world == 1 else 0)))
-    ctx.set_fetch(threads=fetch_threads)
+    # ---- e2e: the host-facing calls with HOST buffers.  One step = H2D of the packed SoA, the scan, DBSCAN1D, and every
+    # result a caller of the reference's interfaces consumes brought to the host: per-region (sum, nonzero) -> mean
+    # coverage, the signature vectors, the labels, and the depth at every signature start (getReadDepth,
+    # sv_caller.cpp:1306) answered from the device-resident map (csv_sigs_depth / csv_depth_at_tid).  Sharded runs add
+    # the host gather (shared memory on the box), the merge and the re-fit of the contigs that were cut.  The 12.4 GB
+    # uint32-per-base map itself stays in HBM (e2e_full_map below measures the step that ships it as well).
+    R_max = int(max_over_ranks(len(regions)))
+    cap_sig = int(max_over_ranks(n_sig)) * 2 + 4096
+    board = None
+    if strong:
+        tag = os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid() if os.environ.get("TORCHELASTIC_RUN_ID") else os.getpid())
+        obj = [tag]
+        dist.broadcast_object_list(obj, src=0)
+        board = ShmBoard(obj[0], rank, world, R_max, cap_sig)
+        barrier()
+        board.attach_all()
+        out = {k: board.view(rank, k) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
+        out_label, out_depth = board.view(rank, "label"), board.view(rank, "depth")
+    else:
+        out = {"start": np.zeros(cap_sig, np.uint32), "end": np.zeros(cap_sig, np.uint32), "kind": np.zeros(cap_sig, np.uint8),
+               "read_idx": np.zeros(cap_sig, np.uint32), "op_idx": np.zeros(cap_sig, np.uint32), "query_pos": np.zeros(cap_sig, np.uint32)}
+        out_label, out_depth = np.zeros(cap_sig, np.int32), np.zeros(cap_sig, np.uint32)
+    region_tid = np.array([t for (t, _, _, _) in regions], np.int32)
 
-    def step_e2e():
-        """One batch: upload everything, scan, fetch everything."""
-        bt = api.Batch(ctx, reads, regions)                       # H2D of the packed SoA
+    def step_e2e(want_checksum=False):
+        bt = api.Batch(ctx, reads, regions)                                        # H2D of the packed SoA
         bt.scan(want_depth=True, want_sigs=True)
-        lab = bt.sigs_dbscan1d(DB_EPS, DB_MIN_PTS)                # D2H labels
+        check(lib().csv_sigs_dbscan1d(ctx.h, bt.h, float(DB_EPS), int(DB_MIN_PTS), ptr(out_label), len(out_label)))   # DBSCAN1D + D2H labels
+        n = bt.sigs_count()
         sums, nzs = bt.depth_stats()
-        bt.depth_all(out_depth)                                   # D2H depth maps (uint32 per base in host memory)
-        sg = bt.sigs()                                            # D2H signatures
+        sg = bt.sigs(out=out, n=n)                                                 # D2H signatures
+        dep = bt.sigs_depth(n=n, out=out_depth)                                    # D2H depth at every signature start
+        cks = bt.depth_checksum() if want_checksum else None
+        sg["label"] = out_label[:n]; sg["depth"] = dep
+        if not strong:
+            bt.free()
+            merged, n_split = finalize_merge([(sg, regions, 0)], ctx, api)
+            return merged, sums, nzs, cks, n_split
+        # sharded: publish, answer the other shards' depth questions, rank 0 merges
+        hdr = board.view(rank, "hdr")
+        un = np.nonzero(dep == 0xffffffff)[0]
+        if len(un) > board.U_CAP:
+            raise SystemExit("bench.py: %d signature starts outside the shard's depth slices (capacity %d)" % (len(un), board.U_CAP))
+        reg_of = np.searchsorted(sg["region_off"], un, side="right") - 1
+        board.view(rank, "u_tid")[:len(un)] = region_tid[reg_of]; board.view(rank, "u_pos")[:len(un)] = sg["start"][un]; board.view(rank, "u_idx")[:len(un)] = un
+        board.view(rank, "region_off")[:len(regions) + 1] = sg["region_off"]
+        board.view(rank, "sums")[:len(regions)] = sums; board.view(rank, "nzs")[:len(regions)] = nzs
+        hdr[0], hdr[1], hdr[2] = n, len(un), len(regions)
+        dist.barrier()
+        for r in range(world):
+            if r == rank:
+                continue
+            nu = int(board.view(r, "hdr")[1])
+            if nu:
+                ans = bt.depth_at_tid(board.view(r, "u_tid")[:nu], board.view(r, "u_pos")[:nu])
+                board.view(rank, "answers")[r * board.U_CAP: r * board.U_CAP + nu] = ans
         bt.free()
-        return len(lab), len(sg["start"]), int(sums.sum()), int(nzs.sum())
+        dist.barrier()
+        if rank != 0:
+            return None, sums, nzs, cks, 0
+        parts = []
+        for r in range(world):
+            h = board.view(r, "hdr"); n_r, nu, nreg = int(h[0]), int(h[1]), int(h[2])
+            d = {k: board.view(r, k)[:n_r] for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos", "label")}
+            dp = board.view(r, "depth")[:n_r]
+            if nu:
+                dp = dp.copy()
+                ui = board.view(r, "u_idx")[:nu]
+                for q in range(world):
+                    if q == r:
+                        continue
+                    a = board.view(q, "answers")[r * board.U_CAP: r * board.U_CAP + nu]
+                    ok = (a != 0xffffffff) & (dp[ui] == 0xffffffff)
+                    dp[ui[ok]] = a[ok]
+            d["depth"] = dp
+            d["region_off"] = board.view(r, "region_off")[:nreg + 1]
+            parts.append((d, plan[r], read_bases[r]))
+        merged, n_split = finalize_merge(parts, ctx, api)
+        return merged, sums, nzs, cks, n_split
+
+    from contextsv_b200._capi import check, lib, ptr
+    read_bases = [read_base]
+    if strong:
+        t = torch.zeros(world, dtype=torch.int64, device="cuda"); t[rank] = read_base
+        dist.all_reduce(t)
+        read_bases = [int(x) for x in t.tolist()]
 
     def timed(step, n_steps):
         barrier()
@@ -360,131 +526,126 @@ def main_ours(args):
         return max_over_ranks(dt), r
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    # one untimed step gives the checksums (and warms the e2e path up)
+    merged, sums, nzs, cks, n_split = step_e2e(want_checksum=True)
+    per_contig = np.zeros(n_contigs, np.int64)
+    for (t_, _, _, _), c in zip(regions, cks.astype(np.int64)):
+        per_contig[t_] += c                                                      # wraps modulo 2^64, like the kernel's sum
+    if world > 1 and strong:
+        tt = torch.from_numpy(per_contig).cuda(); dist.all_reduce(tt); per_contig = tt.cpu().numpy()
+    checksums = None
+    if rank == 0:
+        import hashlib
+        dg = digest_results(merged, n_contigs)
+        checksums = {"depth": hashlib.blake2b(per_contig.tobytes(), digest_size=8).hexdigest(), "signatures": dg[0], "dbscan1d_labels": dg[1], "depth_at_signature_start": dg[2],
+                     "signatures_total": int(sum(len(m["start"]) for m in merged.values())), "contigs_refit_after_merge": n_split}
     if args.skip_e2e:        # profiling runs only (ncu): never used for a reported number
         e2e_steps, dt_max, e2e_value = 0, 0.0, None
     else:
-        for _ in range(min(args.warmup, 2)):
-            step_e2e()
-        st0 = ctx.fetch_stats()
-        dt_max, _ = timed(step_e2e, e2e_steps)
-        st1 = ctx.fetch_stats()
-        narrow_chunks, fallback_chunks = (st1[0] - st0[0]) // e2e_steps, (st1[1] - st0[1]) // e2e_steps     # per step
-        e2e_value = total_reads * e2e_steps / dt_max
-        # the same step with the plain 32-bit DMA of the map (csv_ctx_set_fetch threads = 0), for comparison
-        ctx.set_fetch(threads=0)
         step_e2e()
-        dt_plain, _ = timed(step_e2e, e2e_steps)
-        ctx.set_fetch(threads=fetch_threads)
-        # double-buffered across steps: the SoA of step s + 1 is uploaded (second context, helper thread) while the
-        # maps of step s come back; every step still uploads its own inputs and returns its own results
-        import concurrent.futures as cf
-        ctx2 = api.Context(local_rank)
-        ctx2.set_fetch(threads=fetch_threads)
-        ex = cf.ThreadPoolExecutor(1)
+        dt_max, _ = timed(step_e2e, e2e_steps)
+        e2e_value = genome_reads * e2e_steps / dt_max
 
-        def run_double_buffered(n_steps):
-            lanes = (ctx, ctx2)
-            fut = ex.submit(api.Batch, lanes[0], reads, regions)
-            r = None
-            for s_ in range(n_steps):
-                bt = fut.result()
-                if s_ + 1 < n_steps:
-                    fut = ex.submit(api.Batch, lanes[(s_ + 1) & 1], reads, regions)
-                bt.scan(want_depth=True, want_sigs=True)
-                lab = bt.sigs_dbscan1d(DB_EPS, DB_MIN_PTS)
-                sums, nzs = bt.depth_stats()
-                bt.depth_all(out_depth)
-                sg = bt.sigs()
-                bt.free()
-                r = (len(lab), len(sg["start"]), int(sums.sum()), int(nzs.sum()))
-            return r
-        run_double_buffered(2)
-        db_steps = 2 * e2e_steps
-        barrier()
-        t0 = time.perf_counter()
-        r_db = run_double_buffered(db_steps)
-        dt_db = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        ex.shutdown()
-        ctx2.close()
-    # ---- the same step when the consumers of the depth map query the device (csv_depth_at = getReadDepth for every
-    # signature start, csv_window_sums for the log2 windows) instead of the 12 GB map crossing PCIe.  Extra information:
-    # the contract's e2e above returns the whole map in host memory, as the reference's interface does.
-    def step_e2e_device_consumers():
-        bt = api.Batch(ctx, reads, regions)
+    # ---- sharded run: the single-device answer for the same genome, computed here and now on rank 0
+    checksums_n1 = None
+    if strong and rank == 0:
+        bt = api.Batch(ctx, full, api.whole_contig_regions(contig_len))
         bt.scan(want_depth=True, want_sigs=True)
         lab = bt.sigs_dbscan1d(DB_EPS, DB_MIN_PTS)
-        sums, nzs = bt.depth_stats()
-        sg = bt.sigs()
-        nq = 0
-        for i in range(len(regions)):
-            lo, hi = int(sg["region_off"][i]), int(sg["region_off"][i + 1])
-            if hi > lo and regions[i][1] == 0 and regions[i][2] == regions[i][3]:
-                bt.depth_at(i, sg["start"][lo:hi]); nq += hi - lo
+        sg = bt.sigs(); sg["label"] = lab; sg["depth"] = bt.sigs_depth()
+        c1 = bt.depth_checksum().astype(np.int64)
         bt.free()
-        return nq
+        m1, _ = finalize_merge([(sg, api.whole_contig_regions(contig_len), 0)], ctx, api)
+        d1 = digest_results(m1, n_contigs)
+        import hashlib
+        checksums_n1 = {"depth": hashlib.blake2b(c1.tobytes(), digest_size=8).hexdigest(), "signatures": d1[0], "dbscan1d_labels": d1[1], "depth_at_signature_start": d1[2],
+                        "signatures_total": int(sum(len(m["start"]) for m in m1.values()))}
+    if strong:
+        barrier()
 
-    edc = None
-    if not args.skip_e2e:
-        step_e2e_device_consumers()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            nq = step_e2e_device_consumers()
-        ctx.sync()
-        dt2 = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        edc = {"value": total_reads * e2e_steps / dt2, "unit": "reads/s", "ms_per_step": 1e3 * dt2 / e2e_steps,
-               "h2d_bytes_per_step": 15 * n_reads + 8 + 4 * n_ops + 4 * nq, "d2h_bytes_per_step": 25 * n_sig + 12 * len(regions) + 4 * nq,
-               "note": "depth map stays in HBM; getReadDepth for every signature start served by csv_depth_at"}
-    h2d = 15 * n_reads + 8 + 4 * n_ops
-    d2h_results = 21 * n_sig + 4 * n_sig + 12 * len(regions)
-    d2h_plain = 4 * depth_words + d2h_results
-    e2e_extra = {}
-    if not args.skip_e2e:
-        # bytes that really cross PCIe on the narrow path: one byte per base + header and exception list per chunk,
-        # plus the chunks whose list overflowed, again as 32-bit words
-        chunk, exc = 2 << 20, 2048
-        n_chunks = sum((e - b + chunk - 1) // chunk for (_, b, e, _) in regions)
-        d2h = depth_words + n_chunks * (16 + 8 * exc) + fallback_chunks * 4 * chunk + d2h_results
-        e2e_extra = {"result_bytes_in_host_memory": d2h_plain, "depth_fetch": "narrow: u8 over PCIe + %d host threads widen to uint32 (fetch.cu)" % fetch_threads,
-                     "fetch_chunks_narrow_per_step": narrow_chunks, "fetch_chunks_refetched_plain_per_step": fallback_chunks,
-                     "double_buffered": {"value": total_reads * db_steps / dt_db, "ms_per_step": 1e3 * dt_db / db_steps, "steps": db_steps,
-                                         "note": "upload of step s+1 (second context, helper thread) beside the fetch of step s; pipeline fill included"},
-                     "plain_dma": {"value": total_reads * e2e_steps / dt_plain, "ms_per_step": 1e3 * dt_plain / e2e_steps, "d2h_bytes_per_step": d2h_plain}}
-    else:
-        d2h = d2h_plain
+    # ---- N == 1 extra: the same step when the caller insists on the whole uint32-per-base map in host memory (what the
+    # reference's container holds): narrow fetch, u8 over PCIe + host threads widen (fetch.cu)
+    full_map = None
+    if world == 1 and not args.skip_e2e and not args.no_full_map:
+        out_maps = []
+        for (_, b_, e_, _) in regions:
+            try:
+                out_maps.append(_capi.pinned_empty(e_ - b_, np.uint32))
+            except _capi.CsvError:
+                out_maps.append(np.empty(e_ - b_, np.uint32))
+        fetch_threads = max(1, min(16, (os.cpu_count() or 1) - 2))
+        ctx.set_fetch(threads=fetch_threads)
+
+        def step_full_map():
+            bt = api.Batch(ctx, reads, regions)
+            bt.scan(want_depth=True, want_sigs=True)
+            lab = bt.sigs_dbscan1d(DB_EPS, DB_MIN_PTS)
+            s_, z_ = bt.depth_stats()
+            bt.depth_all(out_maps)
+            sg_ = bt.sigs()
+            bt.free()
+            return len(lab)
+        step_full_map()
+        dt_fm, _ = timed(step_full_map, min(2, e2e_steps))
+        full_map = {"value": n_reads * min(2, e2e_steps) / dt_fm, "unit": "reads/s", "ms_per_step": 1e3 * dt_fm / min(2, e2e_steps),
+                    "result_bytes_in_host_memory": 4 * depth_words + 29 * n_sig, "depth_fetch": "narrow: u8 over PCIe + %d host threads widen to uint32" % fetch_threads}
+        del out_maps
+
+    h2d = sum(v.nbytes for v in reads.values() if isinstance(v, np.ndarray))
+    d2h = 21 * n_sig + 4 * n_sig + 4 * n_sig + 12 * len(regions)
 
     # ---- CPU baseline (rank 0, N == 1): the reference's own code on a bounded sample of the workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         r2, clen2 = reference_sample(cores, args.seed)
-        kind, total = run_reference_steps(r2, clen2, 1, 0)
+        kind, total = run_reference_steps(r2, clen2, 1, 1)
         cpu = {"value": int(r2["n_reads"]) / total, "unit": "reads/s", "cores": cores, "kind": kind,
-               "sample": "%d contigs of %d bp at 30x (%d reads), one contig per host thread, depth + CIGAR signatures + DBSCAN1D, -O2"
+               "sample": "%d contigs of %d bp at 30x (%d reads), one contig per host thread, depth + CIGAR signatures + DBSCAN1D, -O2; 1 warm-up + 1 timed step"
                          % (len(clen2), clen2[0], int(r2["n_reads"]))}
+        try:
+            from oracle.oracle_py import ref_available
+            if ref_available(o0=True):
+                # the build the reference ships (-g, no -O, Makefile:14) on one contig of the sample, single thread
+                sub_r, sub_c = reference_sample(1, args.seed)
+                k0, t0_ = run_reference_steps(sub_r, sub_c, 1, 0, o0=True)
+                k2, t2_ = run_reference_steps(sub_r, sub_c, 1, 0)
+                cpu["as_shipped_O0"] = {"reads_per_s_1_thread": int(sub_r["n_reads"]) / t0_, "O2_reads_per_s_1_thread": int(sub_r["n_reads"]) / t2_,
+                                        "sample": "1 contig of %d bp (%d reads), 1 thread" % (sub_c[0], int(sub_r["n_reads"]))}
+        except Exception as ex:       # the baseline is a reported extra, never a reason to lose the line
+            cpu["as_shipped_O0"] = {"error": str(ex)[:200]}
 
     if rank == 0:
+        match = None if checksums_n1 is None else all(checksums[k] == checksums_n1[k] for k in checksums_n1)
         line = {
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "reads_per_rank": n_reads, "cigar_ops_per_rank": n_ops,
-                       "depth_positions_per_rank": depth_words, "signatures_per_rank": n_sig, "regions_per_rank": len(regions),
-                       "dbscan1d": {"eps": DB_EPS, "min_pts": DB_MIN_PTS, "groups": "per (region, SVType) over signature starts"},
-                       "l2": "inputs_larger_than_l2 (CIGAR %.2f GB read + depth %.2f GB written per step)" % (4 * n_ops / 1e9, 4 * depth_words / 1e9),
-                       "parallelism": "1 process/GPU, %s, no collective" % ("independent samples" if args.scaling == "weak" or world == 1 else "region shards + halo reads"),
-                       "host_generation_s": round(t_gen, 2)},
+            "config": {"workload": workload_name(args.workload), "genome_reads": int(genome_reads), "reads_this_rank": n_reads, "cigar_ops_this_rank": n_ops,
+                       "depth_positions_this_rank": depth_words, "signatures_this_rank": n_sig, "regions_this_rank": len(regions),
+                       "dbscan1d": {"eps": DB_EPS, "min_pts": DB_MIN_PTS, "groups": "per (region, SVType) over signature starts, on the shard that owns them; contigs cut by the plan are re-fit after the host merge (in e2e)"},
+                       "l2": "inputs_larger_than_l2 (this rank: CIGAR %.2f GB read + depth %.2f GB written per step)" % (4 * n_ops / 1e9, 4 * depth_words / 1e9),
+                       "parallelism": "1 process/GPU, no collective on the path; " + ("independent samples per rank" if not strong else
+                                      "one genome in %d cost-balanced region shards (positions + %.1f x ops) with halo reads, host merge" % (world, shard.OP_COST)),
+                       "ms_per_step_fastest_rank": ms_min / args.steps, "host_generation_s": round(t_gen, 2)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), **e2e_extra},
-            "e2e_device_consumers": edc,
+                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1),
+                    "result": "mean coverage inputs, signature vectors, DBSCAN1D labels, depth at every signature start in host memory; the per-base map stays in HBM" +
+                              ("; shards gathered through shared memory, merged and re-fit on rank 0" if strong else "")},
+            "e2e_full_map": full_map,
+            "checksums": checksums, "checksums_single_device": checksums_n1, "checksums_match": match,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
+    if board is not None:
+        barrier()
+        board.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and checksums_n1 is not None and not match:
+        sys.stderr.write("bench.py: sharded results differ from the single-device results\n")
+        return 1
     return 0
 
 
@@ -495,11 +656,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr1_5", "chr21", "small", "ont60x_chr20", "svrich_chr1"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: strong (default) = one genome region-sharded over the ranks [BASELINE configs[3]]; weak = one whole genome per rank")
     ap.add_argument("--seed", type=int, default=20261018 + 2)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-full-map", action="store_true", help="skip the extra e2e_full_map measurement")
     ap.add_argument("--depth-only", action="store_true", help="diagnostic: resident step without signatures / DBSCAN1D (never a reported number)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -11,6 +11,7 @@ import numpy as np
 from . import build as _build
 
 CSV_OK = 0
+CSV_ERR_CAPACITY = 3
 STATUS_NAMES = {0: "CSV_OK", 1: "CSV_ERR_CUDA", 2: "CSV_ERR_ARG", 3: "CSV_ERR_CAPACITY", 4: "CSV_ERR_LIMIT", 5: "CSV_ERR_STATE"}
 
 
@@ -22,7 +23,7 @@ class CsvError(RuntimeError):
 
 class CsvReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_ops", C.c_uint64), ("tid", C.c_void_p), ("pos0", C.c_void_p),
-                ("flag", C.c_void_p), ("mapq", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p)]
+                ("flag", C.c_void_p), ("mapq", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("n_gap", C.c_void_p)]
 
 
 class CsvRegion(C.Structure):
@@ -44,7 +45,8 @@ EXPORTS = [
     "csv_ctx_create", "csv_ctx_destroy", "csv_ctx_sync", "csv_last_error", "csv_version", "csv_host_alloc", "csv_host_free",
     "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_ctx_set_pipeline_chunks", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
     "csv_depth_stats", "csv_depth_fetch", "csv_depth_fetch_all", "csv_ctx_set_fetch", "csv_ctx_fetch_stats", "csv_host_widen_u8", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
-    "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at", "csv_record_summary",
+    "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at", "csv_record_summary", "csv_host_count_gaps",
+    "csv_depth_at_tid", "csv_sigs_depth", "csv_depth_checksum", "csv_batch_reserve_sigs",
 ]
 SYNTH_EXPORTS = ["csv_synth_default_params", "csv_synth_num_reads", "csv_synth_reads", "csv_synth_cigar"]
 
@@ -85,6 +87,8 @@ def lib():
         L.csv_ctx_fetch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.csv_host_widen_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.csv_host_widen_u8.restype = None
+        L.csv_host_count_gaps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        L.csv_host_count_gaps.restype = None
         L.csv_sigs_count.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.csv_sigs_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CsvSigs), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
         L.csv_sigs_dbscan1d.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_uint64]
@@ -94,6 +98,10 @@ def lib():
         L.csv_dbscan1d.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.csv_record_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.csv_depth_at.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.csv_depth_at_tid.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.csv_sigs_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.csv_depth_checksum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.csv_batch_reserve_sigs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.csv_dbscan2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_void_p]
         L.csv_dbscan1d_seg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.csv_largest_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -146,8 +154,20 @@ def reads_struct(r):
         "mapq": np.ascontiguousarray(r["mapq"], np.uint8),
         "cig_off": np.ascontiguousarray(r["cig_off"], np.uint64),
         "cigar": np.ascontiguousarray(r["cigar"], np.uint32),
+        "n_gap": None if r.get("n_gap") is None else np.ascontiguousarray(r["n_gap"], np.uint32),
     }
     n_ops = int(arrs["cig_off"][n]) if n else 0
     s = CsvReads(n, n_ops, ptr(arrs["tid"]), ptr(arrs["pos0"]), ptr(arrs["flag"]), ptr(arrs["mapq"]), ptr(arrs["cig_off"]),
-                 ptr(arrs["cigar"]))
+                 ptr(arrs["cigar"]), ptr(arrs["n_gap"]))
     return s, arrs
+
+
+def count_gaps(r, alloc=None, threads=0):
+    """What a packer hands over as csv_reads::n_gap: the number of D / N ops of every record (host helper of the
+    library, no device needed).  Returns the array; callers store it as r["n_gap"]."""
+    n = int(r["n_reads"])
+    out = (alloc or (lambda k, dt: np.empty(k, dtype=dt)))(max(n, 1), np.uint32)
+    if n:
+        cig = np.ascontiguousarray(r["cigar"], np.uint32); off = np.ascontiguousarray(r["cig_off"], np.uint64)
+        lib().csv_host_count_gaps(ptr(cig), ptr(off), n, ptr(out), int(threads))
+    return out[:n]

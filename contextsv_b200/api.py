@@ -124,12 +124,21 @@ def whole_contig_regions(contig_len, tids=None):
     return [(int(t), 0, int(contig_len[t]) + 1, int(contig_len[t]) + 1) for t in tids]
 
 
+# The packer's share of the pre-pass: when the records come without csv_reads::n_gap (D / N ops per record), Batch
+# counts them on the host before the upload (csv_host_count_gaps).  False leaves the field NULL, and the device falls
+# back to its op-level pre-pass (a second read of every CIGAR word).
+COUNT_GAPS = True
+
+
 class Batch:
     """csv_batch: reads resident in HBM + the regions they are scanned against."""
 
     def __init__(self, ctx, reads, regions):
         self.ctx = ctx
         self.regions = [tuple(int(x) for x in r) for r in regions]
+        if COUNT_GAPS and reads.get("n_gap") is None and int(reads["n_reads"]):
+            reads = dict(reads)
+            reads["n_gap"] = _capi.count_gaps(reads)
         rs, self._keep = _capi.reads_struct(reads)
         arr = (CsvRegion * len(self.regions))(*[CsvRegion(*r) for r in self.regions])
         h = C.c_void_p()
@@ -150,6 +159,7 @@ class Batch:
 
     def scan(self, want_depth=True, want_sigs=True, min_len=50, min_mapq=20):
         p = CsvScanParams(min_len, min_mapq, int(want_depth), int(want_sigs), 0)
+        self._last_scan = p
         check(lib().csv_scan_run(self.ctx.h, self.h, C.byref(p)))
 
     def depth_stats(self):
@@ -178,16 +188,28 @@ class Batch:
         return out
 
     def sigs_count(self):
+        """Signatures of the last pass.  A pass that emitted more than the batch had reserved is run again with the
+        reported capacity (csv_batch_reserve_sigs): the reference's vector has no limit."""
         n = C.c_uint64(0)
-        check(lib().csv_sigs_count(self.ctx.h, self.h, C.byref(n)))
+        rc = lib().csv_sigs_count(self.ctx.h, self.h, C.byref(n))
+        if rc == _capi.CSV_ERR_CAPACITY and int(n.value) > 0:
+            check(lib().csv_batch_reserve_sigs(self.ctx.h, self.h, int(n.value)))
+            check(lib().csv_scan_run(self.ctx.h, self.h, C.byref(self._last_scan)))
+            rc = lib().csv_sigs_count(self.ctx.h, self.h, C.byref(n))
+        check(rc)
         return int(n.value)
 
-    def sigs(self):
-        """dict of arrays in the reference's vector order + 'region_off' [n_regions + 1]."""
-        n = self.sigs_count()
+    def sigs(self, out=None, n=None):
+        """dict of arrays in the reference's vector order + 'region_off' [n_regions + 1].  `out` may hold preallocated
+        arrays (start, end, kind, read_idx, op_idx, query_pos) of enough capacity: results land there (views returned)."""
+        n = self.sigs_count() if n is None else n
         cap = max(n, 1)
-        o = {"start": np.zeros(cap, np.uint32), "end": np.zeros(cap, np.uint32), "kind": np.zeros(cap, np.uint8),
-             "read_idx": np.zeros(cap, np.uint32), "op_idx": np.zeros(cap, np.uint32), "query_pos": np.zeros(cap, np.uint32)}
+        if out is None:
+            o = {"start": np.zeros(cap, np.uint32), "end": np.zeros(cap, np.uint32), "kind": np.zeros(cap, np.uint8),
+                 "read_idx": np.zeros(cap, np.uint32), "op_idx": np.zeros(cap, np.uint32), "query_pos": np.zeros(cap, np.uint32)}
+        else:
+            o = {k: out[k] for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
+            cap = min(len(v) for v in o.values())
         st = CsvSigs(ptr(o["start"]), ptr(o["end"]), ptr(o["kind"]), ptr(o["read_idx"]), ptr(o["op_idx"]), ptr(o["query_pos"]))
         got = C.c_uint64(0)
         off = np.zeros(len(self.regions) + 1, np.uint64)
@@ -196,13 +218,13 @@ class Batch:
         o["region_off"] = off
         return o
 
-    def sigs_dbscan1d(self, eps, min_pts, fetch=True):
+    def sigs_dbscan1d(self, eps, min_pts, fetch=True, out=None, n=None):
         if not fetch:
             check(lib().csv_sigs_dbscan1d(self.ctx.h, self.h, float(eps), int(min_pts), None, 0))
             return None
-        n = self.sigs_count()
-        lab = np.zeros(max(n, 1), np.int32)
-        check(lib().csv_sigs_dbscan1d(self.ctx.h, self.h, float(eps), int(min_pts), ptr(lab), max(n, 1)))
+        n = self.sigs_count() if n is None else n
+        lab = np.zeros(max(n, 1), np.int32) if out is None else out
+        check(lib().csv_sigs_dbscan1d(self.ctx.h, self.h, float(eps), int(min_pts), ptr(lab), len(lab)))
         return lab[:n]
 
     def record_summary(self):
@@ -217,6 +239,26 @@ class Batch:
         pos = np.ascontiguousarray(positions, np.uint32)
         out = np.zeros(len(pos), np.uint32)
         check(lib().csv_depth_at(self.ctx.h, self.h, region, len(pos), ptr(pos), ptr(out)))
+        return out
+
+    def depth_at_tid(self, tid, positions):
+        """getReadDepth for (contig, position) pairs anywhere in the batch; 0xffffffff = not covered by this batch's regions."""
+        t = np.ascontiguousarray(tid, np.int32); pos = np.ascontiguousarray(positions, np.uint32)
+        out = np.zeros(len(pos), np.uint32)
+        check(lib().csv_depth_at_tid(self.ctx.h, self.h, len(pos), ptr(t), ptr(pos), ptr(out)))
+        return out
+
+    def sigs_depth(self, n=None, out=None):
+        """Depth at the start of every signature, in sigs() order (sv_caller.cpp:1306)."""
+        n = self.sigs_count() if n is None else n
+        out = np.zeros(max(n, 1), np.uint32) if out is None else out
+        check(lib().csv_sigs_depth(self.ctx.h, self.h, ptr(out), len(out)))
+        return out[:n]
+
+    def depth_checksum(self):
+        """Additive position-weighted checksum of every region's depth slice (csv_depth_checksum)."""
+        out = np.zeros(len(self.regions), np.uint64)
+        check(lib().csv_depth_checksum(self.ctx.h, self.h, ptr(out)))
         return out
 
     def window_sums(self, region, start_pos, end_pos, sample_size):

@@ -6,7 +6,7 @@ namespace csv {
 constexpr uint32_t kNone = 0xffffffffu;
 
 // u32 slots of csv_batch::d_scalars
-enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_HAS_EMPTY = 6 /* a record without CIGAR: tables need compaction */, SC_COUNT = 16 };
+enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_HAS_EMPTY = 6 /* a record without CIGAR: tables need compaction */, SC_BAD_GAPS = 7 /* csv_reads::n_gap does not match the CIGAR */, SC_COUNT = 16 };
 
 struct SigRaw {          // emission-order signature records (device)
     unsigned long long* key_hi;   // owner region << 32 | start
@@ -38,9 +38,10 @@ struct csv_batch {
     uint64_t ev_cap = 0, sig_cap = 0;
     uint32_t last_min_len = 50;
     bool scanned = false, have_depth = false, have_sigs = false, have_labels = false;
+    bool rec_prepass = false;                 // the caller supplied n_gap[] and records are short: record-level pre-pass (walk.cu)
 
     // input SoA (device)
-    csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar;
+    csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar, d_n_gap;
     // derived per-read tables
     csv::DevBuf d_meta;      // uint4 {pos0, map_size | 0 (contig not requested), flag | mapq << 16, owner region | kNone} per non-empty read
     csv::DevBuf d_key;       // u64 (tid << 32 | pos0 + 1) per non-empty read: the batch's sort key
@@ -50,9 +51,10 @@ struct csv_batch {
     csv::DevBuf d_regs, d_tids, d_reg_sig_cnt;
     csv::DevBuf d_reg_tab;   // u32 [tile_base (n_regions + 1) | len (n_regions)], caller order
     // walk
-    csv::DevBuf d_span_agg, d_span_pre, d_span_status, d_scan_carry, d_span_desc;
+    csv::DevBuf d_span_agg, d_span_pre, d_span_status, d_scan_carry, d_span_desc, d_span_rq, d_ev_check;
     std::vector<csv::PipeChunk> chunks;
     csv::DevBuf d_chunk_tid, d_chunk_bounds;
+    csv::DevBuf d_tickets;   // u32 tile tickets of this batch's chained kernels, zeroed at the start of every pass (one per pipeline chunk)
     // depth
     csv::DevBuf d_events;    // uint32 depth-map indices, sign = slot parity
     csv::DevBuf d_ev_start, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
@@ -62,8 +64,8 @@ struct csv_batch {
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
 
     void release(csv::DevPool* pool = nullptr) {
-        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
-                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds,
+        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_span_rq, &d_ev_check, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
+                              &d_regs, &d_tids, &d_reg_sig_cnt, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds, &d_tickets,
                               &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r, &d_sig_hi, &d_sig_lo, &d_sig_k,
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
@@ -94,7 +96,11 @@ struct SortBufs {
 };
 // digit_mask: bit d set = byte d of the 128-bit key (lo bytes 0-7, hi bytes 8-15) may vary.
 // The sorted data always ends up in bufs.hi / lo / val.
-int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32_t* n_dev, uint32_t digit_mask);
+// first (optional): the sort opens a pipeline whose element count is still raw -- its first kernel clamps *n_raw to
+// clamp_cap, publishes the result in *n_clamped_out (which must then be the sort's n_dev) and, with iota, fills bufs.val
+// with 0, 1, 2, ...: two tiny launches less on the signature side stream.
+struct SortFirst { const uint32_t* n_raw; uint32_t clamp_cap; uint32_t* n_clamped_out; bool iota; };
+int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32_t* n_dev, uint32_t digit_mask, const SortFirst* first = nullptr);
 
 // DBSCAN1D on device-resident points.  d_seg may be null (single fit).
 int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, uint64_t n_upper, const uint32_t* n_dev,

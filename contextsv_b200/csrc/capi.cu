@@ -99,10 +99,26 @@ static int check_overflow(csv_ctx* ctx, csv_batch* b, uint32_t* sc)
         set_error("a record consumes 2^31 or more reference bases: not a valid alignment (BAM positions are int32)");
         return CSV_ERR_LIMIT;
     }
+    if (sc[SC_BAD_GAPS]) {
+        set_error("csv_reads::n_gap does not match the CIGAR: it must hold the number of D / N ops of every record");
+        return CSV_ERR_ARG;
+    }
     if (b->have_sigs && sc[SC_N_SIG] > b->sig_cap) {
-        set_error("signatures: %u emitted, batch capacity is %llu", sc[SC_N_SIG], (unsigned long long)b->sig_cap);
+        set_error("signatures: %u emitted, batch capacity is %llu: csv_batch_reserve_sigs(%u) and scan again", sc[SC_N_SIG], (unsigned long long)b->sig_cap, sc[SC_N_SIG]);
         return CSV_ERR_CAPACITY;
     }
+    return CSV_OK;
+}
+
+// signature-side buffers of a batch, sized by b->sig_cap
+static int alloc_sig_buffers(csv_ctx* ctx, csv_batch* b)
+{
+    const size_t sc = (size_t)b->sig_cap;
+    CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_out_start.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_end.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_kind.ensure(sc, &ctx->pool));
+    CSV_TRY(b->d_out_read.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_op.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_qpos.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_out_seg.ensure(sc * 4, &ctx->pool));
     return CSV_OK;
 }
 
@@ -362,6 +378,10 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
             }
         }
     }
+    // record-level pre-pass: the caller counted the D/N ops per record and records are short (a span start lies a few
+    // dozen ops into the record that crosses it; ONT-like batches keep the op-level pre-pass)
+    static const bool rec_ok = !(getenv("CSV_REC_PREPASS") && atoi(getenv("CSV_REC_PREPASS")) == 0);
+    b->rec_prepass = rec_ok && r->n_gap != nullptr && r->n_reads > 0 && r->n_ops <= (uint64_t)r->n_reads * 1024u;
     b->ev_cap = 2 * (r->n_ops + (uint64_t)r->n_reads) + 2;      // exact bound: 2 per record + 2 per D/N op
     b->sig_cap = std::max<uint64_t>(16, std::min<uint64_t>(r->n_ops, std::max<uint64_t>(1u << 20, r->n_ops / 16)));
 
@@ -370,13 +390,16 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pos0.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16, &ctx->pool)); CSV_TRY(b->d_mapq.ensure(nr + 16, &ctx->pool));
     CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8, &ctx->pool)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64, &ctx->pool));
+    if (b->rec_prepass) { CSV_TRY(b->d_n_gap.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ev_check.ensure((nr + 2) * 4, &ctx->pool)); }
+    CSV_TRY(b->d_span_rq.ensure(((size_t)b->n_spans + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_key.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 512, &ctx->pool));   // the walk copies 272 bytes per span, also for the last one
     CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4, &ctx->pool));
     CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev), &ctx->pool)); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev), &ctx->pool));
     CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4, &ctx->pool)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4, &ctx->pool));
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
     CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / kSpanChunk + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
-    CSV_TRY(b->d_scan_carry.ensure(sizeof(WalkAgg), &ctx->pool)); CSV_TRY(b->d_span_desc.ensure((size_t)b->n_spans * 16 + 16, &ctx->pool));
+    CSV_TRY(b->d_scan_carry.ensure(sizeof(WalkAgg), &ctx->pool)); CSV_TRY(b->d_span_desc.ensure((size_t)b->n_spans * 16 + 32, &ctx->pool));
+    CSV_TRY(b->d_tickets.ensure(b->chunks.size() * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_chunk_tid.ensure(b->chunks.size() * 4 + 16, &ctx->pool)); CSV_TRY(b->d_chunk_bounds.ensure(b->chunks.size() * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
     CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
@@ -385,11 +408,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_wide_list.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_q.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_r.ensure(nt * 8 + 16, &ctx->pool));
     CSV_TRY(b->d_tile_sum.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_nz.ensure(nt * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_sum.ensure(n_regions * 8, &ctx->pool)); CSV_TRY(b->d_nz.ensure(n_regions * 4, &ctx->pool));
-    CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));
-    CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
-    CSV_TRY(b->d_out_start.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_end.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_kind.ensure(sc, &ctx->pool));
-    CSV_TRY(b->d_out_read.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_op.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_qpos.ensure(sc * 4, &ctx->pool));
-    CSV_TRY(b->d_out_seg.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(alloc_sig_buffers(ctx, b.get()));
 
     // ---- uploads (asynchronous when the host buffers are pinned)
     cudaStream_t st = ctx->stream;
@@ -399,6 +418,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
         CSV_CUDA(cudaMemcpyAsync(b->d_flag.p, r->flag, nr * 2, cudaMemcpyHostToDevice, st));
         CSV_CUDA(cudaMemcpyAsync(b->d_mapq.p, r->mapq, nr, cudaMemcpyHostToDevice, st));
         CSV_CUDA(cudaMemcpyAsync(b->d_cig_off.p, r->cig_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (b->rec_prepass) CSV_CUDA(cudaMemcpyAsync(b->d_n_gap.p, r->n_gap, nr * 4, cudaMemcpyHostToDevice, st));
     } else {
         CSV_CUDA(cudaMemsetAsync(b->d_cig_off.p, 0, 8, st));
     }
@@ -419,6 +439,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
         }
     }
     if (nt) CSV_CUDA(cudaMemcpyAsync(b->d_tile_desc.p, tile_desc.data(), nt * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    CSV_CUDA(cudaMemsetAsync(b->d_pmax_part.p, 0, (nr / 2048 + 2) * 8, st));      // look-back status words of k_pmax_chained: epoch 0 == never published
     CSV_CUDA(cudaStreamSynchronize(st));
     *out = b.release();
     return CSV_OK;
@@ -432,6 +453,20 @@ void csv_batch_free(csv_ctx* ctx, csv_batch* b)
     delete b;
 }
 
+int csv_batch_reserve_sigs(csv_ctx* ctx, csv_batch* b, uint64_t n_sigs)
+{
+    if (!ctx || !b) { set_error("csv_batch_reserve_sigs: null argument"); return CSV_ERR_ARG; }
+    if (n_sigs >= (1ull << 30)) { set_error("csv_batch_reserve_sigs: %llu signatures exceed the 2^30 limit", (unsigned long long)n_sigs); return CSV_ERR_LIMIT; }
+    if (n_sigs <= b->sig_cap) return CSV_OK;
+    CSV_CUDA(cudaSetDevice(ctx->device));
+    CSV_TRY(side_join(ctx));
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));            // the buffers are about to change hands
+    b->sig_cap = std::min<uint64_t>(std::max<uint64_t>(n_sigs, 16), std::max<uint64_t>(b->n_ops, 16));
+    b->d_labels.release(&ctx->pool);
+    b->have_sigs = false; b->have_labels = false;            // results of the pass that overflowed are void
+    return alloc_sig_buffers(ctx, b);
+}
+
 int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
 {
     if (!ctx || !b || !p) { set_error("csv_scan_run: null argument"); return CSV_ERR_ARG; }
@@ -441,6 +476,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     b->last_min_len = p->min_len;
     CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
     if (p->want_depth) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));
+    CSV_CUDA(cudaMemsetAsync(b->d_tickets.p, 0, b->chunks.size() * 4 + 16, st));
     { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b, p->min_mapq)); }
     // The pass is pipelined over chunks of whole contigs.  Main stream: the walk, chunk after chunk.  Tile stream:
     // tile ranges + depth tiles of chunk c as soon as the walk of chunk c + 1 is through (the records at the end of
@@ -553,9 +589,11 @@ int csv_sigs_fetch(csv_ctx* ctx, csv_batch* b, csv_sigs* out, uint64_t cap, uint
     if (!ctx || !b || !out || !n_out) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_fetch: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
     uint32_t sc[SC_COUNT];
-    CSV_TRY(check_overflow(ctx, b, sc));
+    sc[SC_N_SIG] = 0;
+    const int ovf = check_overflow(ctx, b, sc);
     const uint64_t n = sc[SC_N_SIG];
-    *n_out = n;
+    *n_out = n;                                              // also with CSV_ERR_CAPACITY: the size to reserve
+    if (ovf != CSV_OK) return ovf;
     if (n > cap) { set_error("csv_sigs_fetch: %llu signatures, caller capacity %llu", (unsigned long long)n, (unsigned long long)cap); return CSV_ERR_CAPACITY; }
     cudaStream_t st = ctx->stream;
     if (n) {
@@ -624,7 +662,14 @@ int csv_cigar_scan(csv_ctx* ctx, const csv_reads* reads, const csv_region* regio
     CSV_TRY(csv_batch_upload(ctx, reads, 1, region, &b));
     csv_scan_params p = {min_len, min_mapq, 0, 1, 0};
     int s = csv_scan_run(ctx, b, &p);
-    if (s == CSV_OK) s = csv_sigs_fetch(ctx, b, out, cap, n_out, nullptr);
+    uint64_t n = 0;
+    if (s == CSV_OK) s = csv_sigs_fetch(ctx, b, out, cap, &n, nullptr);
+    if (s == CSV_ERR_CAPACITY && n > b->sig_cap) {           // more signatures than the batch reserved: the reference has no such limit
+        s = csv_batch_reserve_sigs(ctx, b, n);
+        if (s == CSV_OK) s = csv_scan_run(ctx, b, &p);
+        if (s == CSV_OK) s = csv_sigs_fetch(ctx, b, out, cap, &n, nullptr);
+    }
+    if (n_out) *n_out = n;
     csv_batch_free(ctx, b);
     return s;
 }

@@ -90,76 +90,70 @@ __device__ __forceinline__ unsigned long long pm_value(const unsigned long long*
 }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-// The prefix max runs over the records [bounds[0], bounds[1]) of one pipeline chunk and restarts there: records of
-// earlier contigs can never exceed a (tid, position) of this chunk.
-__global__ void __launch_bounds__(kPmThreads) k_pm_partials(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
-                                                            const uint32_t* bounds, unsigned long long* part)
+// Running maximum of (tid, ref_end) over the records [bounds[0], bounds[1]) of one pipeline chunk, ONE launch: tiles of
+// kPmTile records are claimed by ticket and chained by a look-back.  Records are sorted by contig, so the u64 maximum
+// is a maximum of ref_end that restarts at every contig change: a tile publishes (epoch | flag, max ref_end among the
+// records of its LAST contig) in one 64-bit word -- complete (kFlagPrefix) at once when the tile starts the chunk,
+// starts a new contig or contains a contig change, otherwise its own share first (kFlagAgg) and the complete value after
+// the look-back.  A successor only looks back if its first record continues the contig of the record right before it.
+// The coordinate-order check of the batch rides along.
+// complete: the published value needs nothing from earlier tiles; look: the tile's first records continue the contig of
+// the tile before, so the carry-in has to be fetched (both can hold: a tile that continues a contig AND starts another).
+__device__ __forceinline__ uint32_t lookback_max_u32(unsigned long long* status, uint32_t t, uint32_t aggregate, bool complete, bool look_back, uint32_t epoch)
 {
-    __shared__ unsigned long long s[kPmThreads / 32];
-    const uint32_t k0 = bounds[0], n = bounds[1] - k0;
-    for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
-        unsigned long long v = 0;
-        for (int j = 0; j < kPmItems; j++) {
-            const uint64_t k = (uint64_t)t * kPmTile + j * kPmThreads + threadIdx.x;
-            if (k < n) v = umax64(v, pm_value(meta, ref_end, k0 + (uint32_t)k));
+    const uint32_t lane = lane_id();
+    if (lane == 0) st_volatile_u64(&status[t], lb_pack(epoch, complete ? kFlagPrefix : kFlagAgg, aggregate));
+    if (!look_back) return 0u;
+    uint32_t excl = 0;
+    int64_t look = (int64_t)t - 1;
+    for (;;) {
+        const int64_t idx = look - lane;
+        uint32_t flag, val;
+        do {
+            if (idx >= 0) {
+                const unsigned long long w = ld_volatile_u64(&status[idx]);
+                const uint32_t hi = (uint32_t)(w >> 32);
+                flag = ((hi >> 2) == epoch) ? (hi & 3u) : 0u;
+                val = (uint32_t)w;
+            } else { flag = kFlagPrefix; val = 0; }
+        } while (__any_sync(0xffffffffu, flag == 0));
+        const uint32_t pm = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+        if (pm) {
+            const uint32_t j = __ffs(pm) - 1;
+            excl = max(excl, __reduce_max_sync(0xffffffffu, lane <= j ? val : 0u));
+            break;
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v = umax64(v, __shfl_xor_sync(0xffffffffu, v, d));
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long r = s[0];
-            for (int i = 1; i < kPmThreads / 32; i++) r = umax64(r, s[i]);
-            part[t] = r;
-        }
+        excl = max(excl, __reduce_max_sync(0xffffffffu, val));
+        look -= 32;
     }
+    if (lane == 0 && !complete) st_volatile_u64(&status[t], lb_pack(epoch, kFlagPrefix, max(excl, aggregate)));
+    return excl;
 }
 
-// single CTA: part[t] <- max of part[0..t-1] (exclusive), in place
-__global__ void __launch_bounds__(1024) k_pm_scan_partials(const uint32_t* bounds, unsigned long long* part)
-{
-    __shared__ unsigned long long s_w[32];
-    __shared__ unsigned long long s_carry;
-    const uint32_t n = bounds[1] - bounds[0];
-    const uint32_t n_part = (uint32_t)(((uint64_t)n + kPmTile - 1) / kPmTile);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_part; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const unsigned long long v = i < n_part ? part[i] : 0ull;
-        unsigned long long inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc = umax64(inc, t); }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        unsigned long long pre = s_carry;
-        for (uint32_t w = 0; w < warp; w++) pre = umax64(pre, s_w[w]);
-        unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) excl = 0;
-        if (i < n_part) part[i] = umax64(pre, excl);
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = umax64(pre, inc);
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
-                                                         uint32_t* scalars, const uint32_t* bounds, const unsigned long long* __restrict__ part,
-                                                         unsigned long long* pmax)
+__global__ void __launch_bounds__(kPmThreads) k_pmax_chained(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
+                                                             uint32_t* scalars, const uint32_t* bounds, unsigned long long* pmax,
+                                                             uint32_t* ticket, unsigned long long* status, uint32_t epoch,
+                                                             const uint32_t* __restrict__ ev_start, const uint32_t* __restrict__ ev_check)
 {
     // Global loads and stores are striped (lane-contiguous, one 256-byte row per warp and instruction); the scan wants
     // kPmItems consecutive records per thread.  The tile changes hands in shared memory, rows padded by one word per
     // kPmItems so that the blocked accesses spread over the banks.
     __shared__ unsigned long long s_v[kPmTile + kPmTile / kPmItems];
     __shared__ unsigned long long s_w[kPmThreads / 32];
+    __shared__ uint32_t s_tile, s_excl;
     const uint32_t kb = bounds[0], n = bounds[1] - kb;
     meta += kb; ref_end += kb; pmax += kb;
+    if (ev_check) { ev_start += kb; ev_check += kb; }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t t = blockIdx.x; (uint64_t)t * kPmTile < n; t += gridDim.x) {
+    const uint32_t n_tiles = (uint32_t)(((uint64_t)n + kPmTile - 1) / kPmTile);
+    for (;;) {
+        __syncthreads();                                        // s_v, s_w, s_tile are rewritten by the next tile
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t t = s_tile;
+        if (t >= n_tiles) break;
         const uint64_t base = (uint64_t)t * kPmTile;
-        bool unsorted = false;
+        bool unsorted = false, bad_gaps = false;
 #pragma unroll
         for (int j = 0; j < kPmItems; j++) {
             const uint32_t i = j * kPmThreads + threadIdx.x;
@@ -170,10 +164,14 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
                 v = (key & 0xffffffff00000000ull) | ref_end[k];
                 // coordinate order check rides along: (tid, pos0 + 1) must not decrease (also across chunk borders)
                 if (kb + k > 0 && meta[(long long)k - 1] > key) unsorted = true;
+                // ... and so does the check of the caller's D/N counts: the event slot the walk reached at the end of the
+                // record against the one the record scan derived from csv_reads::n_gap
+                if (ev_check && ev_check[k + 1] != ev_start[k + 1]) bad_gaps = true;
             }
             s_v[i + i / kPmItems] = v;
         }
         if (unsorted) scalars[SC_UNSORTED] = 1;
+        if (bad_gaps) scalars[SC_BAD_GAPS] = 1;
         __syncthreads();
         // blocked arrangement: thread owns kPmItems consecutive records
         const uint32_t o = threadIdx.x * (kPmItems + 1);
@@ -185,7 +183,20 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
         for (int d = 1; d < 32; d <<= 1) { unsigned long long x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc = umax64(inc, x); }
         if (lane == 31) s_w[warp] = inc;
         __syncthreads();
-        unsigned long long pre = part[t];
+        if (warp == 0) {
+            // the tile as a whole: its last contig and the maximum there; the carry-in only concerns its first contig
+            unsigned long long tot = s_w[0];
+#pragma unroll
+            for (int i = 1; i < kPmThreads / 32; i++) tot = umax64(tot, s_w[i]);
+            const uint32_t n_here = n - base < (uint64_t)kPmTile ? (uint32_t)(n - base) : (uint32_t)kPmTile;
+            const uint32_t tid_first = (uint32_t)(meta[base] >> 32), tid_last = (uint32_t)(meta[base + n_here - 1] >> 32);
+            const bool continues = t > 0 && (uint32_t)(meta[(long long)base - 1] >> 32) == tid_first;
+            const uint32_t e = lookback_max_u32(status, t, (uint32_t)tot, !continues || tid_first != tid_last, continues, epoch);
+            // with an unsorted batch (reported above) the high words may disagree: results are void anyway
+            if (lane == 0) s_excl = e;
+        }
+        __syncthreads();
+        unsigned long long pre = s_excl ? (((unsigned long long)(uint32_t)(meta[base] >> 32) << 32) | s_excl) : 0ull;
         for (uint32_t w = 0; w < warp; w++) pre = umax64(pre, s_w[w]);
         unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) excl = 0;
@@ -198,7 +209,6 @@ __global__ void __launch_bounds__(kPmThreads) k_pm_final(const unsigned long lon
             const uint32_t i = j * kPmThreads + threadIdx.x;
             if (base + i < n) pmax[base + i] = s_v[i + i / kPmItems];
         }
-        __syncthreads();                                        // s_v and s_w are rewritten by the next tile
     }
 }
 
@@ -307,10 +317,11 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
     const uint32_t n_part = (uint32_t)(((uint64_t)ch.rec_upper + kPmTile - 1) / kPmTile);
     if (n_part) {
         const uint32_t grid = n_part < (uint32_t)ctx->sm_count * 8 ? n_part : (uint32_t)ctx->sm_count * 8;
-        k_pm_partials<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, bounds, part);
-        k_pm_scan_partials<<<1, 1024, 0, ctx->stream>>>(bounds, part);
-        k_pm_final<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, bounds, part, pmax);
-        ctx->launches += 3;
+        // ticket and status words are the batch's own: this launch runs on the tile stream beside chained scans of the
+        // signature side stream, which share the context's
+        k_pmax_chained<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, bounds, pmax, b->d_tickets.as<uint32_t>() + c, part, next_epoch(ctx),
+                                                             b->d_ev_start.as<uint32_t>(), b->rec_prepass ? b->d_ev_check.as<uint32_t>() : nullptr);
+        ctx->launches++;
     }
     for (const auto& tr : ch.tiles) {
         const uint32_t grid_t = (tr.second - tr.first + 255) / 256;

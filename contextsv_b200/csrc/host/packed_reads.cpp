@@ -17,15 +17,17 @@ void PackedReads::append(const bam1_t* b, bool keep_seq)
     const uint32_t* c = bam_get_cigar(b);
     const uint32_t n = b->core.n_cigar;
     bool want_seq = false;
-    uint32_t rlen = 0;
+    uint32_t rlen = 0, gaps = 0;
     for (uint32_t i = 0; i < n; i++) {
         cigar.push_back(c[i]);
         const uint32_t op = bam_cigar_op(c[i]), len = bam_cigar_oplen(c[i]);
         if (len == 50 && (op == BAM_CINS || op == BAM_CSOFT_CLIP)) want_seq = true;
         if (op == BAM_CMATCH || op == BAM_CDEL || op == BAM_CREF_SKIP || op == BAM_CEQUAL || op == BAM_CDIFF) rlen += len;
+        gaps += (op == BAM_CDEL) | (op == BAM_CREF_SKIP);
     }
     cig_off.push_back(cigar.size());
     ref_end.push_back((uint32_t)b->core.pos + 1u + rlen);
+    n_gap.push_back(gaps);                                  // csv_reads::n_gap: the device's record-level pre-pass starts from it
     if (keep_seq && want_seq) {
         const uint8_t* s = bam_get_seq(b);
         seq4[idx].assign(s, s + ((size_t)b->core.l_qseq + 1) / 2);
@@ -34,7 +36,7 @@ void PackedReads::append(const bam1_t* b, bool keep_seq)
 
 void PackedReads::clear()
 {
-    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); seq4.clear();
+    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); n_gap.clear(); seq4.clear();
     cig_off.assign(1, 0);
 }
 
@@ -43,7 +45,7 @@ void PackedReads::keep_reaching(uint32_t cut)
     PackedReads k;
     for (size_t i = 0; i < pos0.size(); i++) {
         if (ref_end[i] <= cut) continue;
-        k.tid.push_back(tid[i]); k.pos0.push_back(pos0[i]); k.flag.push_back(flag[i]); k.mapq.push_back(mapq[i]); k.ref_end.push_back(ref_end[i]);
+        k.tid.push_back(tid[i]); k.pos0.push_back(pos0[i]); k.flag.push_back(flag[i]); k.mapq.push_back(mapq[i]); k.ref_end.push_back(ref_end[i]); k.n_gap.push_back(n_gap[i]);
         k.cigar.insert(k.cigar.end(), cigar.begin() + (ptrdiff_t)cig_off[i], cigar.begin() + (ptrdiff_t)cig_off[i + 1]);
         k.cig_off.push_back(k.cigar.size());
     }
@@ -113,7 +115,7 @@ csv_reads PackedReads::view() const
     r.n_reads = (uint32_t)pos0.size();
     r.n_ops = cigar.size();
     r.tid = tid.data(); r.pos0 = pos0.data(); r.flag = flag.data(); r.mapq = mapq.data();
-    r.cig_off = cig_off.data(); r.cigar = cigar.data();
+    r.cig_off = cig_off.data(); r.cigar = cigar.data(); r.n_gap = n_gap.data();
     return r;
 }
 
@@ -124,6 +126,9 @@ void pack_iterator(samFile* fp, hts_itr_t* itr, bam1_t* scratch, PackedReads& ou
 
 char base_at(const std::vector<uint8_t>& seq4, uint32_t i)
 {
+    // SEQ '*' (l_qseq == 0) or a CIGAR longer than SEQ: the reference reads whatever follows inside the bam1_t data block;
+    // here the base is reported as N instead of reading past the packed bases
+    if ((size_t)(i >> 1) >= seq4.size()) return 'N';
     const char base = seq_nt16_str[bam_seqi(seq4.data(), i)];
     switch (base) {   // ambiguous bases -> N, either case
         case 'R': case 'Y': case 'K': case 'M': case 'S': case 'W': case 'B': case 'D': case 'H': case 'V':

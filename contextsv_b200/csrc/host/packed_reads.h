@@ -23,6 +23,7 @@ struct PackedReads {
     std::vector<uint64_t> cig_off{0};
     std::vector<uint32_t> cigar;
     std::vector<uint32_t> ref_end;   // pos0 + 1 + reference bases consumed: depth index one past the last covered base
+    std::vector<uint32_t> n_gap;     // D / N ops per record (csv_reads::n_gap)
     // 4-bit bases of the few records that carry an I / S op of exactly 50 bases: the only place the
     // reference looks at the sequence on this path (literal ALT allele, src/sv_caller.cpp:572-591)
     std::unordered_map<uint32_t, std::vector<uint8_t>> seq4;

@@ -21,6 +21,7 @@ constexpr int kSortWarps = kSortThreads / 32;
 struct SortState {              // device
     uint32_t hist[16][256];     // digit histograms, then exclusive bases
     uint32_t trivial[16];       // 1 = all keys share this digit
+    uint32_t blocks_done;       // histogram CTAs that have added their share: the last one turns the counts into bases
 };
 
 __device__ __forceinline__ uint32_t key_digit(unsigned long long hi, unsigned long long lo, int d)
@@ -28,15 +29,27 @@ __device__ __forceinline__ uint32_t key_digit(unsigned long long hi, unsigned lo
     return d < 8 ? (uint32_t)(lo >> (8 * d)) & 255u : (uint32_t)(hi >> (8 * (d - 8))) & 255u;
 }
 
+// Histogram of every digit + (last CTA to finish) exclusive bases and triviality per digit: one launch.  Optionally the
+// first kernel of a pipeline whose element count is still raw: n = min(*n_raw, clamp_cap) is published to *n_clamped_out
+// (block 0) for the kernels that follow, and val[i] = i is written along the way (payload = original position).
 __global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ lo,
-                                                   const uint32_t* n_dev, uint64_t n_host, uint32_t digit_mask, SortState* st)
+                                                   const uint32_t* n_dev, uint64_t n_host, uint32_t digit_mask, SortState* st,
+                                                   const uint32_t* n_raw, uint32_t clamp_cap, uint32_t* n_clamped_out, uint32_t* iota_val)
 {
     __shared__ uint32_t s_h[16][256];
-    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
+    __shared__ uint32_t s_scan[40];
+    __shared__ bool s_last;
+    uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
+    if (n_raw) {
+        const uint32_t r = *n_raw;
+        n = r < clamp_cap ? r : clamp_cap;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *n_clamped_out = (uint32_t)n;
+    }
     for (int i = threadIdx.x; i < 16 * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const unsigned long long l = lo[i], h = hi ? hi[i] : 0ull;
+        if (iota_val) iota_val[i] = (uint32_t)i;
 #pragma unroll
         for (int d = 0; d < 16; d++)
             if ((digit_mask >> d) & 1u) atomicAdd(&s_h[d][key_digit(h, l, d)], 1u);
@@ -46,19 +59,19 @@ __global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __r
         uint32_t v = (&s_h[0][0])[i];
         if (v) atomicAdd(&(&st->hist[0][0])[i], v);
     }
-}
-
-// one CTA of 256 threads: per digit, exclusive scan of the 256 bins + triviality
-__global__ void __launch_bounds__(256) k_sort_bases(const uint32_t* n_dev, uint64_t n_host, uint32_t digit_mask, SortState* st)
-{
-    __shared__ uint32_t s_scan[40];
-    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
+    // last CTA done: per digit, exclusive scan of the 256 bins + triviality
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     for (int d = 0; d < 16; d++) {
         if (!((digit_mask >> d) & 1u)) { if (threadIdx.x == 0) st->trivial[d] = 1; continue; }
-        uint32_t c = st->hist[d][threadIdx.x];
+        const uint32_t c = ld_volatile_u32(&st->hist[d][threadIdx.x]);
         uint32_t tot;
-        uint32_t ex = block_excl_scan_u32(c, s_scan, &tot);
-        int triv = __syncthreads_or(c == (uint32_t)n && n > 0);
+        const uint32_t ex = block_excl_scan_u32(c, s_scan, &tot);
+        const int triv = __syncthreads_or(c == (uint32_t)n && n > 0);
         st->hist[d][threadIdx.x] = ex;
         if (threadIdx.x == 0) st->trivial[d] = (triv || n < 2) ? 1u : 0u;
     }
@@ -130,12 +143,27 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const PassParams P)
         if (t == 0) st_volatile_u64(my, lb_pack(P.epoch, kFlagPrefix, run));
         else {
             st_volatile_u64(my, lb_pack(P.epoch, kFlagAgg, run));
-            for (int64_t p = (int64_t)t - 1; p >= 0; p--) {
-                const unsigned long long* q = P.status + (size_t)p * 256 + tid;
-                unsigned long long wv; uint32_t flag;
-                do { wv = ld_volatile_u64(q); uint32_t h = (uint32_t)(wv >> 32); flag = ((h >> 2) == P.epoch) ? (h & 3u) : 0u; } while (flag == 0);
-                excl += (uint32_t)wv;
-                if (flag == kFlagPrefix) break;
+            // The chain is walked kLook predecessors at a time: their words are loaded together (independent loads, one
+            // round trip to L2) and consumed in order; a word that is not published yet is polled on its own.  Walking
+            // one word per round trip made every pass cost (tiles in flight) x (L2 latency).
+            constexpr int kLook = 8;
+            bool done = false;
+            for (int64_t p = (int64_t)t - 1; p >= 0 && !done; p -= kLook) {
+                unsigned long long wv[kLook];
+#pragma unroll
+                for (int u = 0; u < kLook; u++) wv[u] = p - u >= 0 ? ld_volatile_u64(P.status + (size_t)(p - u) * 256 + tid) : 0ull;
+#pragma unroll
+                for (int u = 0; u < kLook; u++) {
+                    if (done || p - u < 0) continue;
+                    uint32_t h = (uint32_t)(wv[u] >> 32);
+                    uint32_t flag = ((h >> 2) == P.epoch) ? (h & 3u) : 0u;
+                    while (flag == 0) {
+                        wv[u] = ld_volatile_u64(P.status + (size_t)(p - u) * 256 + tid);
+                        h = (uint32_t)(wv[u] >> 32); flag = ((h >> 2) == P.epoch) ? (h & 3u) : 0u;
+                    }
+                    excl += (uint32_t)wv[u];
+                    if (flag == kFlagPrefix) done = true;
+                }
             }
             st_volatile_u64(my, lb_pack(P.epoch, kFlagPrefix, excl + run));
         }
@@ -171,7 +199,7 @@ __global__ void k_sort_normalize(const PassParams P, int n_digits)
     }
 }
 
-int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32_t* n_dev, uint32_t digit_mask)
+int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32_t* n_dev, uint32_t digit_mask, const SortFirst* first)
 {
     if (n_upper >= (1ull << 30)) { set_error("radix sort: %llu keys exceed the 2^30 limit", (unsigned long long)n_upper); return CSV_ERR_LIMIT; }
     const bool has_hi = bufs.hi != nullptr;
@@ -186,9 +214,9 @@ int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32
     uint32_t grid_h = (uint32_t)((n_upper + 255) / 256);
     if (grid_h > (uint32_t)ctx->sm_count * grid_mult(ctx, 8)) grid_h = ctx->sm_count * grid_mult(ctx, 8);
     if (grid_h == 0) grid_h = 1;
-    k_sort_hist<<<grid_h, 256, 0, ctx->stream>>>(bufs.hi, bufs.lo, n_dev, n_upper, digit_mask, st);
-    k_sort_bases<<<1, 256, 0, ctx->stream>>>(n_dev, n_upper, digit_mask, st);
-    ctx->launches += 2;
+    k_sort_hist<<<grid_h, 256, 0, ctx->stream>>>(bufs.hi, bufs.lo, n_dev, n_upper, digit_mask, st, first ? first->n_raw : nullptr, first ? first->clamp_cap : 0u,
+                                                 first ? first->n_clamped_out : nullptr, first && first->iota ? bufs.val : nullptr);
+    ctx->launches++;
     PassParams P;
     P.hi[0] = bufs.hi; P.hi[1] = bufs.hi2; P.lo[0] = bufs.lo; P.lo[1] = bufs.lo2; P.val[0] = bufs.val; P.val[1] = bufs.val2;
     P.n_dev = n_dev; P.n_host = n_upper; P.st = st;

@@ -16,18 +16,6 @@
 
 namespace csv {
 
-__global__ void k_sig_clamp(uint32_t* scalars, uint32_t cap)
-{
-    const uint32_t n = scalars[SC_N_SIG];
-    scalars[SC_N_SIG_EFF] = n < cap ? n : cap;
-}
-
-__global__ void k_sig_iota(uint32_t* val, const uint32_t* scalars)
-{
-    const uint32_t n = scalars[SC_N_SIG_EFF];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) val[i] = i;
-}
-
 // position of every entry inside its run of equal hi = number of entries of the run with a smaller lo
 __global__ void k_sig_tiefix(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ raw_lo, const uint32_t* __restrict__ val,
                              const uint32_t* scalars, uint32_t* out)
@@ -52,7 +40,7 @@ struct GatherParams {
     const unsigned long long *hi, *lo;      // hi: sorted; lo: emission order (indexed by slot)
     const uint32_t* val;
     const uint32_t* raw_k;
-    const WalkAgg *span_pre, *chunk_agg;      // pre-pass prefixes: .qry = query consumed since the last record head before the span
+    const uint2* span_rq;                   // pre-pass: {reference, query} consumed since the last record head before the span
     const uint8_t* raw_kind;
     const uint32_t* ne_idx;
     const unsigned long long* cig_off;
@@ -89,10 +77,10 @@ __global__ void k_sig_gather(const GatherParams P)
         unsigned long long from = c0;
         uint32_t q = 0, pos = m.x;
         if (c0 < span_op0) {
-            const WalkAgg ch = P.chunk_agg[sp / (uint32_t)kSpanChunk], pr = P.span_pre[sp];
-            const uint32_t ref_pre = pr.heads ? pr.ref : ch.ref + pr.ref;
+            const uint2 rq = P.span_rq[sp];
+            const uint32_t ref_pre = rq.x;
             if (!exact || m.x + ref_pre + 1u < m.y) {
-                q = pr.heads ? pr.qry : ch.qry + pr.qry;
+                q = rq.y;
                 pos = m.x + ref_pre;
                 from = span_op0;
             }
@@ -121,9 +109,6 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
     const uint32_t cap = (uint32_t)b->sig_cap;
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
     uint32_t grid = ctx->sm_count * grid_mult(ctx, 4);
-    k_sig_clamp<<<1, 1, 0, ctx->stream>>>(scalars, cap);
-    k_sig_iota<<<grid, 256, 0, ctx->stream>>>(b->d_sig_payload.as<uint32_t>(), scalars);
-    ctx->launches += 2;
     CSV_TRY(ctx->sort_tmp[1].ensure((size_t)cap * 8));
     CSV_TRY(ctx->sort_tmp[3].ensure((size_t)cap * 4));
     SortBufs sb;
@@ -132,13 +117,14 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
     sb.val = b->d_sig_payload.as<uint32_t>(); sb.val2 = ctx->sort_tmp[3].as<uint32_t>();
     uint32_t mask = 0x0fu;                                                       // start
     for (int d = 0; d < 4; d++) if (d == 0 ? b->n_regions > 1 : (b->n_regions >> (8 * d))) mask |= 1u << (4 + d);   // owner region
-    // n_dev is clamped inside the kernels through cap: pass the upper bound and the device count
-    CSV_TRY(radix_sort_pairs(ctx, sb, cap, scalars + SC_N_SIG_EFF, mask));
+    // the sort's first kernel clamps the emitted count to the capacity (SC_N_SIG_EFF) and numbers the entries
+    const SortFirst first = {scalars + SC_N_SIG, cap, scalars + SC_N_SIG_EFF, true};
+    CSV_TRY(radix_sort_pairs(ctx, sb, cap, scalars + SC_N_SIG_EFF, mask, &first));
     k_sig_tiefix<<<grid, 256, 0, ctx->stream>>>(sb.lo, b->d_sig_lo.as<unsigned long long>(), sb.val, scalars, sb.val2);
     ctx->launches++;
     GatherParams P;
     P.hi = sb.lo; P.lo = b->d_sig_lo.as<unsigned long long>(); P.val = sb.val2;
-    P.raw_k = b->d_sig_k.as<uint32_t>(); P.span_pre = b->d_span_pre.as<WalkAgg>(); P.chunk_agg = b->d_span_status.as<WalkAgg>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
+    P.raw_k = b->d_sig_k.as<uint32_t>(); P.span_rq = b->d_span_rq.as<uint2>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
     P.ne_idx = b->d_ne_idx.as<uint32_t>(); P.cig_off = b->d_cig_off.as<unsigned long long>(); P.cigar = b->d_cigar.as<uint32_t>();
     P.meta = b->d_meta.as<uint4>(); P.tids = b->d_tids.as<TidDev>(); P.scalars = scalars; P.cap = cap;
     P.o_start = b->d_out_start.as<uint32_t>(); P.o_end = b->d_out_end.as<uint32_t>(); P.o_read = b->d_out_read.as<uint32_t>();

@@ -38,6 +38,13 @@ struct WalkParams {
     uint32_t span_base;         // first span of this launch (the scan is pipelined in chunks of spans)
     uint32_t span_end;          // one past the last span of this launch
     uint4* span_desc;           // per span {record running in (may be -1), first event slot, ref consumed since the last head, records touched}
+    uint2* span_rq;             // per span {reference, query} consumed since the last record head before the span (k_sig_gather)
+    // record-level pre-pass (host supplied the D/N count of every record, csv_reads::n_gap)
+    const uint32_t* n_gap;      // [n_reads] or null
+    const unsigned long long* cig_off;
+    const uint32_t* ne_idx;     // compact index -> record index
+    uint32_t ev_given;          // ev_start[] comes from the record scan: the walk leaves what it finds in ev_check[] instead
+    uint32_t* ev_check;         // [n_nonempty + 1] event slot the walk reached at the end of every record (compared by k_pmax_chained)
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
@@ -243,8 +250,18 @@ __global__ void __launch_bounds__(256) k_span_finalize(const WalkParams P)
     const uint32_t s = P.span_base + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.span_end) return;
     const WalkAgg e = combine(P.chunk_agg[s / kSpanChunk], P.span_pre[s]);
-    P.span_desc[s] = make_uint4(e.heads - 1u, e.ev, e.ref, P.span_agg[s].heads + 1u);
+    P.span_desc[s] = make_uint4(e.heads - 1u, e.ev, e.ref, 0u);
+    P.span_rq[s] = make_uint2(e.ref, e.qry);
+    // the walk reads a span's descriptor together with its successor's (.x): close the last span of this launch
+    if (s + 1u == P.span_end) P.span_desc[s + 1u] = make_uint4(e.heads + P.span_agg[s].heads - 1u, 0u, 0u, 0u);
 }
+
+// ---- record-level pre-pass (launch_walk): a span's carry-in only concerns the ONE record that runs into it.  The events
+// before the span are sum(2 + 2 gaps) over whole records plus the started part of that record; reference / query
+// consumed since its head are a walk over that record's ops up to the span start.  With the D/N count of every record
+// from the host packer (csv_reads::n_gap; the packer touches every op anyway) the pre-pass is ONE chained scan over
+// RECORDS (16 bytes each) in which the record that crosses a span start also walks its own first ops (a few dozen for
+// HiFi), instead of a second pass over every CIGAR word plus a three-launch span scan.
 
 // ---- TMA bulk copies (global -> shared, completion on an mbarrier): the walk is a persistent kernel whose next
 // span is in flight while the current one is processed; no registers are spent on the prefetch.
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
 {
     __shared__ __align__(128) uint32_t s_ops[2][kWalkSpan];                  // CIGAR words of the span in hand and of the next one
     __shared__ __align__(16) uint8_t s_hb[2][kWalkSpan / 8 + 16];            // their head bits (+ the byte that follows)
-    __shared__ __align__(16) uint4 s_desc[2];                                // their span descriptors
+    __shared__ __align__(16) uint4 s_desc[2][2];                             // their span descriptors, each with its successor's
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_pos1_[2][kWalkSpan + 4];                           // first depth index of the span's records       } double-buffered by
     __shared__ uint4 s_wagg_[2][kWalkThreads / 32];                          // {heads << 16 | events, ref total, ref since   } span parity: one CTA
@@ -309,10 +326,10 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
         const uint32_t o0 = span * (uint32_t)kWalkSpan;
         const uint32_t n = P.n_ops - o0 < (uint32_t)kWalkSpan ? P.n_ops - o0 : (uint32_t)kWalkSpan;
         const uint32_t bytes_ops = (n * 4u + 15u) & ~15u, bytes_hb = kWalkSpan / 8 + 16;
-        mbar_expect_tx(&s_bar[buf], bytes_ops + bytes_hb + 16u);
+        mbar_expect_tx(&s_bar[buf], bytes_ops + bytes_hb + 32u);
         tma_bulk_g2s(s_ops[buf], P.cigar + o0, bytes_ops, &s_bar[buf]);
         tma_bulk_g2s(s_hb[buf], P.headbits + (o0 >> 3), bytes_hb, &s_bar[buf]);
-        tma_bulk_g2s(&s_desc[buf], P.span_desc + span, 16u, &s_bar[buf]);
+        tma_bulk_g2s(&s_desc[buf][0], P.span_desc + span, 32u, &s_bar[buf]);
     };
     if (tid == 0) {
         mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
@@ -331,8 +348,8 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
         uint4* const s_wagg = s_wagg_[buf];
         mbar_wait(&s_bar[buf], (it >> 1) & 1u);
         const uint32_t g0 = span * (uint32_t)kWalkSpan + tid * kWalkOpsPerThread;
-        const uint4 desc = s_desc[buf];
-        const uint32_t k_first = desc.x, n_rec = desc.w;
+        const uint4 desc = s_desc[buf][0];
+        const uint32_t k_first = desc.x, n_rec = s_desc[buf][1].x - desc.x + 1u;   // record heads inside the span + the record running in
         // first index of record k_first + tid: the load is issued here and consumed after the scans
         uint32_t my_p1 = kDeadPos;
         const uint32_t my_k = k_first + tid;                                 // wraps for the span that starts the batch (k_first == -1)
@@ -454,7 +471,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                         if (ie - p1 >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
                         P.events[slot - 1u] = ie;
                         P.ref_end[kt] = p1 != kDeadPos ? ie : 0u;            // not clipped to the map: only compared with tile starts
-                        P.ev_start[kt + 1u] = slot;
+                        (P.ev_given ? P.ev_check : P.ev_start)[kt + 1u] = slot;   // given: k_pmax_chained compares the two
                     }
                     if (b < t.n_valid) {
                         klb++;
@@ -499,13 +516,68 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     P.sig.kind = b->d_sig_kind.as<uint8_t>();
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
-    if (span0 == 0) CSV_CUDA(cudaMemsetAsync(b->d_scan_carry.p, 0, sizeof(WalkAgg), ctx->stream));
+    P.span_rq = b->d_span_rq.as<uint2>();
+    P.n_gap = b->d_n_gap.as<uint32_t>();
+    P.cig_off = b->d_cig_off.as<unsigned long long>();
+    P.ne_idx = b->d_ne_idx.as<uint32_t>();
+    P.ev_given = b->rec_prepass ? 1u : 0u;
+    P.ev_check = b->d_ev_check.as<uint32_t>();
     const uint32_t n = span1 - span0;
-    const uint32_t sc0 = span0 / kSpanChunk, sc1 = (span1 + kSpanChunk - 1) / kSpanChunk;
-    k_span_agg<<<n, kWalkThreads, 0, ctx->stream>>>(P);
-    k_span_scan_local<<<sc1 - sc0, 256, 0, ctx->stream>>>(P, sc0);
-    k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, sc0, sc1, b->d_scan_carry.as<WalkAgg>());
-    k_span_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P);
+    if (b->rec_prepass) {
+        // record-level pre-pass, once per pass (not per pipeline chunk)
+        if (span0 == 0) {
+            const WalkParams Q = P;
+            const uint32_t* n_rec = P.scalars + SC_N_NONEMPTY;
+            auto in = [=] __device__(uint64_t k) -> uint32_t {
+                const uint32_t i = Q.ne_idx[k];
+                const uint32_t ops = (uint32_t)(Q.cig_off[i + 1] - Q.cig_off[i]), g = Q.n_gap[i];
+                return 2u + 2u * (g < ops ? g : ops);                       // clamped: event slots stay inside the event array whatever the caller claims
+            };
+            auto out = [=] __device__(uint64_t k, uint32_t ex, uint32_t v) {
+                const uint32_t i = Q.ne_idx[k];
+                Q.ev_start[k] = ex;
+                const unsigned long long o0 = Q.cig_off[i], o1 = Q.cig_off[i + 1];
+                const uint32_t s_lo = (uint32_t)(o0 / kWalkSpan) + 1u, s_hi = (uint32_t)(o1 / kWalkSpan);
+                if (k == 0) { Q.span_desc[0] = make_uint4(0xffffffffu, 0u, 0u, 0u); Q.span_rq[0] = make_uint2(0u, 0u); }
+                if (s_lo <= s_hi) {
+                    // span starts B with o0 < B <= o1: this record runs into them (or ends right there)
+                    uint32_t ref = 0, qry = 0, gaps = 0;
+                    unsigned long long o = o0;
+                    for (uint32_t s = s_lo; s <= s_hi; s++) {
+                        const unsigned long long B = (unsigned long long)s * kWalkSpan;
+                        for (; o + 4 <= B; o += 4) {                        // four independent loads in flight
+                            const uint32_t w0 = Q.cigar[o], w1 = Q.cigar[o + 1], w2 = Q.cigar[o + 2], w3 = Q.cigar[o + 3];
+                            const uint32_t r0 = (kRefMask >> (w0 & 15u)) & 1u, r1 = (kRefMask >> (w1 & 15u)) & 1u, r2 = (kRefMask >> (w2 & 15u)) & 1u, r3 = (kRefMask >> (w3 & 15u)) & 1u;
+                            const uint32_t q0 = (kQryMask >> (w0 & 15u)) & 1u, q1 = (kQryMask >> (w1 & 15u)) & 1u, q2 = (kQryMask >> (w2 & 15u)) & 1u, q3 = (kQryMask >> (w3 & 15u)) & 1u;
+                            ref += r0 * (w0 >> 4) + r1 * (w1 >> 4) + r2 * (w2 >> 4) + r3 * (w3 >> 4);
+                            qry += q0 * (w0 >> 4) + q1 * (w1 >> 4) + q2 * (w2 >> 4) + q3 * (w3 >> 4);
+                            gaps += (r0 & ~q0) + (r1 & ~q1) + (r2 & ~q2) + (r3 & ~q3);
+                        }
+                        for (; o < B; o++) {
+                            const uint32_t w = Q.cigar[o], r = (kRefMask >> (w & 15u)) & 1u, q = (kQryMask >> (w & 15u)) & 1u;
+                            ref += r * (w >> 4); qry += q * (w >> 4); gaps += r & ~q;
+                        }
+                        // head event of this record, two per D/N op so far, and its tail event if it ends right at the span start
+                        Q.span_desc[s] = make_uint4((uint32_t)k, ex + 1u + 2u * gaps + (B == o1 ? 1u : 0u), ref, 0u);
+                        Q.span_rq[s] = make_uint2(ref, qry);
+                    }
+                }
+                if (k + 1 == (uint64_t)*n_rec) {
+                    Q.ev_start[k + 1] = ex + v;
+                    if (s_hi != Q.n_spans) Q.span_desc[Q.n_spans] = make_uint4((uint32_t)k, 0u, 0u, 0u);      // sentinel: closes the last span
+                }
+            };
+            CSV_TRY(chained_scan(ctx, in, out, b->n_reads, n_rec, nullptr));
+        }
+    } else {
+        if (span0 == 0) CSV_CUDA(cudaMemsetAsync(b->d_scan_carry.p, 0, sizeof(WalkAgg), ctx->stream));
+        const uint32_t sc0 = span0 / kSpanChunk, sc1 = (span1 + kSpanChunk - 1) / kSpanChunk;
+        k_span_agg<<<n, kWalkThreads, 0, ctx->stream>>>(P);
+        k_span_scan_local<<<sc1 - sc0, 256, 0, ctx->stream>>>(P, sc0);
+        k_span_scan_chunks<<<1, 1024, 0, ctx->stream>>>(P, sc0, sc1, b->d_scan_carry.as<WalkAgg>());
+        k_span_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P);
+        ctx->launches += 4;
+    }
     static const int minb = getenv("CSV_WALK_MINB") ? atoi(getenv("CSV_WALK_MINB")) : 4;    // tuning knob: CTAs per SM the compiler targets
     static const int gmul = getenv("CSV_WALK_GRID") ? atoi(getenv("CSV_WALK_GRID")) : 128;   // CTAs per SM in the grid (8 resident): each walks ~10-20 spans, the next one prefetched
     const uint32_t per_sm = (uint32_t)(minb == 5 || minb == 6 ? minb : 4);
@@ -517,7 +589,7 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
         else k_walk<true, true, 4><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
     } else if (p->want_depth) k_walk<true, false, 4><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
     else k_walk<false, true, 4><<<grid, kWalkThreads, 0, ctx->stream>>>(P);
-    ctx->launches += 5;
+    ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }

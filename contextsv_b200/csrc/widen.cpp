@@ -1,8 +1,11 @@
-// widen.cpp -- host half of the narrow depth fetch (fetch.cu): u8 -> u32 with non-temporal stores.
+// widen.cpp -- host-only helpers of the C ABI: the host half of the narrow depth fetch (fetch.cu): u8 -> u32 with
+// non-temporal stores, and the per-record D/N count a packer hands over in csv_reads::n_gap.
 // Plain g++ translation unit (no CUDA): the AVX2 body is selected at run time.
 #include <cstddef>
 #include <cstdint>
 #include <immintrin.h>
+#include <thread>
+#include <vector>
 
 #include "contextsv_b200.h"
 
@@ -37,4 +40,23 @@ extern "C" void csv_host_widen_u8(const uint8_t* src, uint32_t* dst, size_t n)
 {
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
     if (have_avx2) widen_avx2(src, dst, n); else widen_scalar(src, dst, n);
+}
+
+extern "C" void csv_host_count_gaps(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, int threads)
+{
+    if (!cigar || !cig_off || !n_gap_out || n_reads == 0) return;
+    auto work = [=](uint32_t r0, uint32_t r1) {
+        for (uint32_t r = r0; r < r1; r++) {
+            uint32_t g = 0;
+            for (uint64_t o = cig_off[r]; o < cig_off[r + 1]; o++) { const uint32_t op = cigar[o] & 15u; g += (op == 2u) | (op == 3u); }   // BAM_CDEL, BAM_CREF_SKIP
+            n_gap_out[r] = g;
+        }
+    };
+    unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > n_reads / 4096u + 1u) nt = n_reads / 4096u + 1u;
+    if (nt == 1) { work(0, n_reads); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++) pool.emplace_back(work, (uint32_t)((uint64_t)n_reads * t / nt), (uint32_t)((uint64_t)n_reads * (t + 1) / nt));
+    for (auto& th : pool) th.join();
 }

@@ -17,19 +17,49 @@ GRCH38 = [
 ]
 
 
-def plan_regions(contig_len, n_shards):
-    """Cuts the concatenated depth-map index space (sum of L+1) into n_shards contiguous pieces of
-    (almost) equal length.  Returns a list (one entry per shard) of lists of (tid, beg, end, map_size)."""
+OP_COST = 4.7     # cost of one CIGAR op in units of one depth position (B200: walk 3.5 ps/op, depth tiles 0.73 ps/position)
+
+
+def plan_regions(contig_len, n_shards, reads=None, op_cost=OP_COST):
+    """Cuts the concatenated depth-map index space (sum of L+1) into n_shards contiguous pieces of (almost) equal COST
+    = positions + op_cost * CIGAR ops of the records that start there (sum(bases + c * ops)); without
+    `reads` the pieces have equal length.  Uniform HiFi coverage makes the two the same; ONT-dense or SV-rich stretches
+    move the cuts.  Cuts may fall anywhere inside a contig.  Returns a list (one entry per shard) of lists of
+    (tid, beg, end, map_size)."""
     sizes = [int(l) + 1 for l in contig_len]
     total = sum(sizes)
-    bounds = [(total * k) // n_shards for k in range(n_shards + 1)]
+    base_of = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    if reads is None or int(reads["n_reads"]) == 0 or n_shards == 1:
+        bounds = [(total * k) // n_shards for k in range(n_shards + 1)]
+    else:
+        n = int(reads["n_reads"])
+        tid = np.zeros(n, np.int64) if reads.get("tid") is None else np.asarray(reads["tid"]).astype(np.int64)
+        ok = (tid >= 0) & (tid < len(sizes))
+        t_ok = np.where(ok, tid, 0)
+        # concatenated depth index of every record start (clipped into its contig), non-decreasing for sorted records
+        x = base_of[t_ok] + np.clip(np.asarray(reads["pos0"]).astype(np.int64) + 1, 0, np.asarray(sizes, np.int64)[t_ok] - 1)
+        x = np.maximum.accumulate(np.where(ok, x, 0))
+        ops_before = np.asarray(reads["cig_off"]).astype(np.int64)[:n]          # ops of the records before record j
+        f = x.astype(np.float64) + op_cost * ops_before                            # cost of everything left of record j's start
+        f_total = float(total) + op_cost * float(int(reads["n_ops"]))
+        bounds = [0]
+        for k in range(1, n_shards):
+            target = f_total * k / n_shards
+            j = int(np.searchsorted(f, target, side="left"))
+            if j >= n:
+                cut = int(min(total, max(bounds[-1], total - (f_total - target))))   # past the last record: positions only
+            else:
+                # between record j-1 and record j only positions add cost: step back from record j's start
+                cut = int(x[j] - min(f[j] - target, float(x[j] - (x[j - 1] if j else 0))))
+            bounds.append(min(max(cut, bounds[-1]), total))
+        bounds.append(total)
     shards = [[] for _ in range(n_shards)]
     base = 0
-    for tid, size in enumerate(sizes):
+    for tid_, size in enumerate(sizes):
         for k in range(n_shards):
             lo, hi = max(bounds[k], base), min(bounds[k + 1], base + size)
             if lo < hi:
-                shards[k].append((tid, lo - base, hi - base, size))
+                shards[k].append((tid_, lo - base, hi - base, size))
         base += size
     return shards
 
@@ -79,6 +109,8 @@ def select_reads(reads, regions, ends=None):
         "pos0": reads["pos0"][i0:i1], "flag": reads["flag"][i0:i1], "mapq": reads["mapq"][i0:i1],
         "cig_off": (off[i0:i1 + 1] - np.uint64(o0)).astype(np.uint64), "cigar": reads["cigar"][o0:o1],
     }
+    if reads.get("n_gap") is not None:
+        sub["n_gap"] = reads["n_gap"][i0:i1]
     return sub, i0
 
 
@@ -139,21 +171,38 @@ def plan_by_ops(reads, contig_len, max_ops, ends=None):
     return shards
 
 
-def merge_signatures(parts):
+SIG_FIELDS = ("start", "end", "kind", "read_idx", "op_idx", "query_pos")
+
+
+def merge_signatures(parts, extra=()):
     """parts: list of (sigs dict from Batch.sigs(), regions, read index offset) per shard, in genome order.
-    Returns one dict per contig id in the reference's vector order (start, end, reverse insertion order)."""
+    Returns one dict per contig id in the reference's vector order (start, end, reverse insertion order).
+    Every shard's run is already in that order and record indices grow with the shard, so the merge is one stable
+    sort by (start, end) over the runs concatenated in REVERSE shard order: equal keys keep "later record first".
+    Contigs that live in one region are passed through untouched (out[tid]["n_parts"] == 1).  `extra` names further
+    per-signature arrays of the sigs dicts (labels, depths) to carry along."""
+    fields = SIG_FIELDS + tuple(extra)
     per_tid = {}
     for sg, regions, base in parts:
         for r, (tid, _, _, _) in enumerate(regions):
             lo, hi = int(sg["region_off"][r]), int(sg["region_off"][r + 1])
-            d = per_tid.setdefault(tid, {k: [] for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")})
-            for k in d:
-                v = sg[k][lo:hi]
-                d[k].append(v.astype(np.int64) + base if k == "read_idx" else v)
+            per_tid.setdefault(tid, []).append({k: (sg[k][lo:hi].astype(np.int64) + base if k == "read_idx" else sg[k][lo:hi]) for k in fields})
     out = {}
-    for tid, d in per_tid.items():
-        m = {k: np.concatenate(v) if v else np.zeros(0) for k, v in d.items()}
-        seq = m["read_idx"].astype(np.int64) * (1 << 31) + m["op_idx"].astype(np.int64)
-        order = np.lexsort((-seq, m["end"], m["start"]))
-        out[tid] = {k: v[order] for k, v in m.items()}
+    for tid, runs in per_tid.items():
+        runs = [x for x in runs if len(x["start"])] or runs[:1]
+        if len(runs) == 1:
+            m = dict(runs[0])
+        else:
+            in_order = all(int(a["read_idx"].max()) < int(b["read_idx"].min()) for a, b in zip(runs, runs[1:]))
+            if in_order:
+                m = {k: np.concatenate([x[k] for x in reversed(runs)]) for k in fields}
+                key = (m["start"].astype(np.uint64) << np.uint64(32)) | m["end"].astype(np.uint64)
+                order = np.argsort(key, kind="stable")
+            else:                 # runs that interleave (regions handed over out of genome order): the full comparator
+                m = {k: np.concatenate([x[k] for x in runs]) for k in fields}
+                seq = m["read_idx"].astype(np.int64) * (1 << 31) + m["op_idx"].astype(np.int64)
+                order = np.lexsort((-seq, m["end"], m["start"]))
+            m = {k: v[order] for k, v in m.items()}
+        m["n_parts"] = len(runs)
+        out[tid] = m
     return out

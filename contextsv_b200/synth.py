@@ -46,7 +46,7 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def generate(contig_len, params=None, alloc=None, **kw):
+def generate(contig_len, params=None, alloc=None, count_gaps=True, **kw):
     """Returns a dict of numpy arrays in the csv_reads layout.
 
     alloc(shape, dtype) -> ndarray lets the caller place the arrays in pinned memory.
@@ -63,5 +63,10 @@ def generate(contig_len, params=None, alloc=None, **kw):
                       _ptr(cig_off), C.byref(n_ops))
     cigar = alloc(max(int(n_ops.value), 1), np.uint32)
     L.csv_synth_cigar(C.byref(p), C.c_uint32(len(cl)), _ptr(cl), _ptr(cig_off), _ptr(cigar))
-    return {"n_reads": n, "n_ops": int(n_ops.value), "tid": tid, "pos0": pos0, "flag": flag, "mapq": mapq,
-            "cig_off": cig_off, "cigar": cigar[: int(n_ops.value)], "contig_len": cl}
+    r = {"n_reads": n, "n_ops": int(n_ops.value), "tid": tid, "pos0": pos0, "flag": flag, "mapq": mapq,
+         "cig_off": cig_off, "cigar": cigar[: int(n_ops.value)], "contig_len": cl}
+    if count_gaps:
+        # what a packer leaves in csv_reads::n_gap while it copies the CIGAR words: D / N ops per record
+        from . import _capi
+        r["n_gap"] = _capi.count_gaps(r, alloc)
+    return r

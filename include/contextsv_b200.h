@@ -95,6 +95,11 @@ typedef struct {
     const uint8_t*  mapq;      /* [n_reads] MAPQ                                       */
     const uint64_t* cig_off;   /* [n_reads+1] prefix offsets into cigar[]              */
     const uint32_t* cigar;     /* [n_ops] len<<4 | op                                  */
+    const uint32_t* n_gap;     /* [n_reads] optional (NULL = not counted): number of D / N ops (BAM_CDEL,   */
+                               /* BAM_CREF_SKIP) in each record's CIGAR.  The packer touches every op anyway; */
+                               /* with the counts the device finds where each record's depth events go from a  */
+                               /* scan over RECORDS instead of a second pass over every CIGAR word.  Checked   */
+                               /* against the CIGAR during the scan: a wrong count fails with CSV_ERR_ARG.    */
 } csv_reads;
 
 /* A slice [beg,end) of one contig's depth map.  Indices are those of the
@@ -122,6 +127,12 @@ typedef struct csv_batch csv_batch;
 int  csv_batch_upload(csv_ctx* ctx, const csv_reads* reads, uint32_t n_regions,
                       const csv_region* regions, csv_batch** out);
 void csv_batch_free(csv_ctx* ctx, csv_batch* b);
+
+/* Signature capacity of a batch.  Upload reserves max(2^20, n_ops / 16) entries (never more than n_ops); a pass that
+ * emits more fails with CSV_ERR_CAPACITY when its results are fetched (csv_sigs_count / csv_sigs_fetch report the
+ * number emitted in *n_out all the same).  Reserve that many and run the pass again: the reference's vector has no
+ * limit, so a caller must not drop calls.  csv_cigar_scan does this by itself. */
+int csv_batch_reserve_sigs(csv_ctx* ctx, csv_batch* b, uint64_t n_sigs);
 
 typedef struct {
     uint32_t min_len;      /* signature length threshold; reference: 50 (sv_caller.cpp:566)   */
@@ -214,21 +225,37 @@ uint64_t csv_largest_cluster(const int32_t* pts, const int32_t* labels, uint64_t
 /* Window depth sums for CNVCaller::querySNPRegion (cnv_caller.cpp:76-113):
  * integer sum and position count of each of the sample_size windows of
  * [start_pos,end_pos], read from a region's device-resident depth.  The
- * caller finishes with the same libm log2 as the reference. */
+ * caller finishes with the same libm log2 as the reference.  A region that
+ * is a slice of its contig returns its share (the positions inside [beg,end)):
+ * shares of the shards of one contig add up. */
 int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv,
                     const uint32_t* start_pos, const uint32_t* end_pos, int sample_size,
                     uint64_t* sum_out /* [n_sv*sample_size] */, uint32_t* count_out);
 
-/* SVCaller::getReadDepth (sv_caller.cpp:1332-1344) for many positions at once, read from a whole-contig region's
+/* SVCaller::getReadDepth (sv_caller.cpp:1332-1344) for many positions at once, read from a region's
  * device-resident depth: depth_out[i] == map[positions[i]], 0 beyond the map (the reference catches the out_of_range
- * and adds nothing).  With csv_window_sums this serves every consumer of the depth map -- its size, the log2 windows,
- * the VCF's DP / SUPPORT -- without the map crossing PCIe. */
+ * and adds nothing) and 0 outside the region's slice [beg,end).  With csv_window_sums this serves every consumer of
+ * the depth map -- its size, the log2 windows, the VCF's DP / SUPPORT -- without the map crossing PCIe. */
 int csv_depth_at(csv_ctx* ctx, csv_batch* b, uint32_t region, uint64_t n, const uint32_t* positions, uint32_t* depth_out);
+/* The same for (contig, position) pairs anywhere in the batch: the slice that holds each position is looked up on the
+ * device.  0xffffffff marks a position inside its contig that none of this batch's regions covers (another shard's). */
+int csv_depth_at_tid(csv_ctx* ctx, csv_batch* b, uint64_t n, const int32_t* tid, const uint32_t* positions, uint32_t* depth_out);
+/* ... and for every signature of the batch at its start (what saveToVCF asks for each call, sv_caller.cpp:1306), in
+ * csv_sigs_fetch order, without the positions leaving the device.  Same 0xffffffff convention. */
+int csv_sigs_depth(csv_ctx* ctx, csv_batch* b, uint32_t* depth_out, uint64_t cap);
+/* Position-weighted checksum of every region's depth slice: sum of depth[i] * mix64(tid << 32 | index) modulo 2^64
+ * (splitmix64 finaliser).  Additive: the checksums of the shards of a contig add up to the whole contig's, so a
+ * sharded run can be verified against a single-device run without the maps leaving the devices. */
+int csv_depth_checksum(csv_ctx* ctx, csv_batch* b, uint64_t* checksum_out /* [n_regions] */);
 
 /* Per-record summaries the split-read pass starts from (SVCaller::detectSVsFromSplitReads, sv_caller.cpp:150-162):
  * bam_endpos(b) and SVCaller::getAlignmentReadPositions(b) (sv_caller.cpp:663-690) for every record of the batch, in
  * csv_reads order.  Any output may be NULL.  The batch needs no scan first. */
 int csv_record_summary(csv_ctx* ctx, csv_batch* b, int32_t* endpos_out, int32_t* query_start_out, int32_t* query_end_out);
+
+/* Host helper for packers that fill csv_reads::n_gap after the fact: n_gap_out[i] = number of D / N ops of record i
+ * (threads = 0: all cores).  No device needed. */
+void csv_host_count_gaps(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, int threads);
 
 /* ------------------------------------------------------- synthetic inputs */
 

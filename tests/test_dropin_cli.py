@@ -17,7 +17,7 @@ REF_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 def run_cli(exe, d, out, extra=(), env=None):
     os.makedirs(out, exist_ok=True)
     cmd = [exe, "-b", d + "/x.bam", "-r", d + "/x.fa", "-s", d + "/snps.vcf", "-o", out, "--hmm", os.path.join(REF_DIR, "wgs.hmm")] + list(extra)
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180, env=dict(os.environ, **(env or {})))
     assert p.returncode == 0 and "ContextSV finished successfully!" in p.stdout, p.stdout[-2000:]
     with open(os.path.join(out, "output.vcf")) as f:
         return [l for l in f if not l.startswith("##fileDate")]

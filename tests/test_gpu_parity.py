@@ -160,6 +160,75 @@ def test_full_size_whole_genome_properties(ctx, oracle):
     b.free()
 
 
+def test_op_level_prepass_still_serves_records_without_gap_counts(ctx, oracle, monkeypatch):
+    """csv_reads::n_gap is optional.  Every other test hands it over (api.Batch counts the D / N ops like a packer
+    would) and takes the record-level pre-pass; here the field stays NULL and the op-level pre-pass (k_span_agg + span
+    scan) has to give the same bits -- adversarial CIGARs, empty records, multi-contig HiFi, pile-ups."""
+    monkeypatch.setattr(api, "COUNT_GAPS", False)
+    rng = np.random.default_rng(12)
+    for it in range(12):
+        clen = [int(rng.choice([300, 2500, 12000, 70000])) for _ in range(int(rng.integers(1, 4)))]
+        r = util.random_cigar_reads(rng, int(rng.integers(0, 400)), clen, n_tids=len(clen), weird=bool(it % 2), max_ops=int(rng.choice([3, 12, 40])))
+        assert r.get("n_gap") is None
+        check_contigs(ctx, oracle, r, clen)
+    clen = [1_500_000, 700_000, 50_000]
+    r = dict(util.synth_reads(clen, seed=5, n_sv=300, coverage=30.0, frac_len50=0.1))
+    r.pop("n_gap")
+    check_contigs(ctx, oracle, r, clen)
+
+
+def test_record_level_prepass(ctx, oracle):
+    """The record-level pre-pass (csv_reads::n_gap given): span starts inside, at the head of and right behind records,
+    records longer than several spans among short ones, empty CIGARs between real ones, records of gaps only, a batch of
+    exactly k * 1024 ops (the sentinel span), and a wrong count, which must be refused and never trusted."""
+    from oracle.oracle_py import make_reads
+    from contextsv_b200._capi import CsvError, count_gaps
+    rng = np.random.default_rng(5)
+    # (a) total ops an exact multiple of the span, records ending exactly at span starts
+    for n_ops_total, sizes in ((2048, (1024, 512, 512)), (3072, (1000, 24, 1024, 1, 1023)), (1024, (1024,)), (4096, (3000, 1096))):
+        pos, cig = [], []
+        p = 5
+        for sz in sizes:
+            ops = []
+            for j in range(sz):
+                ops.append((int(rng.integers(1, 4)), [M, D, I, N, EQ][int(rng.integers(0, 5))]))
+            pos.append(p); cig.append(ops); p += int(rng.integers(0, 50))
+        r = make_reads(np.array(pos, np.int32), cig)
+        assert int(r["n_ops"]) == n_ops_total
+        check_contigs(ctx, oracle, r, [20000])
+    # (b) long records among short ones, empty records, gap-only records
+    pos, cig = [], []
+    p = 0
+    for i in range(600):
+        kind = i % 7
+        if kind == 0:
+            ops = [(int(rng.integers(1, 30)), [M, D, I, S, N, X][int(rng.integers(0, 6))]) for _ in range(int(rng.integers(1500, 4000)))]
+        elif kind == 1:
+            ops = []
+        elif kind == 2:
+            ops = [(int(rng.integers(1, 9)), D), (3, N)]
+        else:
+            ops = [(int(rng.integers(1, 70)), [M, D, I, S][int(rng.integers(0, 4))]) for _ in range(int(rng.integers(1, 90)))]
+        pos.append(p); cig.append(ops); p += int(rng.integers(0, 400))
+    r = make_reads(np.array(pos, np.int32), cig, flag=rng.choice([0, 16, 0x800, 0x100], 600).astype(np.uint16), mapq=rng.choice([0, 60], 600).astype(np.uint8))
+    assert int(r["n_ops"]) <= 1024 * 600
+    check_contigs(ctx, oracle, r, [p + 50000])
+    # (c) a wrong count is reported, whichever way it is wrong
+    r = dict(util.synth_reads([400_000], seed=9, n_sv=40, coverage=20.0))
+    good = count_gaps(r)
+    assert np.array_equal(good, r["n_gap"]) and good.sum() > 0
+    for delta in (1, -1, 1000):
+        bad = dict(r); g = good.astype(np.int64).copy()
+        nzi = np.nonzero(g > 0)[0]
+        victim = int(nzi[len(nzi) // 3])
+        g[victim] = max(0, g[victim] + delta); bad["n_gap"] = g.astype(np.uint32)
+        b = run_batch(ctx, bad, api.whole_contig_regions([400_000]))
+        with pytest.raises(CsvError, match="n_gap"):
+            b.depth_stats()
+        b.free()
+    check_contigs(ctx, oracle, r, [400_000])
+
+
 def test_inputs_the_path_refuses(ctx):
     """Not silently wrong: unsorted records (the reference needs an indexed = sorted BAM) and a record that consumes
     2^31 reference bases (BAM positions are int32) are reported when results are fetched."""
