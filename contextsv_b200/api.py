@@ -162,6 +162,10 @@ class Batch:
         self._last_scan = p
         check(lib().csv_scan_run(self.ctx.h, self.h, C.byref(p)))
 
+    def release_inputs(self):
+        """Keeps only the results (depth slabs, signature columns, labels): csv_batch_release_inputs."""
+        check(lib().csv_batch_release_inputs(self.ctx.h, self.h))
+
     def depth_stats(self):
         n = len(self.regions)
         s = np.zeros(n, np.uint64); nz = np.zeros(n, np.uint32)

@@ -39,6 +39,7 @@ struct csv_batch {
     uint32_t last_min_len = 50;
     bool scanned = false, have_depth = false, have_sigs = false, have_labels = false;
     bool rec_prepass = false;                 // the caller supplied n_gap[] and records are short: record-level pre-pass (walk.cu)
+    bool inputs_released = false;             // csv_batch_release_inputs: only the results are left (depth slabs, signature columns, labels)
 
     // input SoA (device)
     csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar, d_n_gap;
@@ -70,6 +71,15 @@ struct csv_batch {
                               &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
         for (auto* b : all) b->release(pool);
+    }
+    // everything a pass reads or writes on the way to the results; what stays serves the depth consumers and the fetches
+    void release_inputs(csv::DevPool* pool) {
+        csv::DevBuf* in[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_span_rq, &d_ev_check, &d_meta, &d_key, &d_ne_idx, &d_headbits,
+                             &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds, &d_tickets,
+                             &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r,
+                             &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_kind, &d_sig_payload};
+        for (auto* b : in) b->release(pool);
+        inputs_released = true;
     }
 };
 

@@ -148,6 +148,7 @@ int csv_ctx_create(int device, csv_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (getenv("CSV_CHUNKS")) ctx->pipe_chunks = std::max(1, atoi(getenv("CSV_CHUNKS")));
     if (getenv("CSV_SIDE_GRID")) ctx->side_grid = std::max(0, atoi(getenv("CSV_SIDE_GRID")));
+    if (getenv("CSV_SIDE_CTAS")) ctx->side_ctas = std::max(0, atoi(getenv("CSV_SIDE_CTAS")));
     if (getenv("CSV_DB_SMALL")) ctx->db_small = atoi(getenv("CSV_DB_SMALL")) != 0;
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     // the signature kernels are many and tiny: with the highest priority their CTAs take the first slot a tile CTA frees
@@ -440,7 +441,9 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     }
     if (nt) CSV_CUDA(cudaMemcpyAsync(b->d_tile_desc.p, tile_desc.data(), nt * sizeof(uint4), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemsetAsync(b->d_pmax_part.p, 0, (nr / 2048 + 2) * 8, st));      // look-back status words of k_pmax_chained: epoch 0 == never published
-    CSV_CUDA(cudaStreamSynchronize(st));
+    // No synchronisation here: the tables above come from pageable temporaries, which cudaMemcpyAsync stages before it
+    // returns; the caller's SoA is either pageable (same) or pinned -- then the copies are in flight and the arrays must
+    // stay untouched until a call that waits for the stream (csv_ctx_sync, csv_depth_stats, any fetch).
     *out = b.release();
     return CSV_OK;
 }
@@ -453,9 +456,21 @@ void csv_batch_free(csv_ctx* ctx, csv_batch* b)
     delete b;
 }
 
+int csv_batch_release_inputs(csv_ctx* ctx, csv_batch* b)
+{
+    if (!ctx || !b) { set_error("csv_batch_release_inputs: null argument"); return CSV_ERR_ARG; }
+    if (b->inputs_released) return CSV_OK;
+    CSV_CUDA(cudaSetDevice(ctx->device));
+    CSV_TRY(side_join(ctx));
+    CSV_CUDA(cudaStreamSynchronize(ctx->stream));            // the pass may still be reading them
+    b->release_inputs(&ctx->pool);
+    return CSV_OK;
+}
+
 int csv_batch_reserve_sigs(csv_ctx* ctx, csv_batch* b, uint64_t n_sigs)
 {
     if (!ctx || !b) { set_error("csv_batch_reserve_sigs: null argument"); return CSV_ERR_ARG; }
+    if (b->inputs_released) { set_error("csv_batch_reserve_sigs: the batch's inputs were released"); return CSV_ERR_STATE; }
     if (n_sigs >= (1ull << 30)) { set_error("csv_batch_reserve_sigs: %llu signatures exceed the 2^30 limit", (unsigned long long)n_sigs); return CSV_ERR_LIMIT; }
     if (n_sigs <= b->sig_cap) return CSV_OK;
     CSV_CUDA(cudaSetDevice(ctx->device));
@@ -471,6 +486,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
 {
     if (!ctx || !b || !p) { set_error("csv_scan_run: null argument"); return CSV_ERR_ARG; }
     if (!p->want_depth && !p->want_sigs) { set_error("csv_scan_run: nothing requested"); return CSV_ERR_ARG; }
+    if (b->inputs_released) { set_error("csv_scan_run: the batch's inputs were released (csv_batch_release_inputs): only its results are left"); return CSV_ERR_STATE; }
     CSV_TRY(side_join(ctx));            // the previous pass's signature work may still be reading this batch
     cudaStream_t st = ctx->stream;
     b->last_min_len = p->min_len;

@@ -136,6 +136,7 @@ struct csv_ctx {
     std::vector<cudaEvent_t> ev_chunk;  // walk of chunk c finished (main stream)
     bool side_busy = false, tile_busy = false;
     int side_grid = 0;                  // CTAs per SM the side-stream kernels may take beside the tiles (0 = each kernel's own default)
+    int side_ctas = 0;                  // ... and in total per launch (0 = no cap): every CTA of a side kernel waits for a slot a tile CTA frees
     int pipe_chunks = 1;                // batches uploaded from now on are scanned in up to this many pipelined chunks of contigs
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
@@ -187,6 +188,12 @@ inline uint32_t grid_mult(const csv_ctx* ctx, uint32_t dflt)
 {
     if (ctx->stream == ctx->side_stream && ctx->side_grid > 0 && (uint32_t)ctx->side_grid < dflt) return (uint32_t)ctx->side_grid;
     return dflt;
+}
+// ... and the total a launch may take there (all side-stream kernels are grid-stride or ticket loops: any grid >= 1 is correct)
+inline uint32_t cap_grid(const csv_ctx* ctx, uint64_t grid)
+{
+    if (ctx->stream == ctx->side_stream && ctx->side_ctas > 0 && grid > (uint64_t)ctx->side_ctas) return (uint32_t)ctx->side_ctas;
+    return (uint32_t)grid;
 }
 // RAII stage timer: records an event pair around a pipeline stage when profiling is on.
 struct StageTimer {

@@ -216,7 +216,7 @@ int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, u
     P.run_min = s[8].as<uint32_t>(); P.rkeys = s[9].as<unsigned long long>(); P.rval = s[11].as<uint32_t>();
     P.cid = s[13].as<uint32_t>(); P.counters = s[14].as<uint32_t>();
     P.labels = d_labels; P.n_clusters = d_n_clusters;
-    const uint32_t grid = ctx->sm_count * grid_mult(ctx, 8);
+    const uint32_t grid = cap_grid(ctx, ctx->sm_count * grid_mult(ctx, 8));
     if (d_n_clusters) CSV_CUDA(cudaMemsetAsync(d_n_clusters, 0, sizeof(int32_t) * n_seg, ctx->stream));
     if (!(eps >= 0.0)) {
         P.E = -1;

@@ -11,7 +11,6 @@
 
 namespace csvhost {
 
-namespace {
 std::vector<int> device_list()
 {
     std::vector<int> v;
@@ -27,6 +26,7 @@ std::vector<int> device_list()
     if (v.empty()) v.push_back(0);
     return v;
 }
+namespace {
 std::atomic<unsigned> g_next{0};
 struct Holder {
     csv_ctx* ctx = nullptr;
@@ -44,7 +44,8 @@ struct Stats {
     {
         if (!on) return;
         static const char* names[STAT_COUNT] = {"calculateMeanChromosomeCoverage", "  csv_depth", "findCIGARSVs", "  csv_cigar_scan",
-                                                "DBSCAN1D::fit", "DBSCAN::fit", "csv_ctx_create", "CIGAR pass reused the depth pass's packing"};
+                                                "DBSCAN1D::fit", "DBSCAN::fit", "csv_ctx_create", "findCIGARSVs served by the depth pass", "  BAM decode + packing",
+                                                "log2 windows on the device", "getReadDepth on the device", "findSplitSVSignatures"};
         for (int i = 0; i < STAT_COUNT; i++)
             std::fprintf(stderr, "[contextsv_b200] %-34s %8llu calls %10.3f s %12llu items\n", names[i], calls[i], seconds[i], items[i]);
     }

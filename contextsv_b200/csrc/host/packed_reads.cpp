@@ -4,24 +4,51 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
 
 namespace csvhost {
 
-void PackedReads::append(const bam1_t* b, bool keep_seq)
+namespace {
+std::mutex g_alloc_m;
+void* (*g_alloc)(size_t) = nullptr;
+void (*g_release)(void*) = nullptr;
+void* heap_alloc(size_t n) { void* p = std::malloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
+void heap_release(void* p) { std::free(p); }
+}  // namespace
+
+void set_slab_allocator(void* (*alloc)(size_t), void (*release)(void*))
+{
+    std::lock_guard<std::mutex> lk(g_alloc_m);
+    g_alloc = alloc; g_release = release;
+}
+
+void* slab_alloc(size_t bytes, void (**release_out)(void*))
+{
+    void* (*a)(size_t); void (*r)(void*);
+    { std::lock_guard<std::mutex> lk(g_alloc_m); a = g_alloc; r = g_release; }
+    if (a && r) {
+        if (void* p = a(bytes)) { *release_out = r; return p; }       // pinned memory can run out: fall back to the heap
+    }
+    *release_out = heap_release;
+    return heap_alloc(bytes);
+}
+
+void PackedReads::append(const bam1_t* b, bool keep_seq, bool keep_name, uint64_t serial_no)
 {
     const uint32_t idx = (uint32_t)pos0.size();
     tid.push_back(b->core.tid);
     pos0.push_back((int32_t)b->core.pos);
     flag.push_back(b->core.flag);
     mapq.push_back(b->core.qual);
+    serial.push_back(serial_no);
     const uint32_t* c = bam_get_cigar(b);
     const uint32_t n = b->core.n_cigar;
+    cigar.append(c, n);                                     // one copy of the record's CIGAR words
     bool want_seq = false;
     uint32_t rlen = 0, gaps = 0;
     for (uint32_t i = 0; i < n; i++) {
-        cigar.push_back(c[i]);
         const uint32_t op = bam_cigar_op(c[i]), len = bam_cigar_oplen(c[i]);
-        if (len == 50 && (op == BAM_CINS || op == BAM_CSOFT_CLIP)) want_seq = true;
+        want_seq |= len == 50 && (op == BAM_CINS || op == BAM_CSOFT_CLIP);
         if (op == BAM_CMATCH || op == BAM_CDEL || op == BAM_CREF_SKIP || op == BAM_CEQUAL || op == BAM_CDIFF) rlen += len;
         gaps += (op == BAM_CDEL) | (op == BAM_CREF_SKIP);
     }
@@ -32,23 +59,45 @@ void PackedReads::append(const bam1_t* b, bool keep_seq)
         const uint8_t* s = bam_get_seq(b);
         seq4[idx].assign(s, s + ((size_t)b->core.l_qseq + 1) / 2);
     }
+    if (keep_name) {
+        if (name_off.empty()) name_off.push_back(0);
+        const char* q = bam_get_qname(b);
+        names.append(q, std::strlen(q));
+        name_off.push_back(names.size());
+    }
 }
 
 void PackedReads::clear()
 {
-    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); n_gap.clear(); seq4.clear();
-    cig_off.assign(1, 0);
+    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); n_gap.clear(); serial.clear(); seq4.clear();
+    names.clear(); name_off.clear();
+    cig_off.clear(); cig_off.push_back(0);
+}
+
+void PackedReads::copy_reaching(uint32_t cut, PackedReads& k) const
+{
+    const bool with_names = !name_off.empty();
+    for (size_t i = 0; i < pos0.size(); i++) {
+        if (ref_end[i] <= cut) continue;
+        const uint32_t j = (uint32_t)k.pos0.size();
+        k.tid.push_back(tid[i]); k.pos0.push_back(pos0[i]); k.flag.push_back(flag[i]); k.mapq.push_back(mapq[i]); k.ref_end.push_back(ref_end[i]);
+        k.n_gap.push_back(n_gap[i]); k.serial.push_back(serial[i]);
+        k.cigar.append(cigar.data() + cig_off[i], (size_t)(cig_off[i + 1] - cig_off[i]));
+        k.cig_off.push_back(k.cigar.size());
+        const auto s = seq4.find((uint32_t)i);
+        if (s != seq4.end()) k.seq4[j] = s->second;
+        if (with_names) {
+            if (k.name_off.empty()) k.name_off.push_back(0);
+            k.names.append(names.data() + name_off[i], (size_t)(name_off[i + 1] - name_off[i]));
+            k.name_off.push_back(k.names.size());
+        }
+    }
 }
 
 void PackedReads::keep_reaching(uint32_t cut)
 {
     PackedReads k;
-    for (size_t i = 0; i < pos0.size(); i++) {
-        if (ref_end[i] <= cut) continue;
-        k.tid.push_back(tid[i]); k.pos0.push_back(pos0[i]); k.flag.push_back(flag[i]); k.mapq.push_back(mapq[i]); k.ref_end.push_back(ref_end[i]); k.n_gap.push_back(n_gap[i]);
-        k.cigar.insert(k.cigar.end(), cigar.begin() + (ptrdiff_t)cig_off[i], cigar.begin() + (ptrdiff_t)cig_off[i + 1]);
-        k.cig_off.push_back(k.cigar.size());
-    }
+    copy_reaching(cut, k);
     *this = std::move(k);
 }
 

@@ -214,6 +214,7 @@ int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32
     uint32_t grid_h = (uint32_t)((n_upper + 255) / 256);
     if (grid_h > (uint32_t)ctx->sm_count * grid_mult(ctx, 8)) grid_h = ctx->sm_count * grid_mult(ctx, 8);
     if (grid_h == 0) grid_h = 1;
+    grid_h = cap_grid(ctx, grid_h);
     k_sort_hist<<<grid_h, 256, 0, ctx->stream>>>(bufs.hi, bufs.lo, n_dev, n_upper, digit_mask, st, first ? first->n_raw : nullptr, first ? first->clamp_cap : 0u,
                                                  first ? first->n_clamped_out : nullptr, first && first->iota ? bufs.val : nullptr);
     ctx->launches++;
@@ -222,7 +223,7 @@ int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32
     P.n_dev = n_dev; P.n_host = n_upper; P.st = st;
     P.status = ctx->scan_status.as<unsigned long long>();
     const uint64_t pass_cap = (uint64_t)ctx->sm_count * grid_mult(ctx, 6);
-    uint32_t grid = (uint32_t)(tiles < pass_cap ? tiles : pass_cap);
+    uint32_t grid = cap_grid(ctx, tiles < pass_cap ? tiles : pass_cap);
     for (int d = 0; d < n_digits; d++) {
         if (!((digit_mask >> d) & 1u)) continue;
         P.digit = d;

@@ -55,6 +55,7 @@ using namespace csv;
 extern "C" int csv_record_summary(csv_ctx* ctx, csv_batch* b, int32_t* endpos_out, int32_t* query_start_out, int32_t* query_end_out)
 {
     if (!ctx || !b) { set_error("csv_record_summary: null argument"); return CSV_ERR_ARG; }
+    if (b->inputs_released) { set_error("csv_record_summary: the batch's inputs were released"); return CSV_ERR_STATE; }
     const uint32_t n = b->n_reads;
     if (n == 0 || (!endpos_out && !query_start_out && !query_end_out)) return CSV_OK;
     CSV_CUDA(cudaSetDevice(ctx->device));

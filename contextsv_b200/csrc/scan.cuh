@@ -104,7 +104,7 @@ int chained_scan(csv_ctx* ctx, In in, Out out, uint64_t n_upper, const uint32_t*
     CSV_TRY(next_ticket(ctx, &ticket));
     uint32_t epoch = next_epoch(ctx);
     const uint64_t cap = (uint64_t)ctx->sm_count * grid_mult(ctx, 8);
-    uint64_t grid = tiles < cap ? tiles : cap;
+    uint64_t grid = cap_grid(ctx, tiles < cap ? tiles : cap);
     k_chained_scan<<<(unsigned)grid, kScanThreads, 0, ctx->stream>>>(in, out, n_dev, n_upper, ticket,
                                                                     ctx->scan_status.as<unsigned long long>(), epoch, total_out, run_if);
     ctx->launches++;

@@ -108,7 +108,7 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
 {
     const uint32_t cap = (uint32_t)b->sig_cap;
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
-    uint32_t grid = ctx->sm_count * grid_mult(ctx, 4);
+    uint32_t grid = cap_grid(ctx, ctx->sm_count * grid_mult(ctx, 4));
     CSV_TRY(ctx->sort_tmp[1].ensure((size_t)cap * 8));
     CSV_TRY(ctx->sort_tmp[3].ensure((size_t)cap * 4));
     SortBufs sb;

@@ -263,6 +263,50 @@ __global__ void __launch_bounds__(256) k_span_finalize(const WalkParams P)
 // RECORDS (16 bytes each) in which the record that crosses a span start also walks its own first ops (a few dozen for
 // HiFi), instead of a second pass over every CIGAR word plus a three-launch span scan.
 
+// Second half of the record-level pre-pass: the record scan left {record k, its first event slot, its op range [o0, o1)}
+// in the descriptor of every span start B = s * kWalkSpan the record runs into (o0 < B <= o1).  A group of kCarryLanes
+// lanes sums the class-weighted lengths of the ops [o0, B) -- a few dozen for HiFi -- and turns the entry into what the
+// walk starts the span from: {k, event slot at B, reference consumed since the head, 0} and {reference, query} for the
+// gather.  A record far longer than a span pays O(ops) per span start it crosses: the batch-level test in
+// csv_batch_upload keeps such batches (ONT) on the op-level pre-pass.
+constexpr uint32_t kCarryLanes = 8;
+__global__ void __launch_bounds__(256) k_span_carry(const WalkParams P, uint32_t n_carry)
+{
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / kCarryLanes, gl = threadIdx.x % kCarryLanes;
+    const uint32_t s = g + 1u;
+    const bool live = s <= n_carry;
+    uint4 d = make_uint4(0u, 0u, 0u, 0u);
+    if (live) d = P.span_desc[s];
+    const uint32_t B = s * (uint32_t)kWalkSpan;
+    uint32_t ref = 0, qry = 0, gaps = 0;
+    if (live) {
+        uint32_t o = d.z + gl;
+        for (; o + kCarryLanes < B; o += 2u * kCarryLanes) {                       // two independent loads in flight
+            const uint32_t w0 = __ldg(P.cigar + o), w1 = __ldg(P.cigar + o + kCarryLanes);
+            const uint32_t r0 = (kRefMask >> (w0 & 15u)) & 1u, r1 = (kRefMask >> (w1 & 15u)) & 1u;
+            const uint32_t q0 = (kQryMask >> (w0 & 15u)) & 1u, q1 = (kQryMask >> (w1 & 15u)) & 1u;
+            ref += r0 * (w0 >> 4) + r1 * (w1 >> 4);
+            qry += q0 * (w0 >> 4) + q1 * (w1 >> 4);
+            gaps += (r0 & ~q0) + (r1 & ~q1);
+        }
+        if (o < B) {
+            const uint32_t w = __ldg(P.cigar + o), r = (kRefMask >> (w & 15u)) & 1u, q = (kQryMask >> (w & 15u)) & 1u;
+            ref += r * (w >> 4); qry += q * (w >> 4); gaps += r & ~q;
+        }
+    }
+#pragma unroll
+    for (uint32_t m = kCarryLanes / 2; m > 0; m >>= 1) {
+        ref += __shfl_xor_sync(0xffffffffu, ref, m);
+        qry += __shfl_xor_sync(0xffffffffu, qry, m);
+        gaps += __shfl_xor_sync(0xffffffffu, gaps, m);
+    }
+    if (live && gl == 0) {
+        // head event of the record, two per D/N op so far, and its tail event if it ends right at the span start
+        P.span_desc[s] = make_uint4(d.x, d.y + 1u + 2u * gaps + (B == d.w ? 1u : 0u), ref, 0u);
+        P.span_rq[s] = make_uint2(ref, qry);
+    }
+}
+
 // ---- TMA bulk copies (global -> shared, completion on an mbarrier): the walk is a persistent kernel whose next
 // span is in flight while the current one is processed; no registers are spent on the prefetch.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -539,35 +583,21 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
                 const unsigned long long o0 = Q.cig_off[i], o1 = Q.cig_off[i + 1];
                 const uint32_t s_lo = (uint32_t)(o0 / kWalkSpan) + 1u, s_hi = (uint32_t)(o1 / kWalkSpan);
                 if (k == 0) { Q.span_desc[0] = make_uint4(0xffffffffu, 0u, 0u, 0u); Q.span_rq[0] = make_uint2(0u, 0u); }
-                if (s_lo <= s_hi) {
-                    // span starts B with o0 < B <= o1: this record runs into them (or ends right there)
-                    uint32_t ref = 0, qry = 0, gaps = 0;
-                    unsigned long long o = o0;
-                    for (uint32_t s = s_lo; s <= s_hi; s++) {
-                        const unsigned long long B = (unsigned long long)s * kWalkSpan;
-                        for (; o + 4 <= B; o += 4) {                        // four independent loads in flight
-                            const uint32_t w0 = Q.cigar[o], w1 = Q.cigar[o + 1], w2 = Q.cigar[o + 2], w3 = Q.cigar[o + 3];
-                            const uint32_t r0 = (kRefMask >> (w0 & 15u)) & 1u, r1 = (kRefMask >> (w1 & 15u)) & 1u, r2 = (kRefMask >> (w2 & 15u)) & 1u, r3 = (kRefMask >> (w3 & 15u)) & 1u;
-                            const uint32_t q0 = (kQryMask >> (w0 & 15u)) & 1u, q1 = (kQryMask >> (w1 & 15u)) & 1u, q2 = (kQryMask >> (w2 & 15u)) & 1u, q3 = (kQryMask >> (w3 & 15u)) & 1u;
-                            ref += r0 * (w0 >> 4) + r1 * (w1 >> 4) + r2 * (w2 >> 4) + r3 * (w3 >> 4);
-                            qry += q0 * (w0 >> 4) + q1 * (w1 >> 4) + q2 * (w2 >> 4) + q3 * (w3 >> 4);
-                            gaps += (r0 & ~q0) + (r1 & ~q1) + (r2 & ~q2) + (r3 & ~q3);
-                        }
-                        for (; o < B; o++) {
-                            const uint32_t w = Q.cigar[o], r = (kRefMask >> (w & 15u)) & 1u, q = (kQryMask >> (w & 15u)) & 1u;
-                            ref += r * (w >> 4); qry += q * (w >> 4); gaps += r & ~q;
-                        }
-                        // head event of this record, two per D/N op so far, and its tail event if it ends right at the span start
-                        Q.span_desc[s] = make_uint4((uint32_t)k, ex + 1u + 2u * gaps + (B == o1 ? 1u : 0u), ref, 0u);
-                        Q.span_rq[s] = make_uint2(ref, qry);
-                    }
-                }
+                // span starts B with o0 < B <= o1: this record runs into them (or ends right there).  Parked for k_span_carry,
+                // which sums the record's ops up to B with a group of lanes per span (n_ops < 2^31: offsets fit 32 bits).
+                for (uint32_t s = s_lo; s <= s_hi; s++) Q.span_desc[s] = make_uint4((uint32_t)k, ex, (uint32_t)o0, (uint32_t)o1);
                 if (k + 1 == (uint64_t)*n_rec) {
                     Q.ev_start[k + 1] = ex + v;
                     if (s_hi != Q.n_spans) Q.span_desc[Q.n_spans] = make_uint4((uint32_t)k, 0u, 0u, 0u);      // sentinel: closes the last span
                 }
             };
             CSV_TRY(chained_scan(ctx, in, out, b->n_reads, n_rec, nullptr));
+            const uint32_t n_carry = (uint32_t)(b->n_ops / kWalkSpan);               // span starts B = s * kWalkSpan, 1 <= s <= n_carry
+            if (n_carry) {
+                const uint32_t per_cta = 256 / kCarryLanes;
+                k_span_carry<<<(n_carry + per_cta - 1) / per_cta, 256, 0, ctx->stream>>>(P, n_carry);
+                ctx->launches++;
+            }
         }
     } else {
         if (span0 == 0) CSV_CUDA(cudaMemsetAsync(b->d_scan_carry.p, 0, sizeof(WalkAgg), ctx->stream));

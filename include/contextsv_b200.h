@@ -124,9 +124,19 @@ typedef struct {
  * re-reads the BAM three times). */
 typedef struct csv_batch csv_batch;
 
+/* Enqueues the copies on the context's stream and returns: pageable arrays are staged before the call returns, PINNED
+ * arrays (csv_host_alloc) are read by the copy engine afterwards and must stay untouched until a call that waits for the
+ * stream -- csv_ctx_sync, csv_depth_stats, csv_sigs_count or any fetch. */
 int  csv_batch_upload(csv_ctx* ctx, const csv_reads* reads, uint32_t n_regions,
                       const csv_region* regions, csv_batch** out);
 void csv_batch_free(csv_ctx* ctx, csv_batch* b);
+/* Drops everything of a scanned batch except its RESULTS: the depth slabs (with the region tables csv_window_sums,
+ * csv_depth_at, csv_depth_at_tid and the fetches need), the per-region stats, the signature columns and labels.  The
+ * records, CIGAR words and event lists go back to the context's pool -- for a 30x genome 12.4 of 16 GB stay, for dense
+ * ONT shards a few percent.  A caller that keeps the depth map on the device for the rest of the run (the reference reads
+ * it in querySNPRegion, cnv_caller.cpp:76-113, and getReadDepth, sv_caller.cpp:1332-1344) holds one such batch per shard.
+ * Afterwards csv_scan_run, csv_record_summary and csv_batch_reserve_sigs fail with CSV_ERR_STATE. */
+int  csv_batch_release_inputs(csv_ctx* ctx, csv_batch* b);
 
 /* Signature capacity of a batch.  Upload reserves max(2^20, n_ops / 16) entries (never more than n_ops); a pass that
  * emits more fails with CSV_ERR_CAPACITY when its results are fetched (csv_sigs_count / csv_sigs_fetch report the

@@ -21,9 +21,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 extern "C" const char seq_nt16_str[] = "=ACMGRSVTWYHKDBN";
@@ -31,50 +34,162 @@ extern "C" const char seq_nt16_str[] = "=ACMGRSVTWYHKDBN";
 /* ------------------------------------------------------------ BGZF reader */
 namespace {
 
+/* One BGZF block: header parsed, payload read, inflated.  Used by the sequential reader and by the read-ahead threads. */
+struct Block {
+    int64_t coff = 0, next_coff = 0;
+    std::vector<uint8_t> cbuf, ubuf;
+    size_t clen = 0;
+    bool eof = false, bad = false;
+
+    /* reads the compressed block at coff (no inflate) */
+    void fetch(FILE* f, int64_t at) {
+        coff = at; eof = bad = false; ubuf.clear(); clen = 0;
+        uint8_t h[18];
+        if (fseeko(f, coff, SEEK_SET) != 0) { bad = true; return; }
+        size_t got = fread(h, 1, 18, f);
+        if (got == 0) { eof = true; return; }
+        if (got < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { bad = true; return; }
+        unsigned xlen = h[10] | (h[11] << 8);
+        std::vector<uint8_t> extra(xlen);
+        memcpy(extra.data(), h + 12, xlen < 6 ? xlen : 6);
+        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f) != xlen - 6) { bad = true; return; }
+        int bsize = -1;
+        for (unsigned p = 0; p + 4 <= xlen;) {                 /* find the BC subfield */
+            unsigned slen = extra[p + 2] | (extra[p + 3] << 8);
+            if (extra[p] == 'B' && extra[p + 1] == 'C' && slen == 2) bsize = extra[p + 4] | (extra[p + 5] << 8);
+            p += 4 + slen;
+        }
+        if (bsize < 0) { bad = true; return; }
+        clen = (size_t)bsize + 1 - 12 - xlen - 8;              /* deflate payload */
+        cbuf.resize(clen + 8);
+        if (fseeko(f, coff + 12 + xlen, SEEK_SET) != 0 || fread(cbuf.data(), 1, clen + 8, f) != clen + 8) { bad = true; return; }
+        next_coff = coff + bsize + 1;
+    }
+    void inflate_payload() {
+        if (eof || bad) return;
+        uint32_t isize; memcpy(&isize, cbuf.data() + clen + 4, 4);
+        ubuf.resize(isize);
+        if (!isize) return;
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+        zs.next_in = cbuf.data(); zs.avail_in = (uInt)clen;
+        zs.next_out = ubuf.data(); zs.avail_out = isize;
+        int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END) bad = true;
+    }
+};
+
+/* hts_set_threads(fp, n > 1): one thread reads compressed blocks ahead of the consumer, n threads inflate them; the
+ * consumer takes the blocks in file order.  Restarted by every seek. */
+struct ReadAhead {
+    enum { kRing = 256 };
+    struct Slot { Block b; int state = 0; /* 0 free, 1 compressed, 2 inflating, 3 done */ };
+    std::string path;
+    FILE* f = nullptr;
+    std::vector<Slot> ring = std::vector<Slot>(kRing);
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t head = 0, tail = 0, work = 0;      /* consumer / reader / next slot to inflate */
+    int64_t next_coff = 0;
+    bool stop = false, ended = false;
+    std::thread reader;
+    std::vector<std::thread> workers;
+
+    void start(const std::string& p, int64_t coff, int n_threads) {
+        path = p; f = fopen(p.c_str(), "rb");
+        if (!f) return;
+        next_coff = coff; head = tail = work = 0; stop = ended = false;
+        for (auto& s : ring) s.state = 0;
+        reader = std::thread([this] {
+            for (;;) {
+                Slot* s;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return stop || tail - head < kRing; });
+                    if (stop) return;
+                    s = &ring[tail % kRing];
+                }
+                s->b.fetch(f, next_coff);
+                const bool last = s->b.eof || s->b.bad;
+                if (!last) next_coff = s->b.next_coff;
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    s->state = 1; tail++;
+                    if (last) ended = true;
+                }
+                cv.notify_all();
+                if (last) return;
+            }
+        });
+        for (int i = 0; i < n_threads; i++) workers.emplace_back([this] {
+            for (;;) {
+                Slot* s;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return stop || work < tail; });
+                    if (stop) return;
+                    s = &ring[work % kRing]; work++; s->state = 2;
+                }
+                s->b.inflate_payload();
+                { std::lock_guard<std::mutex> lk(m); s->state = 3; }
+                cv.notify_all();
+            }
+        });
+    }
+    /* next block in file order, swapped into `out`; false once the stream has ended and everything was handed over */
+    bool next(Block& out) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return (head < tail && ring[head % kRing].state == 3) || (ended && head == tail); });
+        if (head == tail) { out.eof = true; out.bad = false; out.ubuf.clear(); return false; }
+        Slot& s = ring[head % kRing];
+        std::swap(out, s.b);
+        s.state = 0; head++;
+        lk.unlock();
+        cv.notify_all();
+        return true;
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        if (reader.joinable()) reader.join();
+        for (auto& t : workers) if (t.joinable()) t.join();
+        workers.clear();
+        if (f) { fclose(f); f = nullptr; }
+    }
+    ~ReadAhead() { shutdown(); }
+};
+
 struct Bgzf {
     FILE* f = nullptr;
-    std::vector<uint8_t> cbuf, ubuf;
+    std::string path;
+    int threads = 0;                       /* hts_set_threads */
+    std::unique_ptr<ReadAhead> ahead;      /* running read-ahead, positioned at next_coff */
+    Block cur;
+    std::vector<uint8_t>& ubuf = cur.ubuf;
     int64_t block_coff = 0;   /* file offset of the block in ubuf */
     int64_t next_coff = 0;    /* file offset of the next block     */
     size_t upos = 0;          /* read cursor inside ubuf           */
     bool eof = false;
 
     bool load_block() {
-        block_coff = next_coff;
-        uint8_t h[18];
-        if (fseeko(f, block_coff, SEEK_SET) != 0) return false;
-        size_t got = fread(h, 1, 18, f);
-        if (got == 0) { eof = true; ubuf.clear(); upos = 0; return false; }
-        if (got < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return false;
-        unsigned xlen = h[10] | (h[11] << 8);
-        /* find the BC subfield */
-        std::vector<uint8_t> extra(xlen);
-        memcpy(extra.data(), h + 12, xlen < 6 ? xlen : 6);
-        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f) != xlen - 6) return false;
-        int bsize = -1;
-        for (unsigned p = 0; p + 4 <= xlen;) {
-            unsigned slen = extra[p + 2] | (extra[p + 3] << 8);
-            if (extra[p] == 'B' && extra[p + 1] == 'C' && slen == 2) bsize = extra[p + 4] | (extra[p + 5] << 8);
-            p += 4 + slen;
+        if (threads > 1) {
+            if (!ahead) { ahead.reset(new ReadAhead); ahead->start(path, next_coff, threads); }
+            if (ahead->f) {
+                ahead->next(cur);
+                upos = 0;
+                if (cur.eof) { eof = true; ubuf.clear(); return false; }
+                if (cur.bad) return false;
+                block_coff = cur.coff; next_coff = cur.next_coff;
+                return true;
+            }
         }
-        if (bsize < 0) return false;
-        size_t clen = (size_t)bsize + 1 - 12 - xlen - 8;   /* deflate payload */
-        cbuf.resize(clen + 8);
-        if (fseeko(f, block_coff + 12 + xlen, SEEK_SET) != 0) return false;
-        if (fread(cbuf.data(), 1, clen + 8, f) != clen + 8) return false;
-        uint32_t isize; memcpy(&isize, cbuf.data() + clen + 4, 4);
-        ubuf.resize(isize);
-        if (isize) {
-            z_stream zs; memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) return false;
-            zs.next_in = cbuf.data(); zs.avail_in = (uInt)clen;
-            zs.next_out = ubuf.data(); zs.avail_out = isize;
-            int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) return false;
-        }
-        next_coff = block_coff + bsize + 1;
+        cur.fetch(f, next_coff);
         upos = 0;
+        if (cur.eof) { eof = true; ubuf.clear(); return false; }
+        cur.inflate_payload();
+        if (cur.bad) return false;
+        block_coff = cur.coff; next_coff = cur.next_coff;
         return true;
     }
     /* read exactly n bytes; returns false at EOF/error */
@@ -92,6 +207,7 @@ struct Bgzf {
         return ((uint64_t)block_coff << 16) | (uint64_t)upos;
     }
     bool seek(uint64_t voff) {
+        ahead.reset();                                     /* read-ahead restarts at the new offset */
         next_coff = (int64_t)(voff >> 16); eof = false;
         ubuf.clear(); upos = 0;
         size_t u = voff & 0xffff;
@@ -275,18 +391,24 @@ samFile* sam_open(const char* fn, const char* mode)
     }
     fp->bz.f = fopen(fn, "rb");
     if (!fp->bz.f) { delete fp; return nullptr; }
+    fp->bz.path = fn;
     return fp;
 }
 
 int sam_close(samFile* fp)
 {
     if (!fp) return -1;
+    fp->bz.ahead.reset();
     if (fp->bz.f) fclose(fp->bz.f);
     delete fp;
     return 0;
 }
 
-int hts_set_threads(htsFile*, int) { return 0; }
+int hts_set_threads(htsFile* fp, int n)
+{
+    if (fp && !fp->is_mem) { fp->bz.ahead.reset(); fp->bz.threads = n; }     /* n > 1: BGZF blocks are inflated ahead of the reader by n threads */
+    return 0;
+}
 const char* hts_get_fn(htsFile* fp) { return fp ? fp->path.c_str() : nullptr; }
 
 sam_hdr_t* sam_hdr_read(samFile* fp)
@@ -350,6 +472,10 @@ hts_idx_t* sam_index_load(samFile* fp, const char* fn)
     /* one linear scan: remember the virtual offset of the first record of each contig */
     htsFile* scan = sam_open(fp->path.c_str(), "r");
     if (!scan) { delete idx; return nullptr; }
+    {   /* a .bai would make this scan unnecessary: keep it short, inflate with every core (at most 16) */
+        unsigned hw = std::thread::hardware_concurrency();
+        hts_set_threads(scan, (int)(hw > 16 ? 16 : (hw < 2 ? 0 : hw)));
+    }
     sam_hdr_t* h = sam_hdr_read(scan);
     if (!h) { sam_close(scan); delete idx; return nullptr; }
     FileIndex fi; fi.first_voff.assign(h->n_targets + 1, UINT64_MAX); fi.records_voff = scan->records_voff;

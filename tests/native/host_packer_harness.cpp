@@ -11,10 +11,15 @@ using csvhost::PackedReads;
 extern "C" {
 
 // every record overlapping `chrom`, in file order, as the depth / CIGAR glue packs them
+static int g_threads = 0;
+// hts_set_threads for the files hp_pack opens from now on (the shim inflates BGZF blocks ahead on that many threads)
+void hp_set_threads(int n) { g_threads = n; }
+
 void* hp_pack(const char* bam, const char* chrom, int keep_seq)
 {
     samFile* fp = sam_open(bam, "r");
     if (!fp) return nullptr;
+    if (g_threads) hts_set_threads(fp, g_threads);
     bam_hdr_t* hdr = sam_hdr_read(fp);
     hts_idx_t* idx = hdr ? sam_index_load(fp, bam) : nullptr;
     hts_itr_t* it = idx ? sam_itr_querys(idx, hdr, chrom) : nullptr;

@@ -101,6 +101,31 @@ def test_packer_reproduces_the_soa(harness, bam):
         L.hp_free(p)
 
 
+def test_threaded_bgzf_read_ahead_yields_the_same_records(harness, tmp_path):
+    """hts_set_threads(n > 1) in the shim: blocks are read and inflated ahead of the consumer by n threads, seeks restart
+    the read-ahead; the packed records must not change (many blocks: ~4 MB of records)."""
+    L = harness
+    clen, names = [400_000, 250_000, 90_000], ["chr20", "chr21", "chr22"]
+    r = synth.generate(clen, seed=5, n_sv=60, coverage=12.0)
+    path = str(tmp_path / "t.bam")
+    bamio.write_bam(path, r, names, clen, seed=2)
+    want = {}
+    for name in names:
+        p = L.hp_pack(path.encode(), name.encode(), 0)
+        want[name] = unpack(L, p); L.hp_free(p)
+    try:
+        for threads in (2, 5):
+            L.hp_set_threads(threads)
+            for name in reversed(names):                       # out of file order: every query seeks
+                p = L.hp_pack(path.encode(), name.encode(), 0)
+                got = unpack(L, p); L.hp_free(p)
+                assert len(got["pos0"]) == len(want[name]["pos0"]) > 50
+                for k in want[name]:
+                    assert np.array_equal(got[k], want[name][k]), (threads, name, k)
+    finally:
+        L.hp_set_threads(0)
+
+
 def test_keep_reaching_is_the_halo_of_the_next_shard(harness, bam):
     L = harness
     path, r, names, clen = bam
