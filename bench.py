@@ -227,7 +227,7 @@ class ShmBoard:
     shared-memory segment on the box and fetches its results straight into it; rank 0 maps all of them and merges."""
     U_CAP = 8192          # signature starts per shard that another shard's depth slice has to answer
 
-    def __init__(self, tag, rank, world, n_regions_max, cap_sig):
+    def __init__(self, tag, rank, world, n_regions_max, cap_sig, n_contigs):
         self.rank, self.world, self.R, self.cap = rank, world, n_regions_max, int(cap_sig)
         self.layout, off = {}, 0
 
@@ -242,6 +242,7 @@ class ShmBoard:
         field("label", np.int32, self.cap); field("kind", np.uint8, self.cap)
         field("u_tid", np.int32, self.U_CAP); field("u_pos", np.uint32, self.U_CAP); field("u_idx", np.uint32, self.U_CAP)
         field("answers", np.uint32, self.U_CAP * world)
+        field("cks", np.uint64, n_contigs); field("tot", np.uint64, 2 * n_contigs)
         self.size = off + 64
         d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
         self.path = lambda r: os.path.join(d, "csvb_%s_%d" % (tag, r))
@@ -405,7 +406,7 @@ def main_ours(args):
 
     # ---- roofline of the dominant kernel and of the whole path (algorithmic bytes); per rank, rank 0's printed
     peak, peak_src = measured_peak_gbs()
-    b_alg = 15 * n_reads + (4 * n_reads if reads.get("n_gap") is not None else 0) + 4 * n_ops + 4 * depth_words + 21 * n_sig + 8 * n_sig
+    b_alg = 15 * n_reads + (4 * n_reads if reads.get("n_gap") is not None else 0) + (4 * n_reads if reads.get("ref_len") is not None else 0) + 4 * n_ops + 4 * depth_words + 21 * n_sig + 8 * n_sig
     tile_ms = stages["k_depth_tiles16"][0] / args.steps  # the dominant kernel alone: CUDA events around its launch(es) on its stream
     tile_bytes = 4 * depth_words
     achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
@@ -441,7 +442,7 @@ def main_ours(args):
         tag = os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid() if os.environ.get("TORCHELASTIC_RUN_ID") else os.getpid())
         obj = [tag]
         dist.broadcast_object_list(obj, src=0)
-        board = ShmBoard(obj[0], rank, world, R_max, cap_sig)
+        board = ShmBoard(obj[0], rank, world, R_max, cap_sig, n_contigs)
         barrier()
         board.attach_all()
         out = {k: board.view(rank, k) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
@@ -452,7 +453,13 @@ def main_ours(args):
         out_label, out_depth = np.zeros(cap_sig, np.int32), np.zeros(cap_sig, np.uint32)
     region_tid = np.array([t for (t, _, _, _) in regions], np.int32)
 
+    phases = {}
+
     def step_e2e(want_checksum=False):
+        t_ph = [time.perf_counter()]
+
+        def mark(name):
+            t_ph.append(time.perf_counter()); phases[name] = 1e3 * (t_ph[-1] - t_ph[-2])
         bt = api.Batch(ctx, reads, regions)                                        # H2D of the packed SoA
         bt.scan(want_depth=True, want_sigs=True)
         check(lib().csv_sigs_dbscan1d(ctx.h, bt.h, float(DB_EPS), int(DB_MIN_PTS), ptr(out_label), len(out_label)))   # DBSCAN1D + D2H labels
@@ -462,9 +469,11 @@ def main_ours(args):
         dep = bt.sigs_depth(n=n, out=out_depth)                                    # D2H depth at every signature start
         cks = bt.depth_checksum() if want_checksum else None
         sg["label"] = out_label[:n]; sg["depth"] = dep
+        mark("upload_scan_fetch")
         if not strong:
             bt.free()
             merged, n_split = finalize_merge([(sg, regions, 0)], ctx, api)
+            mark("merge")
             return merged, sums, nzs, cks, n_split
         # sharded: publish, answer the other shards' depth questions, rank 0 merges
         hdr = board.view(rank, "hdr")
@@ -476,6 +485,7 @@ def main_ours(args):
         board.view(rank, "region_off")[:len(regions) + 1] = sg["region_off"]
         board.view(rank, "sums")[:len(regions)] = sums; board.view(rank, "nzs")[:len(regions)] = nzs
         hdr[0], hdr[1], hdr[2] = n, len(un), len(regions)
+        mark("publish")
         dist.barrier()
         for r in range(world):
             if r == rank:
@@ -486,6 +496,7 @@ def main_ours(args):
                 board.view(rank, "answers")[r * board.U_CAP: r * board.U_CAP + nu] = ans
         bt.free()
         dist.barrier()
+        mark("cross_shard_depth")
         if rank != 0:
             return None, sums, nzs, cks, 0
         parts = []
@@ -506,6 +517,7 @@ def main_ours(args):
             d["region_off"] = board.view(r, "region_off")[:nreg + 1]
             parts.append((d, plan[r], read_bases[r]))
         merged, n_split = finalize_merge(parts, ctx, api)
+        mark("merge")
         return merged, sums, nzs, cks, n_split
 
     from contextsv_b200._capi import check, lib, ptr
@@ -528,16 +540,24 @@ def main_ours(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     # one untimed step gives the checksums (and warms the e2e path up)
     merged, sums, nzs, cks, n_split = step_e2e(want_checksum=True)
-    per_contig = np.zeros(n_contigs, np.int64)
-    for (t_, _, _, _), c in zip(regions, cks.astype(np.int64)):
-        per_contig[t_] += c                                                      # wraps modulo 2^64, like the kernel's sum
-    if world > 1 and strong:
-        tt = torch.from_numpy(per_contig).cuda(); dist.all_reduce(tt); per_contig = tt.cpu().numpy()
+    # per-contig depth checksum / sum / non-zero count: additive over the shards of a contig (modulo 2^64).  Sharded runs add
+    # them up on rank 0 through the shared-memory board, like every other result (no collective on the path).
+    per_contig = np.zeros(n_contigs, np.uint64); tot_contig = np.zeros(2 * n_contigs, np.uint64)
+    with np.errstate(over="ignore"):
+        for (t_, _, _, _), c, s_, z_ in zip(regions, cks.astype(np.uint64), sums.astype(np.uint64), nzs.astype(np.uint64)):
+            per_contig[t_] += c; tot_contig[2 * t_] += s_; tot_contig[2 * t_ + 1] += z_
+        if strong:
+            board.view(rank, "cks")[:] = per_contig; board.view(rank, "tot")[:] = tot_contig
+            barrier()
+            if rank == 0:
+                for r_ in range(1, world):
+                    per_contig += board.view(r_, "cks"); tot_contig += board.view(r_, "tot")
+            barrier()
     checksums = None
     if rank == 0:
         import hashlib
         dg = digest_results(merged, n_contigs)
-        checksums = {"depth": hashlib.blake2b(per_contig.tobytes(), digest_size=8).hexdigest(), "signatures": dg[0], "dbscan1d_labels": dg[1], "depth_at_signature_start": dg[2],
+        checksums = {"depth": hashlib.blake2b(per_contig.tobytes(), digest_size=8).hexdigest(), "depth_sum": int(tot_contig[0::2].sum()), "depth_nonzero": int(tot_contig[1::2].sum()), "signatures": dg[0], "dbscan1d_labels": dg[1], "depth_at_signature_start": dg[2],
                      "signatures_total": int(sum(len(m["start"]) for m in merged.values())), "contigs_refit_after_merge": n_split}
     if args.skip_e2e:        # profiling runs only (ncu): never used for a reported number
         e2e_steps, dt_max, e2e_value = 0, 0.0, None
@@ -553,12 +573,13 @@ def main_ours(args):
         bt.scan(want_depth=True, want_sigs=True)
         lab = bt.sigs_dbscan1d(DB_EPS, DB_MIN_PTS)
         sg = bt.sigs(); sg["label"] = lab; sg["depth"] = bt.sigs_depth()
-        c1 = bt.depth_checksum().astype(np.int64)
+        c1 = bt.depth_checksum().astype(np.uint64)
+        s1_, z1_ = bt.depth_stats()
         bt.free()
         m1, _ = finalize_merge([(sg, api.whole_contig_regions(contig_len), 0)], ctx, api)
         d1 = digest_results(m1, n_contigs)
         import hashlib
-        checksums_n1 = {"depth": hashlib.blake2b(c1.tobytes(), digest_size=8).hexdigest(), "signatures": d1[0], "dbscan1d_labels": d1[1], "depth_at_signature_start": d1[2],
+        checksums_n1 = {"depth": hashlib.blake2b(c1.tobytes(), digest_size=8).hexdigest(), "depth_sum": int(s1_.astype(np.uint64).sum()), "depth_nonzero": int(z1_.astype(np.uint64).sum()), "signatures": d1[0], "dbscan1d_labels": d1[1], "depth_at_signature_start": d1[2],
                         "signatures_total": int(sum(len(m["start"]) for m in m1.values()))}
     if strong:
         barrier()
@@ -630,7 +651,7 @@ def main_ours(args):
                        "ms_per_step_fastest_rank": ms_min / args.steps, "host_generation_s": round(t_gen, 2)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1),
+                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
                     "result": "mean coverage inputs, signature vectors, DBSCAN1D labels, depth at every signature start in host memory; the per-base map stays in HBM" +
                               ("; shards gathered through shared memory, merged and re-fit on rank 0" if strong else "")},
             "e2e_full_map": full_map,
@@ -645,6 +666,9 @@ def main_ours(args):
         dist.destroy_process_group()
     if rank == 0 and checksums_n1 is not None and not match:
         sys.stderr.write("bench.py: sharded results differ from the single-device results\n")
+        for t_ in range(n_contigs):
+            if int(per_contig[t_]) != int(c1[t_]) or int(tot_contig[2 * t_]) != int(s1_[t_]) or int(tot_contig[2 * t_ + 1]) != int(z1_[t_]):
+                sys.stderr.write("  contig %d: checksum %016x / %016x  sum %d / %d  nonzero %d / %d\n" % (t_, int(per_contig[t_]), int(c1[t_]), int(tot_contig[2 * t_]), int(s1_[t_]), int(tot_contig[2 * t_ + 1]), int(z1_[t_])))
         return 1
     return 0
 

@@ -23,7 +23,7 @@ class CsvError(RuntimeError):
 
 class CsvReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_ops", C.c_uint64), ("tid", C.c_void_p), ("pos0", C.c_void_p),
-                ("flag", C.c_void_p), ("mapq", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("n_gap", C.c_void_p)]
+                ("flag", C.c_void_p), ("mapq", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("n_gap", C.c_void_p), ("ref_len", C.c_void_p)]
 
 
 class CsvRegion(C.Structure):
@@ -46,7 +46,7 @@ EXPORTS = [
     "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_ctx_set_pipeline_chunks", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
     "csv_depth_stats", "csv_depth_fetch", "csv_depth_fetch_all", "csv_ctx_set_fetch", "csv_ctx_fetch_stats", "csv_host_widen_u8", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
     "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at", "csv_record_summary", "csv_host_count_gaps",
-    "csv_depth_at_tid", "csv_sigs_depth", "csv_depth_checksum", "csv_batch_reserve_sigs", "csv_batch_release_inputs",
+    "csv_depth_at_tid", "csv_sigs_depth", "csv_depth_checksum", "csv_batch_reserve_sigs", "csv_batch_release_inputs", "csv_host_record_stats",
 ]
 SYNTH_EXPORTS = ["csv_synth_default_params", "csv_synth_num_reads", "csv_synth_reads", "csv_synth_cigar"]
 
@@ -89,6 +89,8 @@ def lib():
         L.csv_host_widen_u8.restype = None
         L.csv_host_count_gaps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         L.csv_host_count_gaps.restype = None
+        L.csv_host_record_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.csv_host_record_stats.restype = None
         L.csv_sigs_count.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.csv_sigs_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CsvSigs), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
         L.csv_sigs_dbscan1d.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_uint64]
@@ -156,10 +158,11 @@ def reads_struct(r):
         "cig_off": np.ascontiguousarray(r["cig_off"], np.uint64),
         "cigar": np.ascontiguousarray(r["cigar"], np.uint32),
         "n_gap": None if r.get("n_gap") is None else np.ascontiguousarray(r["n_gap"], np.uint32),
+        "ref_len": None if r.get("ref_len") is None else np.ascontiguousarray(r["ref_len"], np.uint32),
     }
     n_ops = int(arrs["cig_off"][n]) if n else 0
     s = CsvReads(n, n_ops, ptr(arrs["tid"]), ptr(arrs["pos0"]), ptr(arrs["flag"]), ptr(arrs["mapq"]), ptr(arrs["cig_off"]),
-                 ptr(arrs["cigar"]), ptr(arrs["n_gap"]))
+                 ptr(arrs["cigar"]), ptr(arrs["n_gap"]), ptr(arrs["ref_len"]))
     return s, arrs
 
 
@@ -172,3 +175,15 @@ def count_gaps(r, alloc=None, threads=0):
         cig = np.ascontiguousarray(r["cigar"], np.uint32); off = np.ascontiguousarray(r["cig_off"], np.uint64)
         lib().csv_host_count_gaps(ptr(cig), ptr(off), n, ptr(out), int(threads))
     return out[:n]
+
+
+def record_stats(r, alloc=None, threads=0):
+    """csv_reads::n_gap and csv_reads::ref_len of every record (csv_host_record_stats): what a packer has at hand while it
+    copies the CIGAR words -- D / N ops and reference bases consumed.  Returns (n_gap, ref_len)."""
+    n = int(r["n_reads"])
+    mk = alloc or (lambda k, dt: np.empty(k, dtype=dt))
+    g, l = mk(max(n, 1), np.uint32), mk(max(n, 1), np.uint32)
+    if n:
+        cig = np.ascontiguousarray(r["cigar"], np.uint32); off = np.ascontiguousarray(r["cig_off"], np.uint64)
+        lib().csv_host_record_stats(ptr(cig), ptr(off), n, ptr(g), ptr(l), int(threads))
+    return g[:n], l[:n]

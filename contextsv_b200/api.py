@@ -138,7 +138,7 @@ class Batch:
         self.regions = [tuple(int(x) for x in r) for r in regions]
         if COUNT_GAPS and reads.get("n_gap") is None and int(reads["n_reads"]):
             reads = dict(reads)
-            reads["n_gap"] = _capi.count_gaps(reads)
+            reads["n_gap"], reads["ref_len"] = _capi.record_stats(reads)
         rs, self._keep = _capi.reads_struct(reads)
         arr = (CsvRegion * len(self.regions))(*[CsvRegion(*r) for r in self.regions])
         h = C.c_void_p()

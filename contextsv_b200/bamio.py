@@ -54,7 +54,10 @@ def random_seq4(rng, qlen):
     return ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8)
 
 
-def write_bam(path, reads, contig_names, contig_len, seed=0, seq4=None, seq_off=None):
+def write_bam(path, reads, contig_names, contig_len, seed=0, seq4=None, seq_off=None, qnames=None):
+    """qnames: optional query name per record (default r<i>: every record its own template).  A record with more than
+    65 535 CIGAR ops is written the way htslib writes it (SAM spec 4.2.2): the real CIGAR in a CG:B,I tag and the
+    placeholder <l_seq>S<ref_len>N in the 16-bit CIGAR field."""
     rng = np.random.default_rng(seed)
     w = BgzfWriter(path)
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (n, l) for n, l in zip(contig_names, contig_len))
@@ -68,15 +71,20 @@ def write_bam(path, reads, contig_names, contig_len, seed=0, seq4=None, seq_off=
         c = cig[off[i]:off[i + 1]]
         qlen = int(((c >> 4) * ((_QMASK >> (c & 15)) & 1)).sum())
         rlen = int(((c >> 4) * ((_RMASK >> (c & 15)) & 1)).sum())
-        name = ("r%d" % i).encode() + b"\0"
+        name = (("r%d" % i) if qnames is None else str(qnames[i])).encode() + b"\0"
         pos = int(reads["pos0"][i])
         if seq4 is not None:
             s0 = int(seq_off[i]); sq = bytes(seq4[s0:s0 + (qlen + 1) // 2])
         else:
             sq = bytes(random_seq4(rng, qlen))
+        aux = b""
+        c_field = c
+        if len(c) > 0xffff:
+            aux = b"CGBI" + struct.pack("<I", len(c)) + c.astype("<u4").tobytes()
+            c_field = np.array([(qlen << 4) | 4, (rlen << 4) | 3], np.uint32)
         rec = struct.pack("<iiBBHHHiiii", int(tid[i]) if tid is not None else 0, pos, len(name), int(reads["mapq"][i]),
-                          reg2bin(pos, pos + max(rlen, 1)), len(c), int(reads["flag"][i]), qlen, -1, -1, 0)
-        rec += name + c.astype("<u4").tobytes() + sq + b"\xff" * qlen
+                          reg2bin(pos, pos + max(rlen, 1)), len(c_field), int(reads["flag"][i]), qlen, -1, -1, 0)
+        rec += name + c_field.astype("<u4").tobytes() + sq + b"\xff" * qlen + aux
         w.write(struct.pack("<i", len(rec)) + rec)
     w.close()
 

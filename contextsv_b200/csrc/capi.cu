@@ -100,7 +100,7 @@ static int check_overflow(csv_ctx* ctx, csv_batch* b, uint32_t* sc)
         return CSV_ERR_LIMIT;
     }
     if (sc[SC_BAD_GAPS]) {
-        set_error("csv_reads::n_gap does not match the CIGAR: it must hold the number of D / N ops of every record");
+        set_error("csv_reads::n_gap / ref_len do not match the CIGAR: they must hold the number of D / N ops and the reference bases consumed of every record");
         return CSV_ERR_ARG;
     }
     if (b->have_sigs && sc[SC_N_SIG] > b->sig_cap) {
@@ -383,6 +383,11 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     // dozen ops into the record that crosses it; ONT-like batches keep the op-level pre-pass)
     static const bool rec_ok = !(getenv("CSV_REC_PREPASS") && atoi(getenv("CSV_REC_PREPASS")) == 0);
     b->rec_prepass = rec_ok && r->n_gap != nullptr && r->n_reads > 0 && r->n_ops <= (uint64_t)r->n_reads * 1024u;
+    // ... and with the reference length of every record the tile ranges need nothing from the walk (single-chunk passes)
+    // Measured on B200 (profiles/r2_history.md): beside the walk the ranges cost the walk more than they save after it
+    // (3.88 against 3.70 ms per whole-genome step, whatever the stream priority), so this is opt-in: CSV_CLAIM_REFLEN=1.
+    static const bool claim_ok = getenv("CSV_CLAIM_REFLEN") && atoi(getenv("CSV_CLAIM_REFLEN")) != 0;
+    b->claimed_ref = claim_ok && b->rec_prepass && r->ref_len != nullptr && b->chunks.size() == 1;
     b->ev_cap = 2 * (r->n_ops + (uint64_t)r->n_reads) + 2;      // exact bound: 2 per record + 2 per D/N op
     b->sig_cap = std::max<uint64_t>(16, std::min<uint64_t>(r->n_ops, std::max<uint64_t>(1u << 20, r->n_ops / 16)));
 
@@ -391,7 +396,8 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pos0.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16, &ctx->pool)); CSV_TRY(b->d_mapq.ensure(nr + 16, &ctx->pool));
     CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8, &ctx->pool)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64, &ctx->pool));
-    if (b->rec_prepass) { CSV_TRY(b->d_n_gap.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ev_check.ensure((nr + 2) * 4, &ctx->pool)); }
+    if (b->rec_prepass) CSV_TRY(b->d_n_gap.ensure(nr * 4 + 16, &ctx->pool));
+    if (b->claimed_ref) CSV_TRY(b->d_ref_len.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_span_rq.ensure(((size_t)b->n_spans + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_key.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 512, &ctx->pool));   // the walk copies 272 bytes per span, also for the last one
     CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4, &ctx->pool));
@@ -420,6 +426,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
         CSV_CUDA(cudaMemcpyAsync(b->d_mapq.p, r->mapq, nr, cudaMemcpyHostToDevice, st));
         CSV_CUDA(cudaMemcpyAsync(b->d_cig_off.p, r->cig_off, (nr + 1) * 8, cudaMemcpyHostToDevice, st));
         if (b->rec_prepass) CSV_CUDA(cudaMemcpyAsync(b->d_n_gap.p, r->n_gap, nr * 4, cudaMemcpyHostToDevice, st));
+        if (b->claimed_ref) CSV_CUDA(cudaMemcpyAsync(b->d_ref_len.p, r->ref_len, nr * 4, cudaMemcpyHostToDevice, st));
     } else {
         CSV_CUDA(cudaMemsetAsync(b->d_cig_off.p, 0, 8, st));
     }
@@ -513,6 +520,23 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         StageTimer t(ctx, ST_TILE_RANGES);
         CSV_TRY(launch_tile_hi(ctx, b));                                 // beside the walk
     }
+    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p)); }
+    const bool ranges_first = p->want_depth && b->claimed_ref;           // csv_reads::ref_len: the tile ranges run BESIDE the walk
+    if (ranges_first) {
+        // on the HIGH-priority side stream: the handful of CTAs of the prefix max and the range searches take the first
+        // slots the walk's CTAs free (at normal priority they queue behind the walk's whole grid and the look-back
+        // chain crawls); the tile stream picks the result up through an event
+        CSV_TRY(side_fork(ctx));                                         // after the record scan: ev_start[] is final
+        CSV_CUDA(cudaEventRecord(ctx->ev_tile_join, ctx->tile_stream));  // ... and after k_tile_hi (tile stream): the ranges read its r_hi
+        CSV_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_tile_join, 0));
+        {
+            SideScope side(ctx);
+            StageTimer t(ctx, ST_TILE_RANGES);
+            CSV_TRY(launch_tile_ranges(ctx, b, 0));
+        }
+        CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_join, 0));
+    }
     for (uint32_t c = 0; c < nc; c++) {
         { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1)); }
         CSV_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->main_stream));
@@ -520,7 +544,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
             const uint32_t tc = nc == 1 ? 0 : c - 1;                     // its records are complete now
             CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_chunk[c], 0));
             TileScope ts(ctx);
-            { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, tc)); }
+            if (!ranges_first) { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, tc)); }
             { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b, tc)); }
         }
     }

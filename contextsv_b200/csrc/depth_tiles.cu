@@ -130,10 +130,12 @@ __device__ __forceinline__ uint32_t lookback_max_u32(unsigned long long* status,
     return excl;
 }
 
-__global__ void __launch_bounds__(kPmThreads) k_pmax_chained(const unsigned long long* __restrict__ meta, const uint32_t* __restrict__ ref_end,
+// claim (optional): the pass runs BEFORE the walk on what the caller's csv_reads::ref_len promises -- ref_end[k] is derived
+// here from the record's metadata and claimed reference length (and stored: the walk compares it with what it finds).
+struct PmClaim { const uint4* meta4; const uint32_t* ref_len; const uint32_t* ne_idx; };
+__global__ void __launch_bounds__(kPmThreads) k_pmax_chained(const unsigned long long* __restrict__ meta, uint32_t* __restrict__ ref_end,
                                                              uint32_t* scalars, const uint32_t* bounds, unsigned long long* pmax,
-                                                             uint32_t* ticket, unsigned long long* status, uint32_t epoch,
-                                                             const uint32_t* __restrict__ ev_start, const uint32_t* __restrict__ ev_check)
+                                                             uint32_t* ticket, unsigned long long* status, uint32_t epoch, const PmClaim claim)
 {
     // Global loads and stores are striped (lane-contiguous, one 256-byte row per warp and instruction); the scan wants
     // kPmItems consecutive records per thread.  The tile changes hands in shared memory, rows padded by one word per
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(kPmThreads) k_pmax_chained(const unsigned long
     __shared__ uint32_t s_tile, s_excl;
     const uint32_t kb = bounds[0], n = bounds[1] - kb;
     meta += kb; ref_end += kb; pmax += kb;
-    if (ev_check) { ev_start += kb; ev_check += kb; }
+    const uint4* meta4 = claim.meta4 ? claim.meta4 + kb : nullptr;
+    const uint32_t* ne_idx = claim.meta4 ? claim.ne_idx + kb : nullptr;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = (uint32_t)(((uint64_t)n + kPmTile - 1) / kPmTile);
     for (;;) {
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kPmThreads) k_pmax_chained(const unsigned long
         const uint32_t t = s_tile;
         if (t >= n_tiles) break;
         const uint64_t base = (uint64_t)t * kPmTile;
-        bool unsorted = false, bad_gaps = false;
+        bool unsorted = false;
 #pragma unroll
         for (int j = 0; j < kPmItems; j++) {
             const uint32_t i = j * kPmThreads + threadIdx.x;
@@ -161,17 +164,22 @@ __global__ void __launch_bounds__(kPmThreads) k_pmax_chained(const unsigned long
             unsigned long long v = 0ull;
             if (k < n) {
                 const unsigned long long key = meta[k];
-                v = (key & 0xffffffff00000000ull) | ref_end[k];
+                uint32_t re;
+                if (meta4) {
+                    // the walk's rule (k_walk, phase D): a record that takes part in the depth ends one past its last covered
+                    // index = (uint32)pos0 + 1 + reference bases consumed; any other record counts as 0
+                    const uint4 m = meta4[k];
+                    const bool live = ((m.z >> 30) & 1u) && m.x + 1u < m.y;
+                    re = live ? m.x + 1u + claim.ref_len[ne_idx[k]] : 0u;
+                    ref_end[k] = re;
+                } else re = ref_end[k];
+                v = (key & 0xffffffff00000000ull) | re;
                 // coordinate order check rides along: (tid, pos0 + 1) must not decrease (also across chunk borders)
                 if (kb + k > 0 && meta[(long long)k - 1] > key) unsorted = true;
-                // ... and so does the check of the caller's D/N counts: the event slot the walk reached at the end of the
-                // record against the one the record scan derived from csv_reads::n_gap
-                if (ev_check && ev_check[k + 1] != ev_start[k + 1]) bad_gaps = true;
             }
             s_v[i + i / kPmItems] = v;
         }
         if (unsorted) scalars[SC_UNSORTED] = 1;
-        if (bad_gaps) scalars[SC_BAD_GAPS] = 1;
         __syncthreads();
         // blocked arrangement: thread owns kPmItems consecutive records
         const uint32_t o = threadIdx.x * (kPmItems + 1);
@@ -309,7 +317,7 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
     const PipeChunk& ch = b->chunks[c];
     if (ch.tiles.empty()) return CSV_OK;
     const unsigned long long* meta = b->d_key.as<unsigned long long>();
-    const uint32_t* ref_end = b->d_ref_end.as<uint32_t>();
+    uint32_t* ref_end = b->d_ref_end.as<uint32_t>();
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
     const uint32_t* bounds = b->d_chunk_bounds.as<uint32_t>() + c;
     unsigned long long* part = b->d_pmax_part.as<unsigned long long>();
@@ -319,8 +327,9 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
         const uint32_t grid = n_part < (uint32_t)ctx->sm_count * 8 ? n_part : (uint32_t)ctx->sm_count * 8;
         // ticket and status words are the batch's own: this launch runs on the tile stream beside chained scans of the
         // signature side stream, which share the context's
-        k_pmax_chained<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, bounds, pmax, b->d_tickets.as<uint32_t>() + c, part, next_epoch(ctx),
-                                                             b->d_ev_start.as<uint32_t>(), b->rec_prepass ? b->d_ev_check.as<uint32_t>() : nullptr);
+        PmClaim claim = {nullptr, nullptr, nullptr};
+        if (b->claimed_ref) claim = PmClaim{b->d_meta.as<uint4>(), b->d_ref_len.as<uint32_t>(), b->d_ne_idx.as<uint32_t>()};
+        k_pmax_chained<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, bounds, pmax, b->d_tickets.as<uint32_t>() + c, part, next_epoch(ctx), claim);
         ctx->launches++;
     }
     for (const auto& tr : ch.tiles) {

@@ -54,7 +54,8 @@ void PackedReads::append(const bam1_t* b, bool keep_seq, bool keep_name, uint64_
     }
     cig_off.push_back(cigar.size());
     ref_end.push_back((uint32_t)b->core.pos + 1u + rlen);
-    n_gap.push_back(gaps);                                  // csv_reads::n_gap: the device's record-level pre-pass starts from it
+    n_gap.push_back(gaps);                                  // csv_reads::n_gap / ref_len: the device's record-level pre-pass starts from them
+    ref_len.push_back(rlen);
     if (keep_seq && want_seq) {
         const uint8_t* s = bam_get_seq(b);
         seq4[idx].assign(s, s + ((size_t)b->core.l_qseq + 1) / 2);
@@ -69,7 +70,7 @@ void PackedReads::append(const bam1_t* b, bool keep_seq, bool keep_name, uint64_
 
 void PackedReads::clear()
 {
-    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); n_gap.clear(); serial.clear(); seq4.clear();
+    tid.clear(); pos0.clear(); flag.clear(); mapq.clear(); cigar.clear(); ref_end.clear(); n_gap.clear(); ref_len.clear(); serial.clear(); seq4.clear();
     names.clear(); name_off.clear();
     cig_off.clear(); cig_off.push_back(0);
 }
@@ -81,7 +82,7 @@ void PackedReads::copy_reaching(uint32_t cut, PackedReads& k) const
         if (ref_end[i] <= cut) continue;
         const uint32_t j = (uint32_t)k.pos0.size();
         k.tid.push_back(tid[i]); k.pos0.push_back(pos0[i]); k.flag.push_back(flag[i]); k.mapq.push_back(mapq[i]); k.ref_end.push_back(ref_end[i]);
-        k.n_gap.push_back(n_gap[i]); k.serial.push_back(serial[i]);
+        k.n_gap.push_back(n_gap[i]); k.ref_len.push_back(ref_len[i]); k.serial.push_back(serial[i]);
         k.cigar.append(cigar.data() + cig_off[i], (size_t)(cig_off[i + 1] - cig_off[i]));
         k.cig_off.push_back(k.cigar.size());
         const auto s = seq4.find((uint32_t)i);
@@ -160,11 +161,11 @@ const char* file_name(samFile* fp)
 
 csv_reads PackedReads::view() const
 {
-    csv_reads r;
+    csv_reads r = {};
     r.n_reads = (uint32_t)pos0.size();
     r.n_ops = cigar.size();
     r.tid = tid.data(); r.pos0 = pos0.data(); r.flag = flag.data(); r.mapq = mapq.data();
-    r.cig_off = cig_off.data(); r.cigar = cigar.data(); r.n_gap = n_gap.data();
+    r.cig_off = cig_off.data(); r.cigar = cigar.data(); r.n_gap = n_gap.data(); r.ref_len = ref_len.data();
     return r;
 }
 

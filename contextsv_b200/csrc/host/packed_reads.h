@@ -80,6 +80,7 @@ struct PackedReads {
     Slab<uint32_t> cigar;
     Slab<uint32_t> ref_end;          // pos0 + 1 + reference bases consumed: depth index one past the last covered base
     Slab<uint32_t> n_gap;            // D / N ops per record (csv_reads::n_gap)
+    Slab<uint32_t> ref_len;          // reference bases consumed per record (csv_reads::ref_len)
     Slab<uint64_t> serial;           // number of the record in its iterator's order (stays with a record that moves on as a halo)
     // 4-bit bases of the few records that carry an I / S op of exactly 50 bases: the only place the
     // reference looks at the sequence on this path (literal ALT allele, src/sv_caller.cpp:572-591).  Keyed by index.

@@ -16,7 +16,12 @@
 
 namespace csv {
 
-// position of every entry inside its run of equal hi = number of entries of the run with a smaller lo
+// position of every entry inside its run of equal hi = number of entries of the run with a smaller lo.
+// The run's bounds come from two binary searches over the sorted hi (O(log n) however long the run is); the ranking
+// itself reads the run once per entry.  Runs are a handful of entries (one per read over a breakpoint); a pile-up of n
+// entries at one (region, start) costs n^2 comparisons, but every lane of a warp inside the run reads the SAME entry in
+// the same iteration (two broadcast loads for 32 comparisons): 2e5 entries at one coordinate take a few milliseconds
+// (tests/test_gpu_parity.py::test_signature_pileup_at_one_start).
 __global__ void k_sig_tiefix(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ raw_lo, const uint32_t* __restrict__ val,
                              const uint32_t* scalars, uint32_t* out)
 {
@@ -24,8 +29,27 @@ __global__ void k_sig_tiefix(const unsigned long long* __restrict__ hi, const un
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long h = hi[i];
         uint32_t a = i, b = i + 1;
-        while (a > 0 && hi[a - 1] == h) a--;
-        while (b < n && hi[b] == h) b++;
+        const bool tie_left = i > 0 && hi[i - 1] == h, tie_right = i + 1 < n && hi[i + 1] == h;
+        if (tie_left) {                                      // first index with hi == h: gallop down, then bisect
+            uint32_t lo_ = 0, hi_ = i - 1;                   // hi[hi_] == h
+            for (uint32_t step = 1; hi_ > 0; step <<= 1) {
+                const uint32_t probe = hi_ > step ? hi_ - step : 0u;
+                if (hi[probe] != h) { lo_ = probe + 1; break; }
+                hi_ = probe;
+            }
+            while (lo_ < hi_) { const uint32_t mid = lo_ + ((hi_ - lo_) >> 1); if (hi[mid] == h) hi_ = mid; else lo_ = mid + 1; }
+            a = hi_;
+        }
+        if (tie_right) {                                     // one past the last index with hi == h
+            uint32_t lo_ = i + 1, hi_ = n;                   // hi[lo_] == h
+            for (uint32_t step = 1; lo_ + 1 < n; step <<= 1) {
+                const uint32_t probe = n - lo_ > step ? lo_ + step : n;
+                if (probe >= n || hi[probe] != h) { hi_ = probe < n ? probe : n; break; }
+                lo_ = probe;
+            }
+            while (lo_ + 1 < hi_) { const uint32_t mid = lo_ + ((hi_ - lo_) >> 1); if (hi[mid] == h) lo_ = mid; else hi_ = mid; }
+            b = lo_ + 1;
+        }
         const uint32_t mine = val[i];
         uint32_t rank = 0;
         if (b - a > 1) {

@@ -43,8 +43,9 @@ struct WalkParams {
     const uint32_t* n_gap;      // [n_reads] or null
     const unsigned long long* cig_off;
     const uint32_t* ne_idx;     // compact index -> record index
-    uint32_t ev_given;          // ev_start[] comes from the record scan: the walk leaves what it finds in ev_check[] instead
-    uint32_t* ev_check;         // [n_nonempty + 1] event slot the walk reached at the end of every record (compared by k_pmax_chained)
+    uint32_t ev_given;          // ev_start[] comes from the record scan (csv_reads::n_gap): the walk compares instead of writing
+    uint32_t ref_given;         // ref_end[] comes from csv_reads::ref_len (k_pmax_chained, beside the walk): the walk checks the claim
+    const uint32_t* ref_len;    // [n_reads] the caller's claim, by record index
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
@@ -514,8 +515,12 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                         const uint32_t ie = cb + biasb;                      // one past the last covered index
                         if (ie - p1 >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
                         P.events[slot - 1u] = ie;
-                        P.ref_end[kt] = p1 != kDeadPos ? ie : 0u;            // not clipped to the map: only compared with tile starts
-                        (P.ev_given ? P.ev_check : P.ev_start)[kt + 1u] = slot;   // given: k_pmax_chained compares the two
+                        const uint32_t re = p1 != kDeadPos ? ie : 0u;        // not clipped to the map: only compared with tile starts
+                        // what the caller's per-record counts promised (csv_reads::n_gap / ref_len) is checked here, at the
+                        // one place the truth is known; a wrong count voids the pass (CSV_ERR_ARG at the first fetch)
+                        // (ref_end[] itself is being written by k_pmax_chained on another stream: the claim is read at its source)
+                        if (P.ref_given) { if (p1 != kDeadPos && ie - p1 != P.ref_len[P.ne_idx[kt]]) P.scalars[SC_BAD_GAPS] = 1u; } else P.ref_end[kt] = re;
+                        if (P.ev_given) { if (P.ev_start[kt + 1u] != slot) P.scalars[SC_BAD_GAPS] = 1u; } else P.ev_start[kt + 1u] = slot;
                     }
                     if (b < t.n_valid) {
                         klb++;
@@ -529,11 +534,8 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
     }
 }
 
-// Walks the spans [span0, span1); span0 must be a multiple of kSpanChunk and the chunks of one pass must come in
-// order on one stream (the carry of the span scan lives in b->d_scan_carry).
-int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1)
+static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
 {
-    if (b->n_ops == 0 || span0 >= span1) return CSV_OK;
     WalkParams P;
     P.cigar = b->d_cigar.as<uint32_t>();
     P.n_ops = (uint32_t)b->n_ops;
@@ -543,8 +545,8 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     P.span_pre = b->d_span_pre.as<WalkAgg>();
     P.chunk_agg = b->d_span_status.as<WalkAgg>();
     P.n_spans = b->n_spans;
-    P.span_base = span0;
-    P.span_end = span1;
+    P.span_base = 0;
+    P.span_end = b->n_spans;
     P.span_desc = b->d_span_desc.as<uint4>();
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
@@ -565,11 +567,17 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
     P.cig_off = b->d_cig_off.as<unsigned long long>();
     P.ne_idx = b->d_ne_idx.as<uint32_t>();
     P.ev_given = b->rec_prepass ? 1u : 0u;
-    P.ev_check = b->d_ev_check.as<uint32_t>();
-    const uint32_t n = span1 - span0;
-    if (b->rec_prepass) {
-        // record-level pre-pass, once per pass (not per pipeline chunk)
-        if (span0 == 0) {
+    P.ref_given = b->claimed_ref && p->want_depth ? 1u : 0u;
+    P.ref_len = b->d_ref_len.as<uint32_t>();
+    return P;
+}
+
+// Record-level pre-pass of a batch whose caller counted the D / N ops per record: once per pass, before the walk.
+int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
+{
+    if (!b->rec_prepass || b->n_ops == 0) return CSV_OK;
+    const WalkParams P = walk_params(b, p);
+    {
             const WalkParams Q = P;
             const uint32_t* n_rec = P.scalars + SC_N_NONEMPTY;
             auto in = [=] __device__(uint64_t k) -> uint32_t {
@@ -598,8 +606,21 @@ int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t s
                 k_span_carry<<<(n_carry + per_cta - 1) / per_cta, 256, 0, ctx->stream>>>(P, n_carry);
                 ctx->launches++;
             }
-        }
-    } else {
+    }
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
+// Walks the spans [span0, span1); span0 must be a multiple of kSpanChunk and the chunks of one pass must come in
+// order on one stream (the carry of the span scan lives in b->d_scan_carry).
+int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1)
+{
+    if (b->n_ops == 0 || span0 >= span1) return CSV_OK;
+    WalkParams P = walk_params(b, p);
+    P.span_base = span0;
+    P.span_end = span1;
+    const uint32_t n = span1 - span0;
+    if (!b->rec_prepass) {
         if (span0 == 0) CSV_CUDA(cudaMemsetAsync(b->d_scan_carry.p, 0, sizeof(WalkAgg), ctx->stream));
         const uint32_t sc0 = span0 / kSpanChunk, sc1 = (span1 + kSpanChunk - 1) / kSpanChunk;
         k_span_agg<<<n, kWalkThreads, 0, ctx->stream>>>(P);

@@ -42,14 +42,19 @@ extern "C" void csv_host_widen_u8(const uint8_t* src, uint32_t* dst, size_t n)
     if (have_avx2) widen_avx2(src, dst, n); else widen_scalar(src, dst, n);
 }
 
-extern "C" void csv_host_count_gaps(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, int threads)
+extern "C" void csv_host_record_stats(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, uint32_t* ref_len_out, int threads)
 {
-    if (!cigar || !cig_off || !n_gap_out || n_reads == 0) return;
+    if (!cigar || !cig_off || (!n_gap_out && !ref_len_out) || n_reads == 0) return;
     auto work = [=](uint32_t r0, uint32_t r1) {
         for (uint32_t r = r0; r < r1; r++) {
-            uint32_t g = 0;
-            for (uint64_t o = cig_off[r]; o < cig_off[r + 1]; o++) { const uint32_t op = cigar[o] & 15u; g += (op == 2u) | (op == 3u); }   // BAM_CDEL, BAM_CREF_SKIP
-            n_gap_out[r] = g;
+            uint32_t g = 0, rl = 0;
+            for (uint64_t o = cig_off[r]; o < cig_off[r + 1]; o++) {
+                const uint32_t op = cigar[o] & 15u;
+                g += (op == 2u) | (op == 3u);                                  // BAM_CDEL, BAM_CREF_SKIP
+                if ((0x18du >> op) & 1u) rl += cigar[o] >> 4;                   // M D N = X consume reference
+            }
+            if (n_gap_out) n_gap_out[r] = g;
+            if (ref_len_out) ref_len_out[r] = rl;
         }
     };
     unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
@@ -59,4 +64,9 @@ extern "C" void csv_host_count_gaps(const uint32_t* cigar, const uint64_t* cig_o
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nt; t++) pool.emplace_back(work, (uint32_t)((uint64_t)n_reads * t / nt), (uint32_t)((uint64_t)n_reads * (t + 1) / nt));
     for (auto& th : pool) th.join();
+}
+
+extern "C" void csv_host_count_gaps(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, int threads)
+{
+    csv_host_record_stats(cigar, cig_off, n_reads, n_gap_out, nullptr, threads);
 }

@@ -109,8 +109,9 @@ def select_reads(reads, regions, ends=None):
         "pos0": reads["pos0"][i0:i1], "flag": reads["flag"][i0:i1], "mapq": reads["mapq"][i0:i1],
         "cig_off": (off[i0:i1 + 1] - np.uint64(o0)).astype(np.uint64), "cigar": reads["cigar"][o0:o1],
     }
-    if reads.get("n_gap") is not None:
-        sub["n_gap"] = reads["n_gap"][i0:i1]
+    for k in ("n_gap", "ref_len"):
+        if reads.get(k) is not None:
+            sub[k] = reads[k][i0:i1]
     return sub, i0
 
 

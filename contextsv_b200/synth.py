@@ -66,7 +66,7 @@ def generate(contig_len, params=None, alloc=None, count_gaps=True, **kw):
     r = {"n_reads": n, "n_ops": int(n_ops.value), "tid": tid, "pos0": pos0, "flag": flag, "mapq": mapq,
          "cig_off": cig_off, "cigar": cigar[: int(n_ops.value)], "contig_len": cl}
     if count_gaps:
-        # what a packer leaves in csv_reads::n_gap while it copies the CIGAR words: D / N ops per record
+        # what a packer leaves in csv_reads::n_gap / ref_len while it copies the CIGAR words: D / N ops and reference bases per record
         from . import _capi
-        r["n_gap"] = _capi.count_gaps(r, alloc)
+        r["n_gap"], r["ref_len"] = _capi.record_stats(r, alloc)
     return r

@@ -100,6 +100,10 @@ typedef struct {
                                /* with the counts the device finds where each record's depth events go from a  */
                                /* scan over RECORDS instead of a second pass over every CIGAR word.  Checked   */
                                /* against the CIGAR during the scan: a wrong count fails with CSV_ERR_ARG.    */
+    const uint32_t* ref_len;   /* [n_reads] optional, used together with n_gap: reference bases the record's   */
+                               /* CIGAR consumes (M, D, N, =, X) -- bam_endpos - pos, which a packer has at    */
+                               /* hand.  With it the record ranges of the depth tiles are computed beside the  */
+                               /* CIGAR walk instead of after it.  Checked like n_gap.                         */
 } csv_reads;
 
 /* A slice [beg,end) of one contig's depth map.  Indices are those of the
@@ -266,6 +270,8 @@ int csv_record_summary(csv_ctx* ctx, csv_batch* b, int32_t* endpos_out, int32_t*
 /* Host helper for packers that fill csv_reads::n_gap after the fact: n_gap_out[i] = number of D / N ops of record i
  * (threads = 0: all cores).  No device needed. */
 void csv_host_count_gaps(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, int threads);
+/* ... and csv_reads::ref_len with them (either output may be NULL). */
+void csv_host_record_stats(const uint32_t* cigar, const uint64_t* cig_off, uint32_t n_reads, uint32_t* n_gap_out, uint32_t* ref_len_out, int threads);
 
 /* ------------------------------------------------------- synthetic inputs */
 

@@ -158,6 +158,17 @@ class Reference:
         self.lib = C.CDLL(path)
         self.lib.ref_cigar_scan.restype = C.c_int64
         self.lib.ref_largest_cluster.restype = C.c_uint64
+        if hasattr(self.lib, "ref_split_dump"):
+            self.lib.ref_split_dump.restype = C.c_int64
+            self.lib.ref_split_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
+
+    def split_dump(self, bam_path, out_path, chrom="", threads=1):
+        """SVCaller::findSplitSVSignatures (sv_caller.cpp:68-504) on a BAM file; candidates appended to out_path, one
+        line each (chr, start, end, SVType, ALT, evidence bits, aln_offset, cluster_size).  Returns their number."""
+        n = int(self.lib.ref_split_dump(bam_path.encode(), chrom.encode(), int(threads), out_path.encode()))
+        if n < 0:
+            raise RuntimeError("ref_split_dump failed")
+        return n
 
     def _mem(self, r, contig_len, seq4=None, seq_off=None):
         r = norm_reads(r)

@@ -209,4 +209,32 @@ int64_t ref_record_summary(const csvshim_mem* m, int32_t tid, int32_t* endpos_ou
     return (int64_t)n;
 }
 
+
+/* SVCaller::findSplitSVSignatures (sv_caller.cpp:68-504) on a BAM file: the candidates of every chromosome, appended to
+ * out_path one per line as chr, start, end, SVType, ALT, evidence bits, aln_offset, cluster_size -- the format the
+ * drop-in's CONTEXTSV_B200_DUMP_SPLIT hook writes.  Chromosomes come in the reference's own (hash map) order.
+ * Returns the number of candidates, or -1. */
+int64_t ref_split_dump(const char* bam_path, const char* chr_or_empty, int threads, const char* out_path)
+{
+    std::unordered_map<std::string, std::vector<SVCall>> calls;
+    try {
+        Quiet q(g_quiet);
+        InputData in;
+        in.setLongReadBam(bam_path);
+        in.setThreadCount(threads > 0 ? threads : 1);
+        if (chr_or_empty && *chr_or_empty) in.setChromosome(chr_or_empty);
+        SVCaller caller;
+        caller.findSplitSVSignatures(calls, in);
+    } catch (const std::exception&) { return -1; }
+    FILE* f = fopen(out_path, "a");
+    if (!f) return -1;
+    int64_t n = 0;
+    for (const auto& e : calls)
+        for (const SVCall& c : e.second) {
+            fprintf(f, "%s\t%u\t%u\t%d\t%s\t%lu\t%d\t%d\n", e.first.c_str(), c.start, c.end, (int)c.sv_type, c.alt_allele.c_str(), c.aln_type.to_ulong(), c.aln_offset, c.cluster_size);
+            n++;
+        }
+    fclose(f);
+    return n;
+}
 }  // extern "C"

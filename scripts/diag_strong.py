@@ -29,11 +29,20 @@ bt.free()
 cs = np.zeros(len(contig_len), np.int64); ss = np.zeros(len(contig_len), np.int64); zs = np.zeros(len(contig_len), np.int64)
 for rank, regs in enumerate(plan):
     sub, base = shard.select_reads(full, regs)
+    if os.environ.get("DIAG_PINNED"):
+        from contextsv_b200 import _capi
+        sub = {k: (lambda p, v: (p.__setitem__(slice(None), v), p)[1])(_capi.pinned_empty(len(v), v.dtype), v) if isinstance(v, np.ndarray) else v for k, v in sub.items()}
     b = api.Batch(ctx, sub, regs)
+    for _ in range(int(os.environ.get("DIAG_REPEAT", "0"))):          # what bench.py does before its e2e step: scans, free, same geometry again from the pool
+        b.scan(want_depth=True, want_sigs=True); b.sigs_dbscan1d(100.0, 5, fetch=False)
+    if os.environ.get("DIAG_REPEAT"):
+        ctx.sync(); b.free(); b = api.Batch(ctx, sub, regs)
     b.scan(want_depth=True, want_sigs=True)
     ck = b.depth_checksum().astype(np.int64); s, z = b.depth_stats()
     for i, (t, bb, ee, m) in enumerate(regs):
         cs[t] += ck[i]; ss[t] += int(s[i]); zs[t] += int(z[i])
+        if (bb, ee) == (0, m) and (int(s[i]) != int(s1[t]) or int(z[i]) != int(z1[t])):
+            print("shard %d region %s: sum %d / %d nz %d / %d   <-- DIFFERS" % (rank, (t, bb, ee, m), int(s[i]), int(s1[t]), int(z[i]), int(z1[t])))
         if (t, bb, ee) in keep:
             d = b.depth(i)
             bad = np.nonzero(d != keep[(t, bb, ee)])[0]

@@ -7,7 +7,10 @@ import subprocess
 
 import pytest
 
+import numpy as np
+
 from contextsv_b200 import bamio, synth
+import util
 
 pytestmark = pytest.mark.gpu
 
@@ -39,4 +42,39 @@ def test_cli_vcf_identical(tmp_path, extra, max_ops):
     want = run_cli(ref_exe, d, d + "/out_ref", extra)
     got = run_cli(gpu_exe, d, d + "/out_gpu", extra, {"CONTEXTSV_MAX_OPS": max_ops} if max_ops else None)
     assert len([l for l in want if not l.startswith("#")]) > 10
+    assert got == want
+
+
+def split_bam(d, seed=23):
+    clen, names = [400000, 260000], ["chr21", "chr22"]
+    r = synth.generate(clen, seed=seed, n_sv=40, coverage=12.0, frac_len50=0.2)
+    r2, qnames = util.add_split_events(r, clen, np.random.default_rng(seed), n_events=12)
+    bamio.write_bam(d + "/x.bam", r2, names, clen, seed=1, qnames=qnames)
+    bamio.write_fasta(d + "/x.fa", names, clen)
+    open(d + "/snps.vcf", "w").write("##fileformat=VCFv4.2\n")
+    return r2
+
+
+@pytest.mark.parametrize("extra,max_ops", [((), None), (("-c", "chr22"), None), ((), "4000")])
+def test_cli_split_reads_identical(tmp_path, extra, max_ops):
+    """a BAM with split alignments (primary + supplementary records sharing a query name).  The
+    drop-in decodes the file ONCE -- its findSplitSVSignatures works from what the depth pass parked (device-side
+    record summaries, one batched DBSCAN1D launch sequence for all overlap groups) -- and must produce the reference's
+    split candidates line for line and the reference's VCF byte for byte."""
+    from oracle.oracle_py import Reference
+    ref_exe, gpu_exe = os.path.join(REF_DIR, "contextsv_ref"), os.path.join(REF_DIR, "contextsv_gpu")
+    if not (os.path.exists(ref_exe) and os.path.exists(gpu_exe)):
+        pytest.skip("oracle/_ref CLIs not built (make -C oracle ref dropin)")
+    d = str(tmp_path)
+    split_bam(d)
+    chrom = extra[1] if extra else ""
+    n_ref = Reference().split_dump(d + "/x.bam", d + "/split_ref.txt", chrom=chrom)
+    assert n_ref >= 6
+    want = run_cli(ref_exe, d, d + "/out_ref", extra)
+    env = {"CONTEXTSV_B200_DUMP_SPLIT": d + "/split_gpu.txt", "CONTEXTSV_B200_STATS": "1"}
+    if max_ops:
+        env["CONTEXTSV_MAX_OPS"] = max_ops
+    got = run_cli(gpu_exe, d, d + "/out_gpu", extra, env)
+    assert sorted(open(d + "/split_gpu.txt").read().splitlines()) == sorted(open(d + "/split_ref.txt").read().splitlines())
+    assert any("SPLIT" in l for l in want if not l.startswith("#"))
     assert got == want

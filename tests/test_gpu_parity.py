@@ -7,7 +7,7 @@ import pytest
 
 import util
 from util import M, I, D, N, S, H, P, EQ, X
-from contextsv_b200 import api
+from contextsv_b200 import api, shard
 from contextsv_b200._capi import CsvReads, CsvRegion, CsvSigs, check, lib, ptr, reads_struct
 
 pytestmark = pytest.mark.gpu
@@ -94,7 +94,7 @@ def test_long_reads_spanning_many_spans(ctx, oracle):
 
 def test_full_size_whole_genome_properties(ctx, oracle):
     """BASELINE configs[1] at full size (6.2 M reads, 375 M CIGAR ops, 3.1 G depth positions, one batch): exact parity with
-    the oracle on two whole contigs taken out of the full-size run, and size-independent properties on everything --
+    the oracle on every one of the 24 contigs, and size-independent properties on top --
     sum(depth) == covered bases counted from the CIGARs, INS / DEL signature counts == qualifying ops counted from the CIGARs, every
     region's signature list sorted the way addSVCall leaves it, DBSCAN1D labels dense per group, and a second pass over the
     resident batch reproducing the first bit for bit."""
@@ -138,17 +138,30 @@ def test_full_size_whole_genome_properties(ctx, oracle):
             l = lab[lo:hi][(sg["kind"][lo:hi] == 1) == is_del]
             ids = np.unique(l[l >= 0])
             assert np.all((l >= 0) | (l == -2)) and np.array_equal(ids, np.arange(len(ids)))
-    # ---- exact parity on two whole contigs out of the full-size run
-    for t in (20, 21):
+    # ---- exact parity on ALL 24 contigs of the full-size run (chr1-sized ones included: 5x the records per region of
+    # chr21, equal-start runs in the ranking kernel, tile offsets near 2^31 bytes): the oracle side -- per-base depth loop,
+    # O(N log N) signature order, closed-form DBSCAN1D -- runs one contig per host thread beside the fetches
+    import concurrent.futures as cf
+    import os
+
+    def oracle_side(t, got):
         d, s_, nz_ = oracle.depth(r, t, clen[t] + 1)
-        assert np.array_equal(b.depth(t), d) and int(sums[t]) == s_ and int(nzs[t]) == nz_
+        assert np.array_equal(got, d), "depth of contig %d" % t
+        assert int(sums[t]) == s_ and int(nzs[t]) == nz_, "stats of contig %d" % t
+        del d, got
         o = oracle.cigar_scan(r, t, clen[t] + 1)
         lo, hi = int(sg["region_off"][t]), int(sg["region_off"][t + 1])
+        assert hi - lo == len(o)
         for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
-            assert np.array_equal(sg[f][lo:hi], o[f]), f
+            assert np.array_equal(sg[f][lo:hi], o[f]), (t, f)
         for is_del in (True, False):
             m = (sg["kind"][lo:hi] == 1) == is_del
-            assert np.array_equal(lab[lo:hi][m], oracle.dbscan1d(sg["start"][lo:hi][m].astype(np.int32), 100.0, 5, fast=True))
+            assert np.array_equal(lab[lo:hi][m], oracle.dbscan1d(sg["start"][lo:hi][m].astype(np.int32), 100.0, 5, fast=True)), (t, is_del)
+        return t
+
+    with cf.ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1))) as ex:
+        futs = [ex.submit(oracle_side, t, b.depth(t)) for t in sorted(range(len(clen)), key=lambda t: -clen[t])]
+        assert sorted(f.result() for f in futs) == list(range(len(clen)))
     # ---- idempotence: the second pass over the resident batch gives the same bits
     d21 = b.depth(21).copy()
     b.scan(want_depth=True, want_sigs=True)
@@ -226,6 +239,23 @@ def test_record_level_prepass(ctx, oracle):
         with pytest.raises(CsvError, match="n_gap"):
             b.depth_stats()
         b.free()
+    # (d) ... and so is a wrong reference length (csv_reads::ref_len: the tile ranges are computed from it BEFORE the walk,
+    # the walk compares it with what the CIGAR says)
+    from contextsv_b200._capi import record_stats
+    g2, l2 = record_stats(r)
+    assert np.array_equal(g2, good) and np.array_equal(l2, r["ref_len"]) and np.array_equal(l2.astype(np.int64), shard.ref_end(r) - r["pos0"].astype(np.int64) - 1)
+    plain = np.nonzero((r["flag"] == 0) & (r["pos0"] > 1000))[0]
+    for delta in (1, -1, 5000):
+        bad = dict(r); l = l2.astype(np.int64).copy()
+        victim = int(plain[len(plain) // 3])
+        l[victim] = max(0, l[victim] + delta); bad["ref_len"] = l.astype(np.uint32)
+        b = run_batch(ctx, bad, api.whole_contig_regions([400_000]))
+        with pytest.raises(CsvError, match="ref_len"):
+            b.depth_stats()
+        b.free()
+    # without the lengths (n_gap only) the ranges are computed after the walk, as before
+    only_gaps = dict(r); only_gaps.pop("ref_len")
+    check_contigs(ctx, oracle, only_gaps, [400_000])
     check_contigs(ctx, oracle, r, [400_000])
 
 
@@ -446,6 +476,152 @@ def test_streamed_shards_by_op_budget(ctx, oracle):
             assert np.array_equal(labels[tid][m], oracle.dbscan1d(sg["start"][m].astype(np.int32), 100.0, 5, fast=True))
     with pytest.raises(ValueError):
         shard.plan_by_ops(r, clen, 2000)      # fewer ops than the records over one position hold
+
+
+def test_ont60x_full_contigs_streamed(ctx, oracle):
+    """BASELINE configs[2] at the contig sizes it names: 60x ONT ultra-long reads (N50 50 kb, ~10 % indel rate, ~0.2 CIGAR
+    ops per aligned base) over two whole GRCh38-sized contigs (chr21 + chr22: 0.96e9 CIGAR ops), scanned as a stream of
+    shards of at most 2^28 ops + records -- what the whole genome at this depth (~3.7e10 ops) needs on one device -- and
+    merged on the host.  Exact parity with the oracle: depth of every base, signatures in addSVCall order, DBSCAN1D labels."""
+    from contextsv_b200 import shard
+    import bench
+    clen = [shard.GRCH38[20][1], shard.GRCH38[21][1]]
+    r = util.synth_reads(clen, seed=20261018 + 3, n_sv=400, **bench.SYNTH_KW["ont60x_chr20"])
+    assert int(r["n_ops"]) > 900_000_000
+    max_ops = 1 << 28
+    assert len(shard.plan_by_ops(r, clen, max_ops)) >= 4
+    depth, (sums, nzs), sigs, labels = api.scan_streamed(ctx, r, clen, max_ops=max_ops, eps=100.0, min_pts=5)
+    import concurrent.futures as cf
+
+    def oracle_side(tid):
+        d, s, nz = oracle.depth(r, tid, clen[tid] + 1)
+        assert np.array_equal(depth[tid], d) and int(sums[tid]) == s and int(nzs[tid]) == nz
+        o = oracle.cigar_scan(r, tid, clen[tid] + 1)
+        sg = sigs[tid]
+        assert len(sg["start"]) == len(o) > 1000
+        for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+            assert np.array_equal(sg[f].astype(np.int64), o[f].astype(np.int64)), f
+        for is_del in (True, False):
+            m = (sg["kind"] == 1) if is_del else (sg["kind"] != 1)
+            assert np.array_equal(labels[tid][m], oracle.dbscan1d(sg["start"][m].astype(np.int32), 100.0, 5, fast=True))
+        return True
+    with cf.ThreadPoolExecutor(max_workers=2) as ex:
+        assert all(ex.map(oracle_side, range(len(clen))))
+
+
+def test_long_cigar_cg_tag_through_the_packer(ctx, oracle, tmp_path):
+    """A record with more than 65 535 CIGAR ops (reachable at config 3's read lengths): in the BAM its CIGAR lives in a CG:B,I tag
+    behind the placeholder <l_seq>S<ref_len>N (SAM spec 4.2.2).  BAM -> htslib iterator (the shim promotes the tag like
+    bam_read1 does) -> the C++ host packer -> GPU must give the depth and signatures of the real CIGAR."""
+    import ctypes
+    import subprocess
+    from contextsv_b200 import bamio, build
+    from oracle.oracle_py import make_reads
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host, shim = os.path.join(build.CSRC, "host"), os.path.join(root, "oracle", "htslib_shim")
+    so = str(tmp_path / "libhp.so")
+    p = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + shim, "-I" + os.path.join(root, "oracle"), "-I" + build.INC, "-I" + host,
+                        os.path.join(root, "tests", "native", "host_packer_harness.cpp"), os.path.join(host, "packed_reads.cpp"), os.path.join(shim, "shim.cpp"),
+                        "-o", so, "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    L = ctypes.CDLL(so)
+    L.hp_pack.restype = ctypes.c_void_p; L.hp_pack.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    L.hp_size.restype = ctypes.c_uint64; L.hp_size.argtypes = [ctypes.c_void_p]
+    L.hp_ops.restype = ctypes.c_uint64; L.hp_ops.argtypes = [ctypes.c_void_p]
+    L.hp_copy.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 7
+    L.hp_free.argtypes = [ctypes.c_void_p]
+    rng = np.random.default_rng(77)
+    clen = [900_000]
+    pos, cig = [], []
+    for i in range(40):
+        n_ops = 70_000 if i in (7, 23) else int(rng.integers(20, 3000))          # two records beyond the 16-bit op count
+        ops = []
+        for j in range(n_ops):
+            if j % 2 == 0:
+                ops.append((int(rng.integers(1, 9)), M))
+            else:
+                ops.append((60 if rng.random() < 0.002 else int(rng.integers(1, 3)), [I, D][int(rng.integers(0, 2))]))
+        pos.append(int(rng.integers(0, 200_000))); cig.append(ops)
+    order = np.argsort(pos, kind="stable")
+    r = make_reads(np.array([pos[i] for i in order], np.int32), [cig[i] for i in order])
+    assert int(np.diff(r["cig_off"].astype(np.int64)).max()) > 65_535
+    path = str(tmp_path / "long.bam")
+    bamio.write_bam(path, r, ["chrL"], clen, seed=5)
+    h = L.hp_pack(path.encode(), b"chrL", 0)
+    n, no = int(L.hp_size(h)), int(L.hp_ops(h))
+    assert n == int(r["n_reads"]) and no == int(r["n_ops"])                     # the placeholder CIGARs were replaced by the tags' contents
+    a = {"tid": np.zeros(n, np.int32), "pos0": np.zeros(n, np.int32), "flag": np.zeros(n, np.uint16), "mapq": np.zeros(n, np.uint8),
+         "cig_off": np.zeros(n + 1, np.uint64), "cigar": np.zeros(no, np.uint32), "ref_end": np.zeros(n, np.uint32)}
+    L.hp_copy(h, *[a[k].ctypes.data_as(ctypes.c_void_p) for k in ("tid", "pos0", "flag", "mapq", "cig_off", "cigar", "ref_end")])
+    L.hp_free(h)
+    assert np.array_equal(a["cigar"], r["cigar"]) and np.array_equal(a["cig_off"], r["cig_off"])
+    packed = {"n_reads": n, "n_ops": no, "tid": a["tid"], "pos0": a["pos0"], "flag": a["flag"], "mapq": a["mapq"], "cig_off": a["cig_off"], "cigar": a["cigar"]}
+    check_contigs(ctx, oracle, packed, clen)
+
+
+def test_against_the_compiled_reference_directly(ctx, reference):
+    """Closes the loop on the GPU box: the CUDA path against oracle/_ref -- the reference's own sources compiled unmodified
+    -- without the C restatement in between: depth, mean coverage, SVCall vectors (start, end, type, evidence, ALT) and
+    DBSCAN1D labels on synthetic HiFi records and on adversarial CIGARs."""
+    rng = np.random.default_rng(31)
+    cases = [(util.synth_reads([260_000, 90_000], seed=17, n_sv=80, coverage=22.0, frac_len50=0.3), [260_000, 90_000])]
+    for it in range(4):
+        clen = [int(rng.choice([2500, 12000, 70000])) for _ in range(int(rng.integers(1, 3)))]
+        cases.append((util.random_cigar_reads(rng, int(rng.integers(50, 400)), clen, n_tids=len(clen), weird=bool(it % 2)), clen))
+    for r, clen in cases:
+        seq4, seq_off = util.random_seq4(rng, r)
+        b = run_batch(ctx, r, api.whole_contig_regions(clen))
+        sums, nzs = b.depth_stats()
+        sg = b.sigs()
+        for tid in range(len(clen)):
+            d, s, nz, mean = reference.depth(r, tid, clen)
+            assert np.array_equal(b.depth(tid), d) and int(sums[tid]) == s and int(nzs[tid]) == nz
+            assert (float(s) / float(nz) if nz else 0.0) == mean
+            st, en, ty, ev, alts = reference.cigar_scan(r, tid, clen, seq4=seq4, seq_off=seq_off)
+            lo, hi = int(sg["region_off"][tid]), int(sg["region_off"][tid + 1])
+            assert hi - lo == len(st)
+            assert np.array_equal(sg["start"][lo:hi], st) and np.array_equal(sg["end"][lo:hi], en)
+            kind = sg["kind"][lo:hi]
+            assert np.array_equal(np.where(kind == 1, 0, 3), ty)                                 # SVType: DEL 0, INS 3
+            assert np.array_equal(1 << np.where(kind == 0, 0, np.where(kind == 1, 1, 2)), ev)     # CIGARINS / CIGARDEL / CIGARCLIP bit
+            for i in range(lo, hi):
+                one = {k: sg[k][i] for k in ("start", "end", "kind", "read_idx", "query_pos")}
+                assert util.oracle_alt(seq4, seq_off, one) == alts[i - lo]
+            for t_sv in (0, 3):
+                pts = st[ty == t_sv].astype(np.int32)
+                if len(pts) and len(pts) < 4000:
+                    lab = np.zeros(len(pts), np.int32)
+                    check(lib().csv_dbscan1d(ctx.h, ptr(pts), len(pts), 100.0, 5, ptr(lab), None))
+                    assert np.array_equal(lab, reference.dbscan1d(pts, 100.0, 5))
+        b.free()
+
+
+def test_signature_pileup_at_one_start(ctx, oracle):
+    """2e5 signatures that share one (region, start): amplicon-like data, every read carrying an insertion at the same
+    coordinate.  The radix sort only orders (region, start); the order inside the run -- (end, reverse insertion order) --
+    comes from the ranking kernel, which must stay exact and affordable for a run of this length."""
+    import time
+    from oracle.oracle_py import make_reads
+    rng = np.random.default_rng(3)
+    n = 200_000
+    lens = rng.integers(50, 90, n)
+    cig = [[(10, M), (int(l), I), (20, M)] for l in lens]
+    r = make_reads(np.full(n, 1000, np.int32), cig)
+    clen = [5000]
+    b = run_batch(ctx, r, api.whole_contig_regions(clen))
+    t0 = time.perf_counter()
+    sg = b.sigs()
+    dt = time.perf_counter() - t0
+    o = oracle.cigar_scan(r, 0, clen[0] + 1)
+    assert len(o) == n == len(sg["start"]) and np.all(sg["start"] == 1011)
+    for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+        assert np.array_equal(sg[f], o[f]), f
+    assert dt < 5.0, "ranking a run of %d took %.1f s" % (n, dt)
+    d, s_, nz_ = oracle.depth(r, 0, clen[0] + 1)
+    sums, nzs = b.depth_stats()
+    assert np.array_equal(b.depth(0), d) and int(sums[0]) == s_ and int(nzs[0]) == nz_       # 2e5-deep pile: the 32-bit tile kernel
+    b.free()
 
 
 def test_sv_rich_sweep_eps_minpts(ctx, oracle):

@@ -145,3 +145,45 @@ def golden_record_summary_cases():
         r = norm_reads({"n_reads": len(g[p + "pos0"]), "tid": None, "pos0": g[p + "pos0"], "flag": g[p + "flag"], "mapq": g[p + "mapq"],
                         "cig_off": g[p + "cig_off"], "cigar": g[p + "cigar"]})
         yield i, r, g[p + "keep"], g[p + "endpos"], g[p + "qstart"], g[p + "qend"]
+
+
+# ------------------------------------------------------------------ split-read events
+
+def add_split_events(r, contig_len, rng, n_events=12, reads_per_event=(6, 14)):
+    """Adds split alignments to a packed SoA: groups of reads whose primary alignment ends at one breakpoint and whose
+    supplementary alignment (same query name, flag 0x800) starts at another one on the same contig -- deletion-like
+    (far apart on the reference), insertion-like (an unaligned stretch of the read between the two) and inverted
+    (supplementary on the other strand).  Returns (reads sorted by (tid, pos0), query name per record)."""
+    n0 = int(r["n_reads"])
+    off = np.asarray(r["cig_off"]).astype(np.int64)
+    cig = np.asarray(r["cigar"])
+    recs = [(int(r["tid"][i]) if r.get("tid") is not None else 0, int(r["pos0"][i]), int(r["flag"][i]), int(r["mapq"][i]),
+             cig[off[i]:off[i + 1]], "r%d" % i) for i in range(n0)]
+    for e in range(n_events):
+        t = int(rng.integers(0, len(contig_len)))
+        L = int(contig_len[t])
+        kind = ("del", "ins", "inv")[e % 3]
+        bp1 = int(rng.integers(20_000, L - 80_000))
+        bp2 = bp1 + (int(rng.integers(3_000, 40_000)) if kind != "ins" else int(rng.integers(0, 30)))
+        ins = int(rng.integers(2_500, 6_000)) if kind == "ins" else 0
+        ls_event = int(rng.integers(3_000, 8_000)) if e % 2 == 0 else 0      # every other event: supplementary parts of one length (their ends cluster)
+        for k in range(int(rng.integers(*reads_per_event))):
+            lp = int(rng.integers(4_000, 9_000))
+            ls = ls_event + int(rng.integers(-20, 21)) if ls_event else int(rng.integers(3_000, 8_000))
+            j1, j2 = int(rng.integers(-15, 16)), int(rng.integers(-15, 16))
+            name = "split%d_%d" % (e, k)
+            rev = 16 if rng.random() < 0.3 else 0
+            # primary: lp bases aligned up to the first breakpoint, the rest of the read hard-clipped (a trailing SOFT clip
+            # would count into the reference's query_end, sv_caller.cpp:681, and hide the distance on the read)
+            recs.append((t, bp1 + j1 - lp, rev, 60, np.array([(lp << 4) | 0, ((ins + ls) << 4) | 5], np.uint32), name))
+            # supplementary: the clipped part, aligned from the second breakpoint on
+            sflag = 0x800 | (rev ^ 16 if kind == "inv" else rev)
+            recs.append((t, bp2 + j2, sflag, 60, np.array([((lp + ins) << 4) | 4, (ls << 4) | 0], np.uint32), name))
+    recs.sort(key=lambda x: (x[0], x[1]))
+    cigs = [x[4] for x in recs]
+    cig_off = np.zeros(len(recs) + 1, np.uint64)
+    cig_off[1:] = np.cumsum([len(c) for c in cigs])
+    out = {"n_reads": len(recs), "n_ops": int(cig_off[-1]), "tid": np.array([x[0] for x in recs], np.int32), "pos0": np.array([x[1] for x in recs], np.int32),
+           "flag": np.array([x[2] for x in recs], np.uint16), "mapq": np.array([x[3] for x in recs], np.uint8), "cig_off": cig_off,
+           "cigar": np.concatenate(cigs).astype(np.uint32)}
+    return out, [x[5] for x in recs]
