@@ -46,7 +46,7 @@ EXPORTS = [
     "csv_timer_begin", "csv_timer_end", "csv_ctx_launch_count", "csv_ctx_set_pipeline_chunks", "csv_profile_enable", "csv_profile_read", "csv_batch_upload", "csv_batch_free", "csv_scan_run",
     "csv_depth_stats", "csv_depth_fetch", "csv_depth_fetch_all", "csv_ctx_set_fetch", "csv_ctx_fetch_stats", "csv_host_widen_u8", "csv_depth_device_ptr", "csv_sigs_count", "csv_sigs_fetch", "csv_sigs_dbscan1d",
     "csv_depth", "csv_cigar_scan", "csv_dbscan1d", "csv_dbscan1d_seg", "csv_dbscan2d", "csv_largest_cluster", "csv_window_sums", "csv_depth_at", "csv_record_summary", "csv_host_count_gaps",
-    "csv_depth_at_tid", "csv_sigs_depth", "csv_depth_checksum", "csv_batch_reserve_sigs", "csv_batch_release_inputs", "csv_host_record_stats",
+    "csv_depth_at_tid", "csv_sigs_depth", "csv_depth_checksum", "csv_batch_reserve_sigs", "csv_batch_release_inputs", "csv_host_record_stats", "csv_debug_fetch",
 ]
 SYNTH_EXPORTS = ["csv_synth_default_params", "csv_synth_num_reads", "csv_synth_reads", "csv_synth_cigar"]
 
@@ -103,6 +103,7 @@ def lib():
         L.csv_depth_at_tid.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.csv_sigs_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.csv_depth_checksum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.csv_debug_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.csv_batch_reserve_sigs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.csv_batch_release_inputs.argtypes = [C.c_void_p, C.c_void_p]
         L.csv_dbscan2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_void_p]

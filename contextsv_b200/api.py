@@ -265,6 +265,15 @@ class Batch:
         check(lib().csv_depth_checksum(self.ctx.h, self.h, ptr(out)))
         return out
 
+    def debug_array(self, name, dtype=np.uint32):
+        """Diagnostics: one of the batch's intermediate device arrays (csv_debug_fetch)."""
+        import ctypes as C
+        size = C.c_uint64(0)
+        check(lib().csv_debug_fetch(self.ctx.h, self.h, name.encode(), 0, 0, None, C.byref(size)))
+        out = np.empty(size.value // np.dtype(dtype).itemsize, dtype)
+        check(lib().csv_debug_fetch(self.ctx.h, self.h, name.encode(), 0, out.nbytes, ptr(out), None))
+        return out
+
     def window_sums(self, region, start_pos, end_pos, sample_size):
         s = np.ascontiguousarray(start_pos, np.uint32); e = np.ascontiguousarray(end_pos, np.uint32)
         su = np.zeros(len(s) * sample_size, np.uint64); cn = np.zeros(len(s) * sample_size, np.uint32)

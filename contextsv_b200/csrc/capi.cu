@@ -24,6 +24,8 @@ int next_ticket(csv_ctx* ctx, uint32_t** out)
 {
     if (ctx->ticket_next >= ctx->ticket_cap) {
         const uint32_t cap = 16384;
+        // the counters are about to be zeroed for re-use: chained launches on the other streams may still be drawing from theirs
+        if (ctx->ticket_cap) { CSV_CUDA(cudaStreamSynchronize(ctx->side_stream)); CSV_CUDA(cudaStreamSynchronize(ctx->tile_stream)); CSV_CUDA(cudaStreamSynchronize(ctx->main_stream)); }
         CSV_TRY(ctx->tickets.ensure(cap * sizeof(uint32_t)));
         CSV_CUDA(cudaMemsetAsync(ctx->tickets.p, 0, cap * sizeof(uint32_t), ctx->stream));   // stream-ordered after earlier users
         ctx->ticket_cap = cap; ctx->ticket_next = 0;

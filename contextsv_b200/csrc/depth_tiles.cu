@@ -379,11 +379,14 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 4 : 2)) k_depth_tiles_
     constexpr int kPP = 1024 / kThreads;                           // pairs per thread and batch (2048 events per batch)
     static_assert(kWarps <= 32, "one lane per warp in the offset reduction");
     __shared__ __align__(16) int s_diff[kThreads * kPadW];
-    __shared__ int s_wtot[kWarps], s_wcar[kWarps];
+    // s_wcar_ is double-buffered by tile parity: a warp that runs ahead writes its share of the NEXT tile's carry-in
+    // before the first barrier of that tile, while a slow warp may still be reading this tile's after the second one
+    __shared__ int s_wtot[kWarps], s_wcar_[2][kWarps];
     __shared__ uint2 s_rng[kThreads];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(P.events);
     const uint32_t pair_cap = P.ev_cap >> 1;
+    uint32_t parity = 0;
 
     for (uint32_t i = tid; i < kThreads * kPadW / 4; i += kThreads) reinterpret_cast<int4*>(s_diff)[i] = make_int4(0, 0, 0, 0);
     const uint32_t n_list = P.scalars[SC_N_WIDE];
@@ -412,6 +415,8 @@ __global__ void __launch_bounds__(kTile / PT, (PT == 32 ? 4 : 2)) k_depth_tiles_
 
         const uint32_t n_here = desc.y, T0 = desc.z;
         const uint32_t pb = er.x >> 1, pe = min(er.y >> 1, pair_cap);
+        int* const s_wcar = s_wcar_[parity];
+        parity ^= 1u;
         // ---- stretches of the records that overlap the tile (s_diff is all zero here)
         int mycarry = 0;
         auto apply = [&](const uint2 pr) {
@@ -575,7 +580,11 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
     constexpr int kThreads = 256, kWarps = kThreads / 32, kPP = 1024 / kThreads;
     static_assert(kTile == kWarps * 1024, "a warp owns 1024 positions: 4 rows of 32 chunks of 8");
     __shared__ __align__(16) uint32_t s_d[kTile / 2];
-    __shared__ int s_wtot[kWarps], s_wcar[kWarps];
+    // s_wcar_ is double-buffered by tile parity: a warp that runs ahead (the stores of the others are held up by HBM
+    // back-pressure for thousands of cycles) writes its share of the NEXT tile's carry-in before the first barrier of that
+    // tile, while a slow warp may not have read this tile's yet after the second barrier.  (Seen on B200 as +-k over one
+    // warp's 1024 positions in about one tile in 10^5.)  s_wtot is written between the two barriers: no such window.
+    __shared__ int s_wtot[kWarps], s_wcar_[2][kWarps];
     __shared__ uint2 s_rng[kThreads];                                    // searched path: pair range of 256 records at a time
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint2* __restrict__ pairs = reinterpret_cast<const uint2*>(P.events);
@@ -586,7 +595,7 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
     for (uint32_t i = tid; i < kTile / 8; i += kThreads) reinterpret_cast<uint4*>(s_d)[i] = bias4;
     // tile descriptors {T0, positions, first event, end event} run two tiles ahead of the tile being scanned
     const uint32_t g = gridDim.x;
-    uint32_t t = P.t_begin + blockIdx.x;
+    uint32_t t = P.t_begin + blockIdx.x, parity = 0;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     uint4 cur = t < P.t_end ? __ldg(P.tile_q + t) : zero4;
     uint4 nxt = t + g < P.t_end ? __ldg(P.tile_q + t + g) : zero4;
@@ -636,6 +645,8 @@ __global__ void __launch_bounds__(256, MINB) k_depth_tiles16(const TileParams P)
             for (int u = 0; u < kPP; u++) { const uint32_t i = nb + tid + u * kThreads; pf[u] = i < ne ? __ldg(pairs + i) : make_uint2(kNone, kNone); }
         }
         if (!narrow) { t += g; cur = nxt; nxt = nn; continue; }
+        int* const s_wcar = s_wcar_[parity];                               // flips once per tile that passes the two barriers below
+        parity ^= 1u;
         mycarry = (int)__reduce_add_sync(0xffffffffu, mycarry);
         if (lane == 0) s_wcar[warp] = mycarry;
         __syncthreads();

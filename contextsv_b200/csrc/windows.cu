@@ -216,3 +216,26 @@ extern "C" int csv_depth_checksum(csv_ctx* ctx, csv_batch* b, uint64_t* checksum
     CSV_CUDA(cudaStreamSynchronize(st));
     return CSV_OK;
 }
+
+extern "C" int csv_debug_fetch(csv_ctx* ctx, csv_batch* b, const char* name, uint64_t offset, uint64_t bytes, void* out, uint64_t* size_out)
+{
+    if (!ctx || !b || !name) { set_error("csv_debug_fetch: bad argument"); return CSV_ERR_ARG; }
+    const size_t nr = b->n_reads, nt = b->n_tiles;
+    struct { const char* name; const DevBuf* buf; size_t bytes; } tab[] = {
+        {"events", &b->d_events, (size_t)b->ev_cap * 4}, {"ev_start", &b->d_ev_start, (nr + 1) * 4}, {"ref_end", &b->d_ref_end, nr * 4},
+        {"span_desc", &b->d_span_desc, ((size_t)b->n_spans + 1) * 16}, {"pmax", &b->d_pmax, nr * 8}, {"tile_q", &b->d_tile_q, nt * 16},
+        {"tile_r", &b->d_tile_r, nt * 8}, {"meta", &b->d_meta, nr * 16}, {"key", &b->d_key, nr * 8},
+    };
+    for (const auto& e : tab) {
+        if (strcmp(e.name, name)) continue;
+        if (size_out) *size_out = e.bytes;
+        if (bytes == 0) return CSV_OK;
+        if (!out || !e.buf->p || offset + bytes > e.bytes) { set_error("csv_debug_fetch: %s holds %zu bytes", name, e.bytes); return CSV_ERR_ARG; }
+        CSV_TRY(side_join(ctx));
+        CSV_CUDA(cudaMemcpyAsync(out, (const char*)e.buf->p + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+        return CSV_OK;
+    }
+    set_error("csv_debug_fetch: unknown array %s", name);
+    return CSV_ERR_ARG;
+}

@@ -262,6 +262,11 @@ int csv_sigs_depth(csv_ctx* ctx, csv_batch* b, uint32_t* depth_out, uint64_t cap
  * sharded run can be verified against a single-device run without the maps leaving the devices. */
 int csv_depth_checksum(csv_ctx* ctx, csv_batch* b, uint64_t* checksum_out /* [n_regions] */);
 
+/* Diagnostics: copies `bytes` bytes at `offset` of one of the batch's intermediate device arrays to the host (waits for
+ * the pass).  name: "events", "ev_start", "ref_end", "span_desc", "pmax", "tile_q", "tile_r", "meta", "key".  *size_out
+ * (optional) receives the bytes the array holds; bytes == 0 only queries it.  Not part of the drop-in path. */
+int csv_debug_fetch(csv_ctx* ctx, csv_batch* b, const char* name, uint64_t offset, uint64_t bytes, void* out, uint64_t* size_out);
+
 /* Per-record summaries the split-read pass starts from (SVCaller::detectSVsFromSplitReads, sv_caller.cpp:150-162):
  * bam_endpos(b) and SVCaller::getAlignmentReadPositions(b) (sv_caller.cpp:663-690) for every record of the batch, in
  * csv_reads order.  Any output may be NULL.  The batch needs no scan first. */

@@ -2,6 +2,8 @@
 own outputs) and against the oracle on seeded inputs.  Bit-exact for every integer output."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -170,6 +172,15 @@ def test_full_size_whole_genome_properties(ctx, oracle):
     assert np.array_equal(sums, sums2) and np.array_equal(nzs, nzs2) and np.array_equal(b.depth(21), d21)
     for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
         assert np.array_equal(sg[f], sg2[f])
+    # ---- ... and so does every one of 60 more, with the tile kernel under full HBM back-pressure (regression: a warp
+    # running a whole tile ahead of a stalled one once overwrote its share of the carry-in: +-k over 1024 positions in
+    # about one tile in 10^5, i.e. every third whole-genome pass)
+    cks = b.depth_checksum()
+    for _ in range(60):
+        b.scan(want_depth=True, want_sigs=True)
+        b.sigs_dbscan1d(100.0, 5, fetch=False)
+        s3, z3 = b.depth_stats()
+        assert np.array_equal(s3, sums) and np.array_equal(z3, nzs) and np.array_equal(b.depth_checksum(), cks)
     b.free()
 
 
@@ -245,13 +256,17 @@ def test_record_level_prepass(ctx, oracle):
     g2, l2 = record_stats(r)
     assert np.array_equal(g2, good) and np.array_equal(l2, r["ref_len"]) and np.array_equal(l2.astype(np.int64), shard.ref_end(r) - r["pos0"].astype(np.int64) - 1)
     plain = np.nonzero((r["flag"] == 0) & (r["pos0"] > 1000))[0]
+    claim_on = os.environ.get("CSV_CLAIM_REFLEN", "0") not in ("", "0")     # opt-in (capi.cu: measured slower on B200); ignored otherwise
     for delta in (1, -1, 5000):
         bad = dict(r); l = l2.astype(np.int64).copy()
         victim = int(plain[len(plain) // 3])
         l[victim] = max(0, l[victim] + delta); bad["ref_len"] = l.astype(np.uint32)
         b = run_batch(ctx, bad, api.whole_contig_regions([400_000]))
-        with pytest.raises(CsvError, match="ref_len"):
-            b.depth_stats()
+        if claim_on:
+            with pytest.raises(CsvError, match="ref_len"):
+                b.depth_stats()
+        else:
+            b.depth_stats()                                                  # the claim is not used: a wrong one cannot hurt
         b.free()
     # without the lengths (n_gap only) the ranges are computed after the walk, as before
     only_gaps = dict(r); only_gaps.pop("ref_len")
