@@ -385,9 +385,13 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     // dozen ops into the record that crosses it; ONT-like batches keep the op-level pre-pass)
     static const bool rec_ok = !(getenv("CSV_REC_PREPASS") && atoi(getenv("CSV_REC_PREPASS")) == 0);
     b->rec_prepass = rec_ok && r->n_gap != nullptr && r->n_reads > 0 && r->n_ops <= (uint64_t)r->n_reads * 1024u;
-    // ... and with the reference length of every record the tile ranges need nothing from the walk (single-chunk passes)
-    // Measured on B200 (profiles/r2_history.md): beside the walk the ranges cost the walk more than they save after it
-    // (3.88 against 3.70 ms per whole-genome step, whatever the stream priority), so this is opt-in: CSV_CLAIM_REFLEN=1.
+    // ... and with the reference length of every record the tile ranges need nothing from the walk (single-chunk passes):
+    // the prefix max runs beside the record scan, the range searches are enqueued ahead of the walk, the walk leaves what it
+    // finds in d_ref_chk and k_claim_check compares after it.  Measured on B200 three ways (profiles/r2_history.md) and never a
+    // gain: ranges on the high-priority stream beside the walk 3.88 ms per whole-genome step (the block scheduler drains SMs
+    // for the larger CTAs), the same with the walk not touching the claim 3.75, ranges enqueued ahead of the walk at normal
+    // priority 3.73 (they still end up behind the walk's grid) -- against 3.68 with the ranges after the walk.  Opt-in:
+    // CSV_CLAIM_REFLEN=1.
     static const bool claim_ok = getenv("CSV_CLAIM_REFLEN") && atoi(getenv("CSV_CLAIM_REFLEN")) != 0;
     b->claimed_ref = claim_ok && b->rec_prepass && r->ref_len != nullptr && b->chunks.size() == 1;
     b->ev_cap = 2 * (r->n_ops + (uint64_t)r->n_reads) + 2;      // exact bound: 2 per record + 2 per D/N op
@@ -399,16 +403,18 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_pos0.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16, &ctx->pool)); CSV_TRY(b->d_mapq.ensure(nr + 16, &ctx->pool));
     CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8, &ctx->pool)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64, &ctx->pool));
     if (b->rec_prepass) CSV_TRY(b->d_n_gap.ensure(nr * 4 + 16, &ctx->pool));
-    if (b->claimed_ref) CSV_TRY(b->d_ref_len.ensure(nr * 4 + 16, &ctx->pool));
+    if (b->claimed_ref) { CSV_TRY(b->d_ref_len.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ref_chk.ensure(nr * 4 + 16, &ctx->pool)); }
     CSV_TRY(b->d_span_rq.ensure(((size_t)b->n_spans + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_key.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 512, &ctx->pool));   // the walk copies 272 bytes per span, also for the last one
-    CSV_TRY(b->d_scalars.ensure(SC_COUNT * 4, &ctx->pool));
+    b->state_bytes = ((size_t)SC_COUNT + b->chunks.size() + 4 + n_regions) * 4;
+    CSV_TRY(b->d_scalars.ensure(b->state_bytes, &ctx->pool));
+    b->d_tickets.p = b->d_scalars.as<uint32_t>() + SC_COUNT;
+    b->d_reg_sig_cnt.p = b->d_scalars.as<uint32_t>() + SC_COUNT + b->chunks.size() + 4;
     CSV_TRY(b->d_regs.ensure(regs.size() * sizeof(RegionDev), &ctx->pool)); CSV_TRY(b->d_tids.ensure(tids.size() * sizeof(TidDev), &ctx->pool));
-    CSV_TRY(b->d_reg_sig_cnt.ensure(n_regions * 4, &ctx->pool)); CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4, &ctx->pool));
+    CSV_TRY(b->d_reg_tab.ensure(reg_tab.size() * 4, &ctx->pool));
     CSV_TRY(b->d_span_agg.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool)); CSV_TRY(b->d_span_pre.ensure((size_t)b->n_spans * sizeof(WalkAgg) + 16, &ctx->pool));
     CSV_TRY(b->d_span_status.ensure(((size_t)b->n_spans / kSpanChunk + 2) * sizeof(WalkAgg), &ctx->pool));   // per-chunk aggregates
     CSV_TRY(b->d_scan_carry.ensure(sizeof(WalkAgg), &ctx->pool)); CSV_TRY(b->d_span_desc.ensure((size_t)b->n_spans * 16 + 32, &ctx->pool));
-    CSV_TRY(b->d_tickets.ensure(b->chunks.size() * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_chunk_tid.ensure(b->chunks.size() * 4 + 16, &ctx->pool)); CSV_TRY(b->d_chunk_bounds.ensure(b->chunks.size() * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_events.ensure((size_t)b->ev_cap * 4, &ctx->pool)); CSV_TRY(b->d_depth.ensure(nt * (size_t)kTile * 4, &ctx->pool));
     CSV_TRY(b->d_ev_start.ensure((nr + 2) * 4, &ctx->pool)); CSV_TRY(b->d_ref_end.ensure(nr * 4 + 16, &ctx->pool));
@@ -450,6 +456,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     }
     if (nt) CSV_CUDA(cudaMemcpyAsync(b->d_tile_desc.p, tile_desc.data(), nt * sizeof(uint4), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemsetAsync(b->d_pmax_part.p, 0, (nr / 2048 + 2) * 8, st));      // look-back status words of k_pmax_chained: epoch 0 == never published
+    CSV_CUDA(cudaMemsetAsync(b->d_headbits.p, 0, no / 8 + 512, st));               // record-head bits: a function of cig_off alone, every pass ORs the same bits in (prep.cu)
     // No synchronisation here: the tables above come from pageable temporaries, which cudaMemcpyAsync stages before it
     // returns; the caller's SoA is either pageable (same) or pinned -- then the copies are in flight and the arrays must
     // stay untouched until a call that waits for the stream (csv_ctx_sync, csv_depth_stats, any fetch).
@@ -499,9 +506,8 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     CSV_TRY(side_join(ctx));            // the previous pass's signature work may still be reading this batch
     cudaStream_t st = ctx->stream;
     b->last_min_len = p->min_len;
-    CSV_CUDA(cudaMemsetAsync(b->d_reg_sig_cnt.p, 0, b->n_regions * 4, st));
-    if (p->want_depth) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));
-    CSV_CUDA(cudaMemsetAsync(b->d_tickets.p, 0, b->chunks.size() * 4 + 16, st));
+    CSV_CUDA(cudaMemsetAsync(b->d_scalars.p, 0, b->state_bytes, st));    // scalars, tile tickets, signatures per region: one memset
+    if (p->want_depth && !b->rec_prepass) CSV_CUDA(cudaMemsetAsync(b->d_ev_start.p, 0, 4, st));   // (the record scan writes slot 0 itself)
     { StageTimer t(ctx, ST_PREP); CSV_TRY(launch_prep(ctx, b, p->min_mapq)); }
     // The pass is pipelined over chunks of whole contigs.  Main stream: the walk, chunk after chunk.  Tile stream:
     // tile ranges + depth tiles of chunk c as soon as the walk of chunk c + 1 is through (the records at the end of
@@ -513,32 +519,29 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         CSV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->ev_chunk.push_back(e);
     }
+    const bool ranges_first = p->want_depth && b->claimed_ref;           // csv_reads::ref_len: the tile ranges are ready BEFORE the walk ends
     if (p->want_depth) {
-        CSV_TRY(launch_chunk_bounds(ctx, b));
         CSV_TRY(side_fork(ctx));
         CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_fork, 0));
         TileScope ts(ctx);
         CSV_TRY(launch_depth_begin(ctx, b));
         StageTimer t(ctx, ST_TILE_RANGES);
-        CSV_TRY(launch_tile_hi(ctx, b));                                 // beside the walk
+        CSV_TRY(launch_chunk_bounds(ctx, b));                            // only the tile ranges read them: off the walk's stream
+        CSV_TRY(launch_tile_hi(ctx, b));                                 // beside the record scan / the walk
+        if (ranges_first) CSV_TRY(launch_tile_ranges(ctx, b, 0, 1));     // prefix max of the claimed record ends: beside the record scan
     }
-    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p)); }
-    const bool ranges_first = p->want_depth && b->claimed_ref;           // csv_reads::ref_len: the tile ranges run BESIDE the walk
+    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p, 1)); }
     if (ranges_first) {
-        // on the HIGH-priority side stream: the handful of CTAs of the prefix max and the range searches take the first
-        // slots the walk's CTAs free (at normal priority they queue behind the walk's whole grid and the look-back
-        // chain crawls); the tile stream picks the result up through an event
-        CSV_TRY(side_fork(ctx));                                         // after the record scan: ev_start[] is final
-        CSV_CUDA(cudaEventRecord(ctx->ev_tile_join, ctx->tile_stream));  // ... and after k_tile_hi (tile stream): the ranges read its r_hi
-        CSV_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_tile_join, 0));
-        {
-            SideScope side(ctx);
-            StageTimer t(ctx, ST_TILE_RANGES);
-            CSV_TRY(launch_tile_ranges(ctx, b, 0));
-        }
-        CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        // the range searches need the event slots of the record scan and nothing else: enqueued BEFORE the span carry and the
+        // walk so that their few CTAs are dispatched ahead of the walk's grid (normal priority: a high-priority launch
+        // beside the walk made the block scheduler drain SMs for its larger CTAs and cost the walk 0.15 ms)
+        CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->main_stream));
         CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_join, 0));
+        TileScope ts(ctx);
+        StageTimer t(ctx, ST_TILE_RANGES);
+        CSV_TRY(launch_tile_ranges(ctx, b, 0, 2));
     }
+    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p, 2)); }
     for (uint32_t c = 0; c < nc; c++) {
         { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1)); }
         CSV_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->main_stream));
@@ -568,6 +571,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         StageTimer t(ctx, ST_SIG_SORT);
         CSV_TRY(launch_sig_finish(ctx, b));
     }
+    if (ranges_first) CSV_TRY(launch_claim_check(ctx, b));              // main stream, beside the tiles: only the fetches wait for it
     b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;
     return CSV_OK;
 }

@@ -91,6 +91,12 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// a typed window into somebody else's DevBuf
+struct DevView {
+    void* p = nullptr;
+    template <class T> T* as() const { return (T*)p; }
+};
+
 // Per-stage device timing (CUDA events on the context's stream), for bench.py's roofline.
 enum Stage { ST_PREP = 0, ST_WALK, ST_TILE_RANGES, ST_DEPTH_TILES, ST_SIG_SORT, ST_DBSCAN, ST_TILE_KERNEL /* k_depth_tiles16 alone, inside ST_DEPTH_TILES */, ST_COUNT };
 

@@ -312,7 +312,8 @@ int launch_tile_hi(csv_ctx* ctx, csv_batch* b)
 }
 
 // event slices of the tiles of pipeline chunk c (needs the walk of chunk c + 1: see csv_scan_run)
-int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
+// what: 1 = the prefix max alone, 2 = the range searches alone (it is done), 3 = both
+int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c, int what)
 {
     const PipeChunk& ch = b->chunks[c];
     if (ch.tiles.empty()) return CSV_OK;
@@ -323,7 +324,7 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
     unsigned long long* part = b->d_pmax_part.as<unsigned long long>();
     unsigned long long* pmax = b->d_pmax.as<unsigned long long>();
     const uint32_t n_part = (uint32_t)(((uint64_t)ch.rec_upper + kPmTile - 1) / kPmTile);
-    if (n_part) {
+    if (n_part && (what & 1)) {
         const uint32_t grid = n_part < (uint32_t)ctx->sm_count * 8 ? n_part : (uint32_t)ctx->sm_count * 8;
         // ticket and status words are the batch's own: this launch runs on the tile stream beside chained scans of the
         // signature side stream, which share the context's
@@ -332,7 +333,7 @@ int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t c)
         k_pmax_chained<<<grid, kPmThreads, 0, ctx->stream>>>(meta, ref_end, scalars, bounds, pmax, b->d_tickets.as<uint32_t>() + c, part, next_epoch(ctx), claim);
         ctx->launches++;
     }
-    for (const auto& tr : ch.tiles) {
+    if (what & 2) for (const auto& tr : ch.tiles) {
         const uint32_t grid_t = (tr.second - tr.first + 255) / 256;
         k_tile_ranges<<<grid_t, 256, 0, ctx->stream>>>(b->d_tile_desc.as<uint4>(), tr.first, tr.second, pmax, b->d_ev_start.as<uint32_t>(),
                                                       scalars, bounds, b->d_tile_ev.as<uint2>(), b->d_tile_q.as<uint4>(), b->d_tile_r.as<uint2>(), b->d_wide_list.as<uint32_t>());

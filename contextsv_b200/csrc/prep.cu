@@ -75,9 +75,7 @@ __global__ void __launch_bounds__(256) k_prep_dense(const PrepParams P)
 
 int launch_prep(csv_ctx* ctx, csv_batch* b, uint32_t min_mapq)
 {
-    const uint64_t n_ops = b->n_ops;
-    CSV_CUDA(cudaMemsetAsync(b->d_headbits.p, 0, n_ops / 8 + 16, ctx->stream));
-    CSV_CUDA(cudaMemsetAsync(b->d_scalars.p, 0, SC_COUNT * sizeof(uint32_t), ctx->stream));
+    // (the head-bit map was zeroed at upload and only ever receives the same bits; the scalars at the start of the pass)
     if (b->n_reads == 0) return CSV_OK;
     PrepParams P;
     P.cig_off = b->d_cig_off.as<unsigned long long>();

@@ -44,14 +44,12 @@ struct WalkParams {
     const unsigned long long* cig_off;
     const uint32_t* ne_idx;     // compact index -> record index
     uint32_t ev_given;          // ev_start[] comes from the record scan (csv_reads::n_gap): the walk compares instead of writing
-    uint32_t ref_given;         // ref_end[] comes from csv_reads::ref_len (k_pmax_chained, beside the walk): the walk checks the claim
-    const uint32_t* ref_len;    // [n_reads] the caller's claim, by record index
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
     uint32_t* ref_end;      // [n_nonempty] one past the last covered index (may lie beyond the map); 0 = takes no part in the depth
     uint32_t n_meta;        // entries allocated in meta
-    uint32_t min_len, sig_lut;
+    uint32_t min_len, thr;   // thr = min_len << 4 (0xffffffff when no length can reach min_len)
     uint32_t* scalars;
     SigRaw sig;
     uint32_t sig_cap;
@@ -118,6 +116,15 @@ constexpr uint32_t kRefLut = kRefMask | (kRefMask << 16);
 constexpr uint32_t kGapLut = kGapMask | (kGapMask << 16);
 constexpr uint32_t kSigLut = kSigMask | (kSigMask << 16);
 __device__ __forceinline__ uint32_t class_bit(uint32_t lut, uint32_t w) { return __funnelshift_r(lut, lut, w) & 1u; }
+// ... and the same bit delivered at position J of the result (0 elsewhere): the table is rotated left by J at compile time,
+// so the funnel shift lands the op's bit on J -- one SHF + one LOP3 per op and mask instead of SHF, AND, shift, OR
+template <int J> __device__ __forceinline__ uint32_t class_bit_at(uint32_t lut, uint32_t w)
+{
+    const uint32_t r = J ? ((lut << J) | (lut >> (32 - J))) : lut;
+    return __funnelshift_r(r, r, w) & (1u << J);
+}
+
+template <int V> struct IntC { static constexpr int value = V; };
 
 // one step of an inclusive warp scan: SHFL + predicated add
 __device__ __forceinline__ uint32_t scan_step_u32(uint32_t x, int d)
@@ -419,14 +426,17 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
         uint32_t c[kWalkOpsPerThread + 1];
         uint32_t gm = 0, sm = 0;
         c[0] = 0;
-        const uint32_t thr = P.min_len << 4;
-#pragma unroll
-        for (int j = 0; j < kWalkOpsPerThread; j++) {
+        const uint32_t thr = P.thr;                                          // min_len << 4: a word at or above it is an op of at least min_len
+        auto phase_a = [&](auto jc) {
+            constexpr int j = decltype(jc)::value;
             const uint32_t w = t.w[j];
             c[j + 1] = c[j] + class_bit(kRefLut, w) * (w >> 4);
-            if (DEPTH) gm |= class_bit(kGapLut, w) << j;
-            if (SIGS) sm |= (w >= thr ? class_bit(P.sig_lut, w) : 0u) << j;
-        }
+            if (DEPTH) gm |= class_bit_at<j>(kGapLut, w);
+            if (SIGS) sm |= w >= thr ? class_bit_at<j>(kSigLut, w) : 0u;
+        };
+        phase_a(IntC<0>()); phase_a(IntC<1>()); phase_a(IntC<2>()); phase_a(IntC<3>());
+        phase_a(IntC<4>()); phase_a(IntC<5>()); phase_a(IntC<6>()); phase_a(IntC<7>());
+        static_assert(kWalkOpsPerThread == 8, "phase A is unrolled by hand");
         const uint32_t vmask = (1u << t.n_valid) - 1u, hbv = t.hb & vmask, tails = (t.hb >> 1) & vmask;
         const uint32_t heads = __popc(hbv);
         const uint32_t evn = heads + __popc(tails) + 2u * __popc(gm);
@@ -470,19 +480,35 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
             uint32_t kl = he_ex >> 16;                                       // s_pos1 slot of the record running into my ops
             const uint32_t rc_entry = lower ? (S - c[kWalkOpsPerThread]) + Xs : carry + (S - c[kWalkOpsPerThread]);
             const uint32_t kl_entry = kl, bias_entry = s_pos1[kl] + rc_entry;
-            uint32_t bias = bias_entry;
-            // ---- C
-            uint32_t* evp = P.events + T_ev;
+            // ---- C: the D / N events, in op order (32-bit slot arithmetic; the address is formed where the store is)
+            if (DEPTH) {
+                uint32_t bias = bias_entry, ev = T_ev;
+                const uint32_t* sp = s_pos1 + kl;
 #pragma unroll
-            for (int j = 0; j < kWalkOpsPerThread; j++) {
-                if ((hbv >> j) & 1u) { kl++; bias = s_pos1[kl] - c[j]; if (DEPTH) evp += (j ? 2 : 1); }      // tail event of the record before + my head event
-                if (DEPTH && ((gm >> j) & 1u)) { evp[0] = c[j] + bias; evp[1] = c[j + 1] + bias; evp += 2; }   // D / N: -1 at its first index, +1 one past its last
-                if (SIGS && ((sm >> j) & 1u)) {                              // rare: I / D / S of at least min_len
-                    const uint32_t w = t.w[j], op = w & 15u, len = w >> 4;
+                for (int j = 0; j < kWalkOpsPerThread; j++) {
+                    if ((hbv >> j) & 1u) { sp++; bias = *sp - c[j]; ev += (j ? 2u : 1u); }                  // tail event of the record before + my head event
+                    if ((gm >> j) & 1u) { uint32_t* e = P.events + ev; e[0] = c[j] + bias; e[1] = c[j + 1] + bias; ev += 2u; }   // -1 at its first index, +1 one past its last
+                }
+            }
+            // ---- signatures: I / D / S of at least min_len -- about one op in 600, so the ops are not tested one by one in
+            // the loop above; the record and the reference consumed since its head are rebuilt from the masks for the few
+            if (SIGS && sm) {
+                uint32_t todo = sm;
+                while (todo) {
+                    const uint32_t j = __ffs(todo) - 1u;
+                    todo &= todo - 1u;
+                    const uint32_t hb_low = hbv & ((2u << j) - 1u);          // record heads at my ops 0..j
+                    kl = kl_entry + __popc(hb_low);
+                    const uint32_t cj = sel9(c, j);
+                    const uint32_t since = hb_low ? cj - sel9(c, 31u - __clz(hb_low)) : rc_entry + cj;   // reference consumed since the head
+                    uint32_t w = t.w[0];
+#pragma unroll
+                    for (int u = 1; u < kWalkOpsPerThread; u++) w = j == (uint32_t)u ? t.w[u] : w;
+                    const uint32_t op = w & 15u, len = w >> 4;
                     const uint32_t k = k_first + kl;
                     const uint4 m = __ldg(P.meta + k);
                     if (m.z >> 31) {
-                        const uint32_t pos1 = m.x + 1u + (c[j] + bias - s_pos1[kl]);  // reference's `pos + 1` at this op (uint32)
+                        const uint32_t pos1 = m.x + 1u + since;             // reference's `pos + 1` at this op (uint32)
                         const bool beyond = pos1 >= m.y;
                         const uint32_t start = pos1, end = start + len - 1u;
                         if (!(op == 4 && beyond) && start <= end) {          // sv_caller.cpp:602-604, sv_object.cpp:25-28
@@ -516,10 +542,10 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                         if (ie - p1 >= 0x80000000u) P.scalars[SC_ABSURD] = 1u;   // 2^31 reference bases in one record: not an alignment
                         P.events[slot - 1u] = ie;
                         const uint32_t re = p1 != kDeadPos ? ie : 0u;        // not clipped to the map: only compared with tile starts
-                        // what the caller's per-record counts promised (csv_reads::n_gap / ref_len) is checked here, at the
-                        // one place the truth is known; a wrong count voids the pass (CSV_ERR_ARG at the first fetch)
-                        // (ref_end[] itself is being written by k_pmax_chained on another stream: the claim is read at its source)
-                        if (P.ref_given) { if (p1 != kDeadPos && ie - p1 != P.ref_len[P.ne_idx[kt]]) P.scalars[SC_BAD_GAPS] = 1u; } else P.ref_end[kt] = re;
+                        // what the caller's per-record counts promised (csv_reads::n_gap / ref_len) is checked against what the
+                        // CIGAR says: the event slots right here, the reference length by k_claim_check after the walk (then
+                        // P.ref_end is the batch's check array); a wrong count voids the pass (CSV_ERR_ARG at the first fetch)
+                        P.ref_end[kt] = re;
                         if (P.ev_given) { if (P.ev_start[kt + 1u] != slot) P.scalars[SC_BAD_GAPS] = 1u; } else P.ev_start[kt + 1u] = slot;
                     }
                     if (b < t.n_valid) {
@@ -551,10 +577,12 @@ static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
     P.events = b->d_events.as<uint32_t>();
     P.ev_cap = (uint32_t)b->ev_cap;
     P.ev_start = b->d_ev_start.as<uint32_t>();
-    P.ref_end = b->d_ref_end.as<uint32_t>();
+    // with csv_reads::ref_len the tile ranges were derived from the claim before the walk (d_ref_end is theirs): the walk
+    // leaves what it finds in the check array and k_claim_check compares the two
+    P.ref_end = (b->claimed_ref && p->want_depth ? b->d_ref_chk : b->d_ref_end).as<uint32_t>();
     P.n_meta = b->n_reads;
     P.min_len = p->min_len < (1u << 28) ? p->min_len : 0u;
-    P.sig_lut = p->min_len < (1u << 28) ? kSigLut : 0u;                      // CIGAR lengths have 28 bits: nothing can reach a larger threshold
+    P.thr = p->min_len < (1u << 28) ? p->min_len << 4 : 0xffffffffu;          // CIGAR lengths have 28 bits: nothing reaches a larger threshold (0xffffffff itself is op 15)
     P.scalars = b->d_scalars.as<uint32_t>();
     P.sig.key_hi = b->d_sig_hi.as<unsigned long long>();
     P.sig.key_lo = b->d_sig_lo.as<unsigned long long>();
@@ -567,17 +595,16 @@ static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
     P.cig_off = b->d_cig_off.as<unsigned long long>();
     P.ne_idx = b->d_ne_idx.as<uint32_t>();
     P.ev_given = b->rec_prepass ? 1u : 0u;
-    P.ref_given = b->claimed_ref && p->want_depth ? 1u : 0u;
-    P.ref_len = b->d_ref_len.as<uint32_t>();
     return P;
 }
 
 // Record-level pre-pass of a batch whose caller counted the D / N ops per record: once per pass, before the walk.
-int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
+// what: 1 = the record scan (event slots, span starts parked), 2 = the span carry, 3 = both
+int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int what)
 {
     if (!b->rec_prepass || b->n_ops == 0) return CSV_OK;
     const WalkParams P = walk_params(b, p);
-    {
+    if (what & 1) {
             const WalkParams Q = P;
             const uint32_t* n_rec = P.scalars + SC_N_NONEMPTY;
             auto in = [=] __device__(uint64_t k) -> uint32_t {
@@ -600,6 +627,8 @@ int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
                 }
             };
             CSV_TRY(chained_scan(ctx, in, out, b->n_reads, n_rec, nullptr));
+    }
+    if (what & 2) {
             const uint32_t n_carry = (uint32_t)(b->n_ops / kWalkSpan);               // span starts B = s * kWalkSpan, 1 <= s <= n_carry
             if (n_carry) {
                 const uint32_t per_cta = 256 / kCarryLanes;
@@ -607,6 +636,26 @@ int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
                 ctx->launches++;
             }
     }
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
+// csv_reads::ref_len against the CIGARs: claimed[k] (k_pmax_chained derived it before the walk) and found[k] (the walk)
+__global__ void __launch_bounds__(256) k_claim_check(const uint32_t* __restrict__ claimed, const uint32_t* __restrict__ found, uint32_t* scalars)
+{
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    bool bad = false;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) bad |= claimed[k] != found[k];
+    if (bad) scalars[SC_BAD_GAPS] = 1u;
+}
+
+// after the last walk chunk of a pass whose tile ranges came from the claim; beside the tiles, nothing waits for it but the fetches
+int launch_claim_check(csv_ctx* ctx, csv_batch* b)
+{
+    if (!b->claimed_ref || b->n_reads == 0) return CSV_OK;
+    const uint32_t grid = (b->n_reads + 255) / 256 < (uint32_t)ctx->sm_count * 4 ? (b->n_reads + 255) / 256 : (uint32_t)ctx->sm_count * 4;
+    k_claim_check<<<grid, 256, 0, ctx->stream>>>(b->d_ref_end.as<uint32_t>(), b->d_ref_chk.as<uint32_t>(), b->d_scalars.as<uint32_t>());
+    ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
