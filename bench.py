@@ -227,7 +227,7 @@ class ShmBoard:
     shared-memory segment on the box and fetches its results straight into it; rank 0 maps all of them and merges."""
     U_CAP = 8192          # signature starts per shard that another shard's depth slice has to answer
 
-    def __init__(self, tag, rank, world, n_regions_max, cap_sig, n_contigs):
+    def __init__(self, tag, rank, world, n_regions_max, cap_sig, n_contigs, cap_merged=0):
         self.rank, self.world, self.R, self.cap = rank, world, n_regions_max, int(cap_sig)
         self.layout, off = {}, 0
 
@@ -243,7 +243,17 @@ class ShmBoard:
         field("u_tid", np.int32, self.U_CAP); field("u_pos", np.uint32, self.U_CAP); field("u_idx", np.uint32, self.U_CAP)
         field("answers", np.uint32, self.U_CAP * world)
         field("cks", np.uint64, n_contigs); field("tot", np.uint64, 2 * n_contigs)
-        self.size = off + 64
+        # contigs this rank finalises because it holds their first region and another rank the rest: merged vectors
+        self.cap_m = int(cap_merged)
+        field("m_hdr", np.int64, 2 * n_contigs + 2)           # per contig (offset, length) in the m_ arrays, length -1 = not here
+        for k in ("m_start", "m_end", "m_op_idx", "m_query_pos", "m_depth"):
+            field(k, np.uint32, self.cap_m)
+        field("m_read_idx", np.int64, self.cap_m); field("m_label", np.int32, self.cap_m); field("m_kind", np.uint8, self.cap_m)
+        # two copies, used by steps of alternating parity: a rank that runs ahead fetches step s + 1 into the other copy
+        # while the owner of a cut contig still reads its step-s run (by step s + 2 both have passed step s + 1's barriers)
+        self.half = (off + 64 + 4095) & ~4095
+        self.size = 2 * self.half
+        self.base = 0
         d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
         self.path = lambda r: os.path.join(d, "csvb_%s_%d" % (tag, r))
         self.segs = {rank: np.memmap(self.path(rank), dtype=np.uint8, mode="w+", shape=(self.size,))}
@@ -253,8 +263,12 @@ class ShmBoard:
             if r not in self.segs:
                 self.segs[r] = np.memmap(self.path(r), dtype=np.uint8, mode="r+", shape=(self.size,))
 
+    def flip(self):
+        self.base = self.half - self.base
+
     def view(self, r, name):
         off, dt, n = self.layout[name]
+        off += self.base
         return self.segs[r][off:off + dt.itemsize * n].view(dt)
 
     def close(self):
@@ -442,11 +456,10 @@ def main_ours(args):
         tag = os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid() if os.environ.get("TORCHELASTIC_RUN_ID") else os.getpid())
         obj = [tag]
         dist.broadcast_object_list(obj, src=0)
-        board = ShmBoard(obj[0], rank, world, R_max, cap_sig, n_contigs)
+        board = ShmBoard(obj[0], rank, world, R_max, cap_sig, n_contigs, cap_merged=int(sum_over_ranks(n_sig)) + 4096)
         barrier()
         board.attach_all()
-        out = {k: board.view(rank, k) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
-        out_label, out_depth = board.view(rank, "label"), board.view(rank, "depth")
+        out = out_label = out_depth = None      # bound per step to the board copy of its parity
     else:
         out = {"start": np.zeros(cap_sig, np.uint32), "end": np.zeros(cap_sig, np.uint32), "kind": np.zeros(cap_sig, np.uint8),
                "read_idx": np.zeros(cap_sig, np.uint32), "op_idx": np.zeros(cap_sig, np.uint32), "query_pos": np.zeros(cap_sig, np.uint32)}
@@ -454,12 +467,23 @@ def main_ours(args):
     region_tid = np.array([t for (t, _, _, _) in regions], np.int32)
 
     phases = {}
+    holders = {}                 # contig -> ranks that hold a region of it, in genome order
+    for r_, regs_ in enumerate(plan if strong else []):
+        for (t_, _, _, _) in regs_:
+            if r_ not in holders.setdefault(t_, []):
+                holders[t_].append(r_)
+    my_cut_contigs = [t_ for t_, rs in sorted(holders.items()) if len(rs) > 1 and rs[0] == rank]
 
     def step_e2e(want_checksum=False):
         t_ph = [time.perf_counter()]
 
         def mark(name):
             t_ph.append(time.perf_counter()); phases[name] = 1e3 * (t_ph[-1] - t_ph[-2])
+        nonlocal out, out_label, out_depth
+        if strong:
+            board.flip()
+            out = {k: board.view(rank, k) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
+            out_label, out_depth = board.view(rank, "label"), board.view(rank, "depth")
         bt = api.Batch(ctx, reads, regions)                                        # H2D of the packed SoA
         bt.scan(want_depth=True, want_sigs=True)
         check(lib().csv_sigs_dbscan1d(ctx.h, bt.h, float(DB_EPS), int(DB_MIN_PTS), ptr(out_label), len(out_label)))   # DBSCAN1D + D2H labels
@@ -497,28 +521,74 @@ def main_ours(args):
         bt.free()
         dist.barrier()
         mark("cross_shard_depth")
-        if rank != 0:
-            return None, sums, nzs, cks, 0
-        parts = []
-        for r in range(world):
-            h = board.view(r, "hdr"); n_r, nu, nreg = int(h[0]), int(h[1]), int(h[2])
-            d = {k: board.view(r, k)[:n_r] for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos", "label")}
-            dp = board.view(r, "depth")[:n_r]
-            if nu:
-                dp = dp.copy()
-                ui = board.view(r, "u_idx")[:nu]
-                for q in range(world):
-                    if q == r:
+        # every contig is finalised by the rank that holds its FIRST region: nothing to do for the contigs it holds whole;
+        # a contig the plan cut is merged there with the addSVCall comparator (the other ranks' runs come through the
+        # board, their depths completed with the answers) and its DBSCAN1D groups are re-fit on that rank's own device.
+        # No rank waits for another one after the second barrier.
+        m_hdr = board.view(rank, "m_hdr"); m_hdr[:] = -1
+        parts_by_tid = {}
+        for t in my_cut_contigs:
+            parts = []
+            for r in holders[t]:
+                h = board.view(r, "hdr"); n_r, nu, nreg = int(h[0]), int(h[1]), int(h[2])
+                roff = board.view(r, "region_off")[:nreg + 1]
+                dp_all = None
+                for ri, (tt, _, _, _) in enumerate(plan[r]):
+                    if tt != t:
                         continue
-                    a = board.view(q, "answers")[r * board.U_CAP: r * board.U_CAP + nu]
-                    ok = (a != 0xffffffff) & (dp[ui] == 0xffffffff)
-                    dp[ui[ok]] = a[ok]
-            d["depth"] = dp
-            d["region_off"] = board.view(r, "region_off")[:nreg + 1]
-            parts.append((d, plan[r], read_bases[r]))
-        merged, n_split = finalize_merge(parts, ctx, api)
+                    lo, hi = int(roff[ri]), int(roff[ri + 1])
+                    d = {k: board.view(r, k)[lo:hi] for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos", "label")}
+                    dp = board.view(r, "depth")[lo:hi]
+                    if nu:
+                        if dp_all is None:
+                            dp_all = board.view(r, "depth")[:n_r].copy()
+                            ui = board.view(r, "u_idx")[:nu]
+                            for q in range(world):
+                                if q == r:
+                                    continue
+                                a = board.view(q, "answers")[r * board.U_CAP: r * board.U_CAP + nu]
+                                ok = (a != 0xffffffff) & (dp_all[ui] == 0xffffffff)
+                                dp_all[ui[ok]] = a[ok]
+                        dp = dp_all[lo:hi]
+                    d["depth"] = dp
+                    d["region_off"] = np.array([0, hi - lo], np.uint64)
+                    parts.append((d, [plan[r][ri]], read_bases[r]))
+            parts_by_tid[t] = parts
+        n_split = 0
+        if parts_by_tid:
+            merged_cut, n_split = finalize_merge([p_ for t in sorted(parts_by_tid) for p_ in parts_by_tid[t]], ctx, api)
+            o = 0
+            for t in sorted(merged_cut):
+                m = merged_cut[t]; n_t = len(m["start"])
+                if o + n_t > board.cap_m:
+                    raise SystemExit("bench.py: merged contigs exceed the board's capacity")
+                for k in ("start", "end", "op_idx", "query_pos", "depth", "read_idx", "label", "kind"):
+                    board.view(rank, "m_" + k)[o:o + n_t] = m[k]
+                m_hdr[2 * t], m_hdr[2 * t + 1] = o, n_t
+                o += n_t
         mark("merge")
-        return merged, sums, nzs, cks, n_split
+        return None, sums, nzs, cks, n_split
+
+    def collect_merged():
+        """Rank 0, outside the timed region: the per-contig result vectors where their owners left them (digests only)."""
+        out = {}
+        for t in range(n_contigs):
+            if t not in holders:
+                continue
+            r = holders[t][0]
+            if len(holders[t]) > 1:
+                o, n_t = (int(x) for x in board.view(r, "m_hdr")[2 * t: 2 * t + 2])
+                if n_t < 0:
+                    raise SystemExit("bench.py: contig %d was not finalised by rank %d" % (t, r))
+                out[t] = {k: board.view(r, "m_" + k)[o:o + n_t] for k in ("start", "end", "op_idx", "query_pos", "depth", "read_idx", "label", "kind")}
+            else:
+                h = board.view(r, "hdr"); nreg = int(h[2])
+                roff = board.view(r, "region_off")[:nreg + 1]
+                ri = [i for i, g in enumerate(plan[r]) if g[0] == t][0]
+                lo, hi = int(roff[ri]), int(roff[ri + 1])
+                out[t] = {k: board.view(r, k)[lo:hi] for k in ("start", "end", "kind", "op_idx", "query_pos", "label", "depth")}
+                out[t]["read_idx"] = board.view(r, "read_idx")[lo:hi].astype(np.int64) + read_bases[r]
+        return out
 
     from contextsv_b200._capi import check, lib, ptr
     read_bases = [read_base]
@@ -548,10 +618,13 @@ def main_ours(args):
             per_contig[t_] += c; tot_contig[2 * t_] += s_; tot_contig[2 * t_ + 1] += z_
         if strong:
             board.view(rank, "cks")[:] = per_contig; board.view(rank, "tot")[:] = tot_contig
+            n_split_all = int(sum_over_ranks(n_split))
             barrier()
             if rank == 0:
                 for r_ in range(1, world):
                     per_contig += board.view(r_, "cks"); tot_contig += board.view(r_, "tot")
+                merged = {t_: {k: np.array(v) for k, v in m_.items()} for t_, m_ in collect_merged().items()}
+                n_split = n_split_all
             barrier()
     checksums = None
     if rank == 0:
@@ -653,7 +726,7 @@ def main_ours(args):
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
                     "result": "mean coverage inputs, signature vectors, DBSCAN1D labels, depth at every signature start in host memory; the per-base map stays in HBM" +
-                              ("; shards gathered through shared memory, merged and re-fit on rank 0" if strong else "")},
+                              ("; contigs the plan cut are merged and re-fit by the rank that holds their first region (the other runs come through shared memory on the box)" if strong else "")},
             "e2e_full_map": full_map,
             "checksums": checksums, "checksums_single_device": checksums_n1, "checksums_match": match,
             "gpu_launches": int(launches), "clocks": clocks,

@@ -47,6 +47,20 @@ for _ in range(3):
         w = np.nonzero((c != c0) | (s != s0))[0]
         print("warm-up pass differs from the first pass: regions %s sum delta %s nz delta %s" % ([regs[i] for i in w], [int(s[i]) - int(s0[i]) for i in w], [int(z[i]) - int(z0[i]) for i in w]), flush=True)
 print("reference pass: %d regions, sum %d" % (len(regs), int(s0.astype(np.uint64).sum())), flush=True)
+if os.environ.get("STRESS_TIME"):
+    # resident passes of this shard alone, timed like bench.py's value (what one rank of an N-way run does per step)
+    for _ in range(3):
+        b.scan(want_depth=True, want_sigs=True); b.sigs_dbscan1d(100.0, 5, fetch=False)
+    ctx.sync(); ctx.profile_read(reset=True); ctx.profile_enable(True)
+    n_t = 20
+    ctx.timer_begin()
+    for _ in range(n_t):
+        b.scan(want_depth=True, want_sigs=True); b.sigs_dbscan1d(100.0, 5, fetch=False)
+    ms = ctx.timer_end()
+    ctx.profile_enable(False)
+    st = ctx.profile_read(reset=True)
+    print("shard %d/%d: %.4f ms/step  %s" % (rank, world, ms / n_t, {k: round(v[0] / n_t, 4) for k, v in st.items()}), flush=True)
+    sys.exit(0)
 bad_total = 0
 t0 = time.time()
 for it in range(iters):
