@@ -39,6 +39,8 @@ SYNTH_KW = {
     "ont60x_chr20": dict(profile=1, coverage=60.0, read_len_mean=50000.0, indel_rate=0.10, indel_len_max=4),
     # BASELINE configs[4] in small: SV-rich set with per-read breakpoint jitter (100k SVs over the genome ~ 8.5k on chr1)
     "svrich_chr1": dict(sv_jitter_sd=10.0),
+    # BASELINE configs[4] at full size: the whole genome with 100k SVs
+    "svrich_wgs": dict(sv_jitter_sd=10.0),
 }
 
 
@@ -49,6 +51,8 @@ def workload_contigs(name):
         return [shard.GRCH38[0][1]], 8500
     if name == "wgs30x":
         return [l for _, l in shard.GRCH38], 25000
+    if name == "svrich_wgs":
+        return [l for _, l in shard.GRCH38], 100000
     if name == "chr1_5":
         return [l for _, l in shard.GRCH38[:5]], 8500
     if name == "chr21":
@@ -62,6 +66,7 @@ def workload_name(name):
     return {"ont60x_chr20": "synthetic 60x ONT ultra-long chr20 (N50 50 kb, dense CIGAR) [BASELINE configs[2], one shard of the stream]",
             "svrich_chr1": "synthetic 30x HiFi chr1, SV-rich (8.5k SVs, breakpoint jitter) [BASELINE configs[4], one chromosome]",
             "wgs30x": "synthetic whole-genome 30x HiFi GRCh38-shaped (24 contigs, 15 kb reads, 25k SVs) [BASELINE configs[1]]",
+            "svrich_wgs": "synthetic whole-genome 30x HiFi, SV-rich (100k SVs, breakpoint jitter) [BASELINE configs[4]]",
             "chr1_5": "synthetic 30x HiFi chr1-chr5 (1.06 Gb; profiling workload)",
             "chr21": "synthetic 30x HiFi chr21 [BASELINE configs[0]]",
             "small": "synthetic 30x HiFi, 2 contigs of 5+3 Mb (debug)"}[name]
@@ -135,6 +140,22 @@ def measured_peak_gbs():
 
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: keep this rank's threads (and, by first touch, its pinned host buffers) on the CPUs next to its GPU,
+    so that the ranks' host->device copies do not all cross the same socket link.  Returns the affinity it set, or None where
+    the box does not say (container without NUMA information, NVML missing): then nothing changes."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return {"cpus": len(after), "of": before}
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------- reference arm
@@ -320,6 +341,7 @@ def main_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before anything is allocated: pinned buffers land on the GPU's side of the host
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -721,7 +743,7 @@ def main_ours(args):
                        "l2": "inputs_larger_than_l2 (this rank: CIGAR %.2f GB read + depth %.2f GB written per step)" % (4 * n_ops / 1e9, 4 * depth_words / 1e9),
                        "parallelism": "1 process/GPU, no collective on the path; " + ("independent samples per rank" if not strong else
                                       "one genome in %d cost-balanced region shards (positions + %.1f x ops) with halo reads, host merge" % (world, shard.OP_COST)),
-                       "ms_per_step_fastest_rank": ms_min / args.steps, "host_generation_s": round(t_gen, 2)},
+                       "ms_per_step_fastest_rank": ms_min / args.steps, "host_generation_s": round(t_gen, 2), "cpu_affinity_rank0": numa},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
@@ -752,7 +774,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr1_5", "chr21", "small", "ont60x_chr20", "svrich_chr1"])
+    ap.add_argument("--workload", default="wgs30x", choices=["wgs30x", "chr1_5", "chr21", "small", "ont60x_chr20", "svrich_chr1", "svrich_wgs"])
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N > 1: strong (default) = one genome region-sharded over the ranks [BASELINE configs[3]]; weak = one whole genome per rank")
     ap.add_argument("--seed", type=int, default=20261018 + 2)
