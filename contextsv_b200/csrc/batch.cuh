@@ -13,6 +13,8 @@ struct SigRaw {          // emission-order signature records (device)
     unsigned long long* key_lo;   // end << 32 | ~global op index  (ties: reverse insertion order)
     uint32_t* k;                  // compact (non-empty) read index
     uint8_t* kind;                // bit 7: query_pos needs the exact sequential recomputation
+    uint32_t* bucket;             // depth tile (clamped into the owner region's) the start falls into: the ordering's bucket
+    uint32_t* arrival;            // arrival number inside the bucket (any order: ranked by key afterwards)
 };
 }  // namespace csv
 
@@ -55,7 +57,7 @@ struct csv_batch {
     // [scalars (SC_COUNT) | tile tickets of the chained kernels (one per pipeline chunk, + 4) | signatures per region (n_regions)]
     csv::DevView d_tickets, d_reg_sig_cnt;
     size_t state_bytes = 0;
-    csv::DevBuf d_reg_tab;   // u32 [tile_base (n_regions + 1) | len (n_regions)], caller order
+    csv::DevBuf d_reg_tab;   // u32 [tile_base (n_regions + 1) | len (n_regions) | beg (n_regions)], caller order
     // walk
     csv::DevBuf d_span_agg, d_span_pre, d_span_status, d_scan_carry, d_span_desc, d_span_rq;
     std::vector<csv::PipeChunk> chunks;
@@ -65,14 +67,15 @@ struct csv_batch {
     csv::DevBuf d_ev_start, d_ref_end, d_pmax, d_pmax_part;   // per non-empty read
     csv::DevBuf d_depth, d_sum, d_nz, d_tile_desc, d_tile_ev, d_tile_sum, d_tile_nz, d_wide_list, d_tile_q, d_tile_r;
     // signatures
-    csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_kind, d_sig_payload;
+    csv::DevBuf d_sig_hi, d_sig_lo, d_sig_k, d_sig_kind, d_sig_payload, d_sig_bucket, d_sig_arrival;
+    csv::DevBuf d_bucket_cnt, d_bucket_base;   // u32 per depth tile: signatures that start there (zero between passes), first slot of the bucket
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
 
     void release(csv::DevPool* pool = nullptr) {
         csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_ref_len, &d_ref_chk, &d_span_rq, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
                               &d_regs, &d_tids, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds,
                               &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r, &d_sig_hi, &d_sig_lo, &d_sig_k,
-                              &d_sig_kind, &d_sig_payload, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
+                              &d_sig_kind, &d_sig_payload, &d_sig_bucket, &d_sig_arrival, &d_bucket_cnt, &d_bucket_base, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
                               &d_out_qpos, &d_out_seg, &d_labels};
         for (auto* b : all) b->release(pool);
     }
@@ -81,7 +84,7 @@ struct csv_batch {
         csv::DevBuf* in[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_ref_len, &d_ref_chk, &d_span_rq, &d_meta, &d_key, &d_ne_idx, &d_headbits,
                              &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds,
                              &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r,
-                             &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_kind, &d_sig_payload};
+                             &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_kind, &d_sig_payload, &d_sig_bucket, &d_sig_arrival, &d_bucket_cnt, &d_bucket_base};
         for (auto* b : in) b->release(pool);
         inputs_released = true;
     }

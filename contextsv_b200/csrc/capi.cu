@@ -118,6 +118,7 @@ static int alloc_sig_buffers(csv_ctx* ctx, csv_batch* b)
     const size_t sc = (size_t)b->sig_cap;
     CSV_TRY(b->d_sig_hi.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_lo.ensure(sc * 8, &ctx->pool)); CSV_TRY(b->d_sig_k.ensure(sc * 4, &ctx->pool));
     CSV_TRY(b->d_sig_kind.ensure(sc, &ctx->pool)); CSV_TRY(b->d_sig_payload.ensure(sc * 4, &ctx->pool));
+    CSV_TRY(b->d_sig_bucket.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_sig_arrival.ensure(sc * 4, &ctx->pool));
     CSV_TRY(b->d_out_start.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_end.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_kind.ensure(sc, &ctx->pool));
     CSV_TRY(b->d_out_read.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_op.ensure(sc * 4, &ctx->pool)); CSV_TRY(b->d_out_qpos.ensure(sc * 4, &ctx->pool));
     CSV_TRY(b->d_out_seg.ensure(sc * 4, &ctx->pool));
@@ -342,9 +343,9 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
         }
         t.count++;
     }
-    std::vector<uint32_t> reg_tab(2 * n_regions + 1);
+    std::vector<uint32_t> reg_tab(3 * n_regions + 1);
     for (uint32_t i = 0; i <= n_regions; i++) reg_tab[i] = b->tile_base[i];
-    for (uint32_t i = 0; i < n_regions; i++) reg_tab[n_regions + 1 + i] = regions[i].end - regions[i].beg;
+    for (uint32_t i = 0; i < n_regions; i++) { reg_tab[n_regions + 1 + i] = regions[i].end - regions[i].beg; reg_tab[2 * n_regions + 1 + i] = regions[i].beg; }
 
     b->n_spans = (uint32_t)((r->n_ops + kWalkSpan - 1) / kWalkSpan);
     // ---- pipeline chunks: cuts only between contigs, walk ranges aligned to the chunks of the span scan
@@ -423,6 +424,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     CSV_TRY(b->d_wide_list.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_tile_q.ensure(nt * 16 + 16, &ctx->pool)); CSV_TRY(b->d_tile_r.ensure(nt * 8 + 16, &ctx->pool));
     CSV_TRY(b->d_tile_sum.ensure(nt * 8 + 16, &ctx->pool)); CSV_TRY(b->d_tile_nz.ensure(nt * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_sum.ensure(n_regions * 8, &ctx->pool)); CSV_TRY(b->d_nz.ensure(n_regions * 4, &ctx->pool));
+    CSV_TRY(b->d_bucket_cnt.ensure(nt * 4 + 16, &ctx->pool)); CSV_TRY(b->d_bucket_base.ensure(nt * 4 + 16, &ctx->pool));
     CSV_TRY(alloc_sig_buffers(ctx, b.get()));
 
     // ---- uploads (asynchronous when the host buffers are pinned)
@@ -456,6 +458,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     }
     if (nt) CSV_CUDA(cudaMemcpyAsync(b->d_tile_desc.p, tile_desc.data(), nt * sizeof(uint4), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemsetAsync(b->d_pmax_part.p, 0, (nr / 2048 + 2) * 8, st));      // look-back status words of k_pmax_chained: epoch 0 == never published
+    CSV_CUDA(cudaMemsetAsync(b->d_bucket_cnt.p, 0, nt * 4 + 16, st));              // signatures per depth tile: the ordering's scan leaves zeros behind for the next pass
     CSV_CUDA(cudaMemsetAsync(b->d_headbits.p, 0, no / 8 + 512, st));               // record-head bits: a function of cig_off alone, every pass ORs the same bits in (prep.cu)
     // No synchronisation here: the tables above come from pageable temporaries, which cudaMemcpyAsync stages before it
     // returns; the caller's SoA is either pageable (same) or pinned -- then the copies are in flight and the arrays must

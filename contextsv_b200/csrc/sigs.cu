@@ -11,8 +11,21 @@
 // NUMBER is what costs); the order inside a run of equal (region, start) -- a
 // handful of entries, one per read over the same breakpoint -- is fixed by ranking
 // lo inside the run.
+//
+// Default ordering (launch_sig_finish): no sort at all.  Every signature was counted into the depth tile its start
+// falls into when the walk emitted it (SigRaw::bucket / arrival), tiles are in (region, position) order, so
+//   one chained scan over the per-tile counts  -> first slot of every bucket (and the counts zeroed for the next pass),
+//   one scatter                                -> the signatures of a bucket side by side, in arrival order,
+//   one rank + gather kernel                   -> position inside the bucket = number of its entries with a smaller
+//                                                 128-bit key, outputs written in place.
+// A bucket holds the signatures of 8192 reference positions: one or two at 30x.  Three launches instead of the radix
+// sort's ten on a stream that runs beside the HBM-bound tile kernel, where every launch costs the tiles SM slots.  The
+// cost is quadratic in the bucket size like the tie ranking it replaces (2e5 signatures in one tile: a few ms); the
+// radix path stays as CSV_SIG_ORDER=radix.
 #include "batch.cuh"
 #include "scan.cuh"
+
+#include <cstdlib>
 
 namespace csv {
 
@@ -77,12 +90,10 @@ struct GatherParams {
     uint8_t* o_kind;
 };
 
-__global__ void k_sig_gather(const GatherParams P)
+// output row i <- emitted signature `slot` with keys (hi, lo)
+__device__ __forceinline__ void gather_one(const GatherParams& P, uint32_t i, uint32_t slot, unsigned long long hi, unsigned long long lo)
 {
-    const uint32_t n = P.scalars[SC_N_SIG_EFF];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = P.val[i];
-        const unsigned long long hi = P.hi[i], lo = P.lo[slot];
+    {
         const uint32_t g = 0xffffffffu - (uint32_t)lo;
         const uint32_t k = P.raw_k[slot];
         const uint32_t read = P.ne_idx[k];
@@ -128,11 +139,82 @@ __global__ void k_sig_gather(const GatherParams P)
     }
 }
 
+__global__ void k_sig_gather(const GatherParams P)
+{
+    const uint32_t n = P.scalars[SC_N_SIG_EFF];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = P.val[i];
+        gather_one(P, i, slot, P.hi[i], P.lo[slot]);
+    }
+}
+
+// ---- bucket ordering
+__global__ void __launch_bounds__(256) k_bucket_scatter(const uint32_t* __restrict__ bucket, const uint32_t* __restrict__ arrival,
+                                                         const uint32_t* __restrict__ bucket_base, const uint32_t* scalars, uint32_t* perm)
+{
+    const uint32_t n = scalars[SC_N_SIG_EFF];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) perm[bucket_base[bucket[i]] + arrival[i]] = i;
+}
+
+// P.hi / P.lo: the keys in emission order; perm: emitted slots bucket by bucket
+__global__ void __launch_bounds__(256) k_bucket_rank_gather(const GatherParams P, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ bucket,
+                                                             const uint32_t* __restrict__ bucket_base)
+{
+    const uint32_t n = P.scalars[SC_N_SIG_EFF];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const uint32_t slot = perm[s];
+        const uint32_t bk = bucket[slot];
+        const uint32_t b0 = bucket_base[bk], b1 = bucket_base[bk + 1u];
+        const unsigned long long hi = P.hi[slot], lo = P.lo[slot];
+        uint32_t rank = 0;
+        for (uint32_t j = b0; j < b1; j++) {
+            const uint32_t o = perm[j];
+            const unsigned long long h2 = P.hi[o], l2 = P.lo[o];
+            rank += (h2 < hi || (h2 == hi && l2 < lo)) ? 1u : 0u;
+        }
+        gather_one(P, b0 + rank, slot, hi, lo);
+    }
+}
+
+static GatherParams gather_params(csv_batch* b)
+{
+    GatherParams P;
+    P.hi = b->d_sig_hi.as<unsigned long long>(); P.lo = b->d_sig_lo.as<unsigned long long>(); P.val = nullptr;
+    P.raw_k = b->d_sig_k.as<uint32_t>(); P.span_rq = b->d_span_rq.as<uint2>(); P.raw_kind = b->d_sig_kind.as<uint8_t>();
+    P.ne_idx = b->d_ne_idx.as<uint32_t>(); P.cig_off = b->d_cig_off.as<unsigned long long>(); P.cigar = b->d_cigar.as<uint32_t>();
+    P.meta = b->d_meta.as<uint4>(); P.tids = b->d_tids.as<TidDev>(); P.scalars = b->d_scalars.as<uint32_t>(); P.cap = (uint32_t)b->sig_cap;
+    P.o_start = b->d_out_start.as<uint32_t>(); P.o_end = b->d_out_end.as<uint32_t>(); P.o_read = b->d_out_read.as<uint32_t>();
+    P.o_op = b->d_out_op.as<uint32_t>(); P.o_qpos = b->d_out_qpos.as<uint32_t>(); P.o_seg = b->d_out_seg.as<uint32_t>();
+    P.o_kind = b->d_out_kind.as<uint8_t>();
+    P.min_len = b->last_min_len;
+    return P;
+}
+
 int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
 {
     const uint32_t cap = (uint32_t)b->sig_cap;
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
     uint32_t grid = cap_grid(ctx, ctx->sm_count * grid_mult(ctx, 4));
+    static const bool use_radix = getenv("CSV_SIG_ORDER") && !strcmp(getenv("CSV_SIG_ORDER"), "radix");
+    if (!use_radix) {
+        // the scan always runs over every bucket: it is what leaves the counters at zero for the next pass
+        uint32_t* cnt = b->d_bucket_cnt.as<uint32_t>();
+        uint32_t* base = b->d_bucket_base.as<uint32_t>();
+        const uint32_t n_tiles = b->n_tiles;
+        CSV_TRY(chained_scan(ctx,
+                             [=] __device__(uint64_t t) -> uint32_t { return cnt[t]; },
+                             [=] __device__(uint64_t t, uint32_t ex, uint32_t v) { base[t] = ex; cnt[t] = 0u; if (t + 1 == n_tiles) base[n_tiles] = ex + v; },
+                             n_tiles, nullptr, scalars + SC_N_SIG_EFF));
+        uint32_t* perm = b->d_sig_payload.as<uint32_t>();
+        k_bucket_scatter<<<grid, 256, 0, ctx->stream>>>(b->d_sig_bucket.as<uint32_t>(), b->d_sig_arrival.as<uint32_t>(), base, scalars, perm);
+        const GatherParams G = gather_params(b);
+        k_bucket_rank_gather<<<grid, 256, 0, ctx->stream>>>(G, perm, b->d_sig_bucket.as<uint32_t>(), base);
+        ctx->launches += 2;
+        CSV_CUDA(cudaGetLastError());
+        return CSV_OK;
+    }
+    // radix path: the bucket counters still have to return to zero
+    CSV_CUDA(cudaMemsetAsync(b->d_bucket_cnt.p, 0, (size_t)b->n_tiles * 4 + 16, ctx->stream));
     CSV_TRY(ctx->sort_tmp[1].ensure((size_t)cap * 8));
     CSV_TRY(ctx->sort_tmp[3].ensure((size_t)cap * 4));
     SortBufs sb;

@@ -54,6 +54,9 @@ struct WalkParams {
     SigRaw sig;
     uint32_t sig_cap;
     uint32_t* reg_sig_cnt;
+    const uint32_t* reg_tab;    // [tile_base (n_regions + 1) | len (n_regions) | beg (n_regions)], caller order
+    uint32_t n_regions;
+    uint32_t* bucket_cnt;       // signatures per depth tile
 };
 
 
@@ -520,6 +523,13 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                                 const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
                                 P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
                                 atomicAdd(&P.reg_sig_cnt[m.w], 1u);
+                                // the ordering's bucket: the depth tile of the owner region the start falls into (clamped into
+                                // the region: monotone in start, which is all the bucket order needs)
+                                const uint32_t tb = P.reg_tab[m.w], nt = P.reg_tab[m.w + 1u] - tb, beg = P.reg_tab[2u * P.n_regions + 1u + m.w];
+                                const uint32_t rel = start >= beg ? (start - beg) >> kTileShift : 0u;
+                                const uint32_t bk = tb + (rel < nt ? rel : nt - 1u);
+                                P.sig.bucket[sl] = bk;
+                                P.sig.arrival[sl] = atomicAdd(&P.bucket_cnt[bk], 1u);
                             }
                         }
                     }
@@ -588,6 +598,11 @@ static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
     P.sig.key_lo = b->d_sig_lo.as<unsigned long long>();
     P.sig.k = b->d_sig_k.as<uint32_t>();
     P.sig.kind = b->d_sig_kind.as<uint8_t>();
+    P.sig.bucket = b->d_sig_bucket.as<uint32_t>();
+    P.sig.arrival = b->d_sig_arrival.as<uint32_t>();
+    P.reg_tab = b->d_reg_tab.as<uint32_t>();
+    P.n_regions = b->n_regions;
+    P.bucket_cnt = b->d_bucket_cnt.as<uint32_t>();
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
     P.span_rq = b->d_span_rq.as<uint2>();

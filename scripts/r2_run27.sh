@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -6
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/r2_b27_$name.json 2>gpurun_out/r2_b27_$name.err; python -c "
+import json;d=json.load(open('gpurun_out/r2_b27_$name.json'));print('$name', round(d['ms_per_step'],4), round(d['roofline']['path']['frac'],4), {k:round(v,3) for k,v in d['roofline']['stage_ms_per_step'].items()}, d['gpu_launches'])"; tail -2 gpurun_out/r2_b27_$name.err; }
+run bucket X=1
+run radix CSV_SIG_ORDER=radix
+for o in bucket radix; do echo $o; CSV_SIG_ORDER=$o STRESS_TIME=1 timeout 300 python scripts/stress_shard.py 8 3 2>&1 | tail -1; done
