@@ -122,6 +122,8 @@ struct SortFirst { const uint32_t* n_raw; uint32_t clamp_cap; uint32_t* n_clampe
 int radix_sort_pairs(csv_ctx* ctx, SortBufs bufs, uint64_t n_upper, const uint32_t* n_dev, uint32_t digit_mask, const SortFirst* first = nullptr);
 
 // DBSCAN1D on device-resident points.  d_seg may be null (single fit).
+int dbscan1d_sorted_sigs(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, uint64_t n_upper, const uint32_t* n_dev,
+                         uint32_t n_seg, double eps, int min_pts, int32_t* d_labels);
 int dbscan1d_device(csv_ctx* ctx, const int32_t* d_pts, const uint32_t* d_seg, uint64_t n_upper, const uint32_t* n_dev,
                     uint32_t n_seg, double eps, int min_pts, int32_t* d_labels, int32_t* d_n_clusters /* [n_seg] or null */,
                     bool value_sorted = false /* points of one segment come in ascending order */);

@@ -246,6 +246,10 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
 int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts)
 {
     CSV_TRY(b->d_labels.ensure((size_t)b->sig_cap * 4 + 16));
+    static const bool fused = !(getenv("CSV_DB_SIGS") && !strcmp(getenv("CSV_DB_SIGS"), "general"));
+    if (fused && eps >= 0.0)
+        return dbscan1d_sorted_sigs(ctx, b->d_out_start.as<int32_t>(), b->d_out_seg.as<uint32_t>(), b->sig_cap, b->d_scalars.as<uint32_t>() + SC_N_SIG_EFF,
+                                    b->n_regions * 2, eps, min_pts, b->d_labels.as<int32_t>());
     return dbscan1d_device(ctx, b->d_out_start.as<int32_t>(), b->d_out_seg.as<uint32_t>(), b->sig_cap,
                            b->d_scalars.as<uint32_t>() + SC_N_SIG_EFF, b->n_regions * 2, eps, min_pts, b->d_labels.as<int32_t>(), nullptr,
                            true /* the signature list is sorted by (region, start) */);
