@@ -57,11 +57,19 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 // out(i, exclusive_prefix, value) is called for every i < n; in(i) yields the u32 addend.
 // total_out (optional) receives the sum of all n values.
+// Global accesses are STRIPED (consecutive threads take consecutive elements: in() and out() usually read and write
+// arrays indexed by the element, and a thread that took kScanItems consecutive ones turned every warp load into 32
+// sectors -- the record scan of the walk's pre-pass was bound by L1 wavefronts, not by its look-back); the scan itself
+// wants kScanItems consecutive elements per thread, so values and prefixes change hands in shared memory (rows padded by
+// one word per kScanItems: the blocked accesses are conflict-free).
+__device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + i / kScanItems; }
+
 template <class In, class Out>
 __global__ void __launch_bounds__(kScanThreads) k_chained_scan(In in, Out out, const uint32_t* n_dev, uint64_t n_host,
                                                                uint32_t* ticket, unsigned long long* status, uint32_t epoch,
                                                                uint32_t* total_out, const uint32_t* run_if)
 {
+    __shared__ uint32_t s_x[kScanTile + kScanTile / kScanItems];
     __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_tile, s_excl;
     if (run_if && *run_if == 0u) return;            // optional device-side switch: the whole launch is a no-op
@@ -69,15 +77,24 @@ __global__ void __launch_bounds__(kScanThreads) k_chained_scan(In in, Out out, c
     const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
     if (n == 0) { if (total_out && blockIdx.x == 0 && threadIdx.x == 0) *total_out = 0; return; }
     for (;;) {
-        __syncthreads();
+        __syncthreads();                             // s_x, s_tile of the tile before
         if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t t = s_tile;
         if (t >= n_tiles) break;
-        const uint64_t base = (uint64_t)t * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+        const uint64_t tile0 = (uint64_t)t * kScanTile;
+        uint32_t vs[kScanItems];                     // my striped elements: tile0 + j * kScanThreads + threadIdx.x
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) {
+            const uint32_t e = j * kScanThreads + threadIdx.x;
+            vs[j] = (tile0 + e < n) ? in(tile0 + e) : 0u;
+            s_x[scan_pad(e)] = vs[j];
+        }
+        __syncthreads();
+        const uint32_t b0 = threadIdx.x * kScanItems;   // my blocked elements: tile0 + b0 + j
         uint32_t v[kScanItems], sum = 0;
 #pragma unroll
-        for (int j = 0; j < kScanItems; j++) { v[j] = (base + j < n) ? in(base + j) : 0u; sum += v[j]; }
+        for (int j = 0; j < kScanItems; j++) { v[j] = s_x[scan_pad(b0 + j)]; sum += v[j]; }
         uint32_t tile_total;
         uint32_t ex = block_excl_scan_u32(sum, s_scan, &tile_total);
         if (threadIdx.x < 32) {
@@ -90,7 +107,13 @@ __global__ void __launch_bounds__(kScanThreads) k_chained_scan(In in, Out out, c
         __syncthreads();
         ex += s_excl;
 #pragma unroll
-        for (int j = 0; j < kScanItems; j++) { if (base + j < n) out(base + j, ex, v[j]); ex += v[j]; }
+        for (int j = 0; j < kScanItems; j++) { s_x[scan_pad(b0 + j)] = ex; ex += v[j]; }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) {
+            const uint32_t e = j * kScanThreads + threadIdx.x;
+            if (tile0 + e < n) out(tile0 + e, s_x[scan_pad(e)], vs[j]);
+        }
     }
 }
 
