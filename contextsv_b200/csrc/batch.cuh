@@ -101,7 +101,7 @@ int launch_tile_hi(csv_ctx* ctx, csv_batch* b);
 int launch_tile_ranges(csv_ctx* ctx, csv_batch* b, uint32_t chunk, int what = 3);
 int launch_depth_begin(csv_ctx* ctx, csv_batch* b);
 int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t chunk);
-int launch_depth_finish(csv_ctx* ctx, csv_batch* b);
+int launch_depth_finish(csv_ctx* ctx, csv_batch* b, int what = 3);
 int launch_sig_finish(csv_ctx* ctx, csv_batch* b);
 int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts);
 int launch_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv, const uint32_t* d_start,

@@ -53,7 +53,7 @@ static cudaEvent_t get_event(csv_ctx* ctx)
 }
 StageTimer::StageTimer(csv_ctx* c, int s) : ctx(c), stage(s)
 {
-    if (!ctx->profile) return;
+    if (!ctx->profile || (ctx->profile == 2 && s != ST_TILE_KERNEL)) return;
     cudaEvent_t e0 = get_event(ctx); e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
     ctx->stage_events[stage].emplace_back(e0, e1);
@@ -266,7 +266,7 @@ int csv_ctx_fetch_stats(const csv_ctx* ctx, uint64_t* narrow_chunks_out, uint64_
 int csv_profile_enable(csv_ctx* ctx, int on)
 {
     if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
-    ctx->profile = on != 0;
+    ctx->profile = on < 0 ? 0 : on;
     return CSV_OK;
 }
 
@@ -545,23 +545,53 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         CSV_TRY(launch_tile_ranges(ctx, b, 0, 2));
     }
     { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p, 2)); }
+    if (nc == 1) {
+        // One chunk: the whole critical chain stays on the main stream (walk -> prefix max -> range searches -> tiles ->
+        // reductions; no cross-stream hop in it).  The signature side stream forks right behind the walk; what the tile
+        // stream did beside the walk (clears, chunk bounds, static halves of the ranges) is long finished when it is joined.
+        { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[0].span0, b->chunks[0].span1)); }
+        if (p->want_sigs && p->want_depth) {
+            CSV_TRY(side_fork(ctx));
+            SideScope side(ctx);
+            StageTimer t(ctx, ST_SIG_SORT);
+            CSV_TRY(launch_sig_finish(ctx, b));
+        } else if (p->want_sigs) {
+            StageTimer t(ctx, ST_SIG_SORT);
+            CSV_TRY(launch_sig_finish(ctx, b));
+        }
+        if (p->want_depth) {
+            CSV_CUDA(cudaEventRecord(ctx->ev_tile_join, ctx->tile_stream));
+            CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_tile_join, 0));
+            ctx->tile_busy = false;
+            if (!ranges_first) { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, 0)); }
+            // the pile-up tiles (a launch that finds its list empty, as a rule) run on the tile stream BESIDE the 16-bit
+            // kernel: different tiles, nothing shared; the reductions wait for both
+            CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->main_stream));
+            CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_join, 0));
+            { TileScope ts(ctx); CSV_TRY(launch_depth_finish(ctx, b, 1)); }
+            CSV_CUDA(cudaEventRecord(ctx->ev_tile_join, ctx->tile_stream));
+            ctx->tile_busy = false;
+            StageTimer t(ctx, ST_DEPTH_TILES);
+            CSV_TRY(launch_depth_tiles(ctx, b, 0));
+            CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_tile_join, 0));
+            CSV_TRY(launch_depth_finish(ctx, b, 2));
+        }
+    } else {
     for (uint32_t c = 0; c < nc; c++) {
         { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1)); }
         CSV_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->main_stream));
-        if (p->want_depth && (c >= 1 || nc == 1)) {
-            const uint32_t tc = nc == 1 ? 0 : c - 1;                     // its records are complete now
+        if (p->want_depth && c >= 1) {
+            const uint32_t tc = c - 1;                                   // its records are complete now
             CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_chunk[c], 0));
             TileScope ts(ctx);
-            if (!ranges_first) { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, tc)); }
+            { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, tc)); }
             { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b, tc)); }
         }
     }
     if (p->want_depth) {
         TileScope ts(ctx);
-        if (nc > 1) {
-            { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, nc - 1)); }
-            { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b, nc - 1)); }
-        }
+        { StageTimer t(ctx, ST_TILE_RANGES); CSV_TRY(launch_tile_ranges(ctx, b, nc - 1)); }
+        { StageTimer t(ctx, ST_DEPTH_TILES); CSV_TRY(launch_depth_tiles(ctx, b, nc - 1)); }
         StageTimer t(ctx, ST_DEPTH_TILES);
         CSV_TRY(launch_depth_finish(ctx, b));
     }
@@ -573,6 +603,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     } else if (p->want_sigs) {
         StageTimer t(ctx, ST_SIG_SORT);
         CSV_TRY(launch_sig_finish(ctx, b));
+    }
     }
     if (ranges_first) CSV_TRY(launch_claim_check(ctx, b));              // main stream, beside the tiles: only the fetches wait for it
     b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;

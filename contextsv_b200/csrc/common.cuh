@@ -159,7 +159,7 @@ struct csv_ctx {
     bool db_small = true;               // csv_dbscan1d takes the one-launch path for <= kDbSmallMax points (CSV_DB_SMALL=0 turns it off)
     int sm_count = csv::kSMs;
     csv::DevPool pool;                  // parked batch buffers
-    bool profile = false;
+    int profile = 0;                    // 0 off, 1 = every stage (diagnostics), 2 = the dominant kernel only (bench.py's timed region)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stage_events[csv::ST_COUNT];
     std::vector<cudaEvent_t> spare_events;
     double stage_ms[csv::ST_COUNT] = {0};

@@ -792,15 +792,21 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t c)
 }
 
 // after the last chunk: pile-up tiles with 32-bit counters, then the per-region reductions
-int launch_depth_finish(csv_ctx* ctx, csv_batch* b)
+// what: 1 = the pile-up tiles (32-bit counters; needs the tile ranges of every chunk), 2 = the per-region reductions
+// (needs every tile), 3 = both, in this order on the current stream
+int launch_depth_finish(csv_ctx* ctx, csv_batch* b, int what)
 {
     if (b->n_tiles == 0) return CSV_OK;
     TileParams P = tile_params(b);
-    const uint32_t grid_w = b->n_tiles < (uint32_t)ctx->sm_count * 4 ? b->n_tiles : (uint32_t)ctx->sm_count * 4;
-    k_depth_tiles_wide<32><<<grid_w, kTile / 32, 0, ctx->stream>>>(P);    // exits at once when the wide list is empty
+    if (what & 1) {
+        const uint32_t grid_w = b->n_tiles < (uint32_t)ctx->sm_count * 4 ? b->n_tiles : (uint32_t)ctx->sm_count * 4;
+        k_depth_tiles_wide<32><<<grid_w, kTile / 32, 0, ctx->stream>>>(P);    // exits at once when the wide list is empty
+        ctx->launches++;
+    }
+    if (!(what & 2)) { CSV_CUDA(cudaGetLastError()); return CSV_OK; }
     const uint32_t grid_r = (b->n_tiles + 255) / 256 < (uint32_t)ctx->sm_count * 8 ? (b->n_tiles + 255) / 256 : (uint32_t)ctx->sm_count * 8;
     k_region_stats<<<grid_r, 256, 0, ctx->stream>>>(P.tile_desc, b->n_tiles, P.tile_sum, P.tile_nz, b->d_sum.as<unsigned long long>(), b->d_nz.as<uint32_t>());
-    ctx->launches += 2;
+    ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }

@@ -72,7 +72,9 @@ void csv_host_widen_u8(const uint8_t* src, uint32_t* dst, size_t n);
 /* Kernels launched by this context since creation. */
 uint64_t csv_ctx_launch_count(const csv_ctx* ctx);
 /* Per-stage device time of the scan pipeline (event pairs around each stage while
- * enabled).  csv_profile_read synchronises, fills up to max_stages entries
+ * enabled).  on = 1: every stage; on = 2: only the dominant kernel (k_depth_tiles16) -- every event pair is a stream
+ * operation between two kernels, a dozen of them per pass cost the pass about 1 %; on = 0: off.
+ * csv_profile_read synchronises, fills up to max_stages entries
  * (stage name, accumulated ms, number of timed calls) and returns the number of
  * stages, or a negative csv_status. */
 int csv_profile_enable(csv_ctx* ctx, int on);

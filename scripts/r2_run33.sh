@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/r2_b34_$name.json 2>gpurun_out/r2_b34_$name.err; python -c "
+import json;d=json.load(open('gpurun_out/r2_b34_$name.json'));print('$name', round(d['ms_per_step'],4), round(d['roofline']['path']['frac'],4), {k:round(v,3) for k,v in d['roofline']['stage_ms_per_step'].items()}, d['gpu_launches'], d['roofline']['stage_note'][-22:])"; tail -2 gpurun_out/r2_b34_$name.err; }
+run a X=1
+run b X=1
+STRESS_TIME=1 timeout 300 python scripts/stress_shard.py 8 3 2>&1 | tail -1
