@@ -421,21 +421,23 @@ def main_ours(args):
         t0_, b0_ = regions[0][0], regions[0][1]
         own_reads = int(np.count_nonzero((tid > t0_) | (idx >= b0_))) if n_reads else 0
         genome_reads = sum_over_ranks(own_reads)
-    ctx.profile_read(reset=True)
-    ctx.profile_enable(2)            # timed region: CUDA events around the dominant kernel only (roofline.achieved)
-    barrier()
-    sampler.mark_begin()
-    launches0 = ctx.launches
-    ctx.timer_begin()
-    for _ in range(args.steps):
-        step_resident()
-    ms = ctx.timer_end()
-    sampler.mark_end()
-    barrier()
-    clocks = sampler.stop()
-    launches = ctx.launches - launches0
-    ctx.profile_enable(0)
-    stages = ctx.profile_read(reset=True)
+    def timed_region():
+        ctx.profile_read(reset=True)
+        ctx.profile_enable(2)        # timed region: CUDA events around the dominant kernel only (roofline.achieved)
+        barrier()
+        sampler.mark_begin()
+        l0 = ctx.launches
+        ctx.timer_begin()
+        for _ in range(args.steps):
+            step_resident()
+        ms_ = ctx.timer_end()
+        sampler.mark_end()
+        barrier()
+        ctx.profile_enable(0)
+        return ms_, ctx.launches - l0, ctx.profile_read(reset=True)
+
+    ms, launches, stages = timed_region()
+    retimed = None
     # stage breakdown: a second, fully instrumented run of the same steps (an event pair around every stage costs the pass
     # about 1 %, so it stays out of the timed region; only reported under roofline.stage_ms_per_step)
     ctx.profile_enable(1)
@@ -445,6 +447,13 @@ def main_ours(args):
     ms_instrumented = ctx.timer_end()
     ctx.profile_enable(0)
     stages_all = ctx.profile_read(reset=True)
+    # A timed region MORE than twice as long as the instrumented repeat of the same steps was disturbed from outside (seen on
+    # fresh boxes: a first process after heavy host work stalls for seconds inside its first launches).  It is measured
+    # once more and both numbers are reported (the contract's rule for a disturbed run: reject and re-measure once).
+    if max_over_ranks(1.0 if ms > 2.0 * ms_instrumented else 0.0) > 0.5:
+        retimed = {"first_ms_per_step": max_over_ranks(ms) / args.steps, "instrumented_ms_per_step": ms_instrumented / args.steps}
+        ms, launches, stages = timed_region()
+    clocks = sampler.stop()
     stages_all["k_depth_tiles16"] = stages["k_depth_tiles16"]
     stages = stages_all
     ms_max = max_over_ranks(ms)
@@ -763,7 +772,7 @@ def main_ours(args):
                               ("; contigs the plan cut are merged and re-fit by the rank that holds their first region (the other runs come through shared memory on the box)" if strong else "")},
             "e2e_full_map": full_map,
             "checksums": checksums, "checksums_single_device": checksums_n1, "checksums_match": match,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "retimed": retimed,
         }
         print(json.dumps(line))
     if board is not None:

@@ -528,7 +528,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_fork, 0));
         TileScope ts(ctx);
         CSV_TRY(launch_depth_begin(ctx, b));
-        StageTimer t(ctx, ST_TILE_RANGES);
+        // (not timed as a stage: these run beside the walk, off the critical path; ST_TILE_RANGES is what follows the walk)
         CSV_TRY(launch_chunk_bounds(ctx, b));                            // only the tile ranges read them: off the walk's stream
         CSV_TRY(launch_tile_hi(ctx, b));                                 // beside the record scan / the walk
         if (ranges_first) CSV_TRY(launch_tile_ranges(ctx, b, 0, 1));     // prefix max of the claimed record ends: beside the record scan
