@@ -6,7 +6,10 @@ namespace csv {
 constexpr uint32_t kNone = 0xffffffffu;
 
 // u32 slots of csv_batch::d_scalars
-enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_HAS_EMPTY = 6 /* a record without CIGAR: tables need compaction */, SC_BAD_GAPS = 7 /* csv_reads::n_gap does not match the CIGAR */, SC_COUNT = 16 };
+enum { SC_N_NONEMPTY = 0, SC_N_SIG = 1, SC_UNSORTED = 2, SC_N_SIG_EFF = 3 /* min(SC_N_SIG, sig_cap) */, SC_N_WIDE = 4 /* tiles on the wide list */, SC_ABSURD = 5 /* a record spans >= 2^31 reference bases */, SC_HAS_EMPTY = 6 /* a record without CIGAR: tables need compaction */, SC_BAD_GAPS = 7 /* csv_reads::n_gap does not match the CIGAR */, SC_SIG_DROPPED = 8 /* a signature found its slot beyond sig_cap */,
+       SC_SIG_SUB0 = 16 /* kSigSub slot counters: a signature of CTA c draws from counter c % kSigSub and owns raw slot index * kSigSub + c % kSigSub (one counter for all was 1.4 ns per signature: same-address atomics); SC_N_SIG is their sum, formed on the host */,
+       SC_COUNT = 48 };
+constexpr uint32_t kSigSub = 32;
 
 struct SigRaw {          // emission-order signature records (device)
     unsigned long long* key_hi;   // owner region << 32 | start
@@ -57,6 +60,7 @@ struct csv_batch {
     // [scalars (SC_COUNT) | tile tickets of the chained kernels (one per pipeline chunk, + 4) | signatures per region (n_regions)]
     csv::DevView d_tickets, d_reg_sig_cnt;
     size_t state_bytes = 0;
+    uint32_t sig_sub_mask = csv::kSigSub - 1;  // see SC_SIG_SUB0
     csv::DevBuf d_reg_tab;   // u32 [tile_base (n_regions + 1) | len (n_regions) | beg (n_regions)], caller order
     // walk
     csv::DevBuf d_span_agg, d_span_pre, d_span_status, d_scan_carry, d_span_desc, d_span_rq;
@@ -104,6 +108,7 @@ int launch_depth_tiles(csv_ctx* ctx, csv_batch* b, uint32_t chunk);
 int launch_depth_finish(csv_ctx* ctx, csv_batch* b, int what = 3);
 int launch_sig_finish(csv_ctx* ctx, csv_batch* b);
 int launch_sig_dbscan(csv_ctx* ctx, csv_batch* b, double eps, int min_pts);
+bool sig_order_radix();   // CSV_SIG_ORDER=radix: the sort-based order (one slot counter, dense raw slots)
 int launch_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t n_sv, const uint32_t* d_start,
                        const uint32_t* d_end, int sample_size, unsigned long long* d_sum, uint32_t* d_cnt);
 

@@ -87,6 +87,9 @@ static int read_scalars(csv_ctx* ctx, csv_batch* b, uint32_t* out /* SC_COUNT */
     CSV_CUDA(cudaMemcpyAsync(ctx->pinned_small, b->d_scalars.p, SC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CSV_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(out, ctx->pinned_small, SC_COUNT * sizeof(uint32_t));
+    uint64_t n_sig = 0;
+    for (uint32_t i = 0; i < kSigSub; i++) n_sig += out[SC_SIG_SUB0 + i];
+    out[SC_N_SIG] = (uint32_t)std::min<uint64_t>(n_sig, 0xffffffffu);      // emitted, whether stored or dropped
     return CSV_OK;
 }
 
@@ -105,8 +108,14 @@ static int check_overflow(csv_ctx* ctx, csv_batch* b, uint32_t* sc)
         set_error("csv_reads::n_gap / ref_len do not match the CIGAR: they must hold the number of D / N ops and the reference bases consumed of every record");
         return CSV_ERR_ARG;
     }
-    if (b->have_sigs && sc[SC_N_SIG] > b->sig_cap) {
-        set_error("signatures: %u emitted, batch capacity is %llu: csv_batch_reserve_sigs(%u) and scan again", sc[SC_N_SIG], (unsigned long long)b->sig_cap, sc[SC_N_SIG]);
+    if (b->have_sigs && (sc[SC_SIG_DROPPED] || sc[SC_N_SIG] > b->sig_cap)) {
+        // raw slots are dealt out by kSigSub counters: the one that ran ahead hits the capacity a little before the sum
+        // does, so what to reserve is the emitted count plus that slack
+        const uint64_t grow = std::max<uint64_t>(sc[SC_N_SIG], b->sig_cap);
+        const uint64_t want = grow + grow / 8 + 64 * kSigSub;
+        set_error("signatures: %u emitted, batch capacity is %llu: csv_batch_reserve_sigs(%llu) and scan again", sc[SC_N_SIG], (unsigned long long)b->sig_cap, (unsigned long long)want);
+        sc[SC_N_SIG] = (uint32_t)std::min<uint64_t>(want, 0xffffffffu);
+        b->sig_sub_mask = 0;      // the pass that follows deals dense slots: it fits as soon as the capacity covers the count
         return CSV_ERR_CAPACITY;
     }
     return CSV_OK;
@@ -395,6 +404,9 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     // CSV_CLAIM_REFLEN=1.
     static const bool claim_ok = getenv("CSV_CLAIM_REFLEN") && atoi(getenv("CSV_CLAIM_REFLEN")) != 0;
     b->claimed_ref = claim_ok && b->rec_prepass && r->ref_len != nullptr && b->chunks.size() == 1;
+    // small batches (and the radix order) keep ONE slot counter and dense raw slots: contention is no matter there, and a
+    // handful of CTAs would not spread over the counters anyway
+    b->sig_sub_mask = (sig_order_radix() || r->n_ops < (1u << 22)) ? 0u : kSigSub - 1u;
     b->ev_cap = 2 * (r->n_ops + (uint64_t)r->n_reads) + 2;      // exact bound: 2 per record + 2 per D/N op
     b->sig_cap = std::max<uint64_t>(16, std::min<uint64_t>(r->n_ops, std::max<uint64_t>(1u << 20, r->n_ops / 16)));
 

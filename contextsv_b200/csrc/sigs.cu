@@ -149,11 +149,26 @@ __global__ void k_sig_gather(const GatherParams P)
 }
 
 // ---- bucket ordering
+// raw slot i = index * kSigSub + counter (walk.cu): a lane always meets the same counter (the stride is a multiple of 32)
 __global__ void __launch_bounds__(256) k_bucket_scatter(const uint32_t* __restrict__ bucket, const uint32_t* __restrict__ arrival,
-                                                         const uint32_t* __restrict__ bucket_base, const uint32_t* scalars, uint32_t* perm)
+                                                         const uint32_t* __restrict__ bucket_base, const uint32_t* scalars, uint32_t cap, uint32_t sub_mask,
+                                                         uint32_t* perm, const uint32_t* __restrict__ reg_tab, uint32_t n_regions, uint32_t* reg_sig_cnt)
 {
-    const uint32_t n = scalars[SC_N_SIG_EFF];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) perm[bucket_base[bucket[i]] + arrival[i]] = i;
+    static_assert(kSigSub == 32, "one slot counter per lane");
+    // signatures per region (caller order): the buckets of a region are its depth tiles, so the counts are differences of
+    // the bucket scan -- the walk does not count them (one same-address atomic less per signature)
+    if (blockIdx.x == 0 && sub_mask != 0)
+        for (uint32_t r = threadIdx.x; r < n_regions; r += blockDim.x) reg_sig_cnt[r] = bucket_base[reg_tab[r + 1u]] - bucket_base[reg_tab[r]];
+    if (sub_mask == 0) {                                      // one counter, dense slots
+        const uint32_t n = min(scalars[SC_SIG_SUB0], cap);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) perm[bucket_base[bucket[i]] + arrival[i]] = i;
+        return;
+    }
+    const uint32_t mine = scalars[SC_SIG_SUB0 + (threadIdx.x & 31u)];
+    const uint32_t most = __reduce_max_sync(0xffffffffu, mine);
+    const uint64_t end = (uint64_t)most * kSigSub;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x)
+        if ((uint32_t)(i / kSigSub) < mine && i < cap) perm[bucket_base[bucket[i]] + arrival[i]] = (uint32_t)i;
 }
 
 // P.hi / P.lo: the keys in emission order; perm: emitted slots bucket by bucket
@@ -190,12 +205,18 @@ static GatherParams gather_params(csv_batch* b)
     return P;
 }
 
+bool sig_order_radix()
+{
+    static const bool use_radix = getenv("CSV_SIG_ORDER") && !strcmp(getenv("CSV_SIG_ORDER"), "radix");
+    return use_radix;
+}
+
 int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
 {
     const uint32_t cap = (uint32_t)b->sig_cap;
     uint32_t* scalars = b->d_scalars.as<uint32_t>();
     uint32_t grid = cap_grid(ctx, ctx->sm_count * grid_mult(ctx, 4));
-    static const bool use_radix = getenv("CSV_SIG_ORDER") && !strcmp(getenv("CSV_SIG_ORDER"), "radix");
+    const bool use_radix = sig_order_radix();
     if (!use_radix) {
         // the scan always runs over every bucket: it is what leaves the counters at zero for the next pass
         uint32_t* cnt = b->d_bucket_cnt.as<uint32_t>();
@@ -206,7 +227,8 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
                              [=] __device__(uint64_t t, uint32_t ex, uint32_t v) { base[t] = ex; cnt[t] = 0u; if (t + 1 == n_tiles) base[n_tiles] = ex + v; },
                              n_tiles, nullptr, scalars + SC_N_SIG_EFF));
         uint32_t* perm = b->d_sig_payload.as<uint32_t>();
-        k_bucket_scatter<<<grid, 256, 0, ctx->stream>>>(b->d_sig_bucket.as<uint32_t>(), b->d_sig_arrival.as<uint32_t>(), base, scalars, perm);
+        k_bucket_scatter<<<grid, 256, 0, ctx->stream>>>(b->d_sig_bucket.as<uint32_t>(), b->d_sig_arrival.as<uint32_t>(), base, scalars, cap, b->sig_sub_mask, perm,
+                                                        b->d_reg_tab.as<uint32_t>(), b->n_regions, b->d_reg_sig_cnt.as<uint32_t>());
         const GatherParams G = gather_params(b);
         k_bucket_rank_gather<<<grid, 256, 0, ctx->stream>>>(G, perm, b->d_sig_bucket.as<uint32_t>(), base);
         ctx->launches += 2;
@@ -224,7 +246,7 @@ int launch_sig_finish(csv_ctx* ctx, csv_batch* b)
     uint32_t mask = 0x0fu;                                                       // start
     for (int d = 0; d < 4; d++) if (d == 0 ? b->n_regions > 1 : (b->n_regions >> (8 * d))) mask |= 1u << (4 + d);   // owner region
     // the sort's first kernel clamps the emitted count to the capacity (SC_N_SIG_EFF) and numbers the entries
-    const SortFirst first = {scalars + SC_N_SIG, cap, scalars + SC_N_SIG_EFF, true};
+    const SortFirst first = {scalars + SC_SIG_SUB0, cap, scalars + SC_N_SIG_EFF, true};   // one counter, dense slots (csv_batch::sig_sub_mask == 0)
     CSV_TRY(radix_sort_pairs(ctx, sb, cap, scalars + SC_N_SIG_EFF, mask, &first));
     k_sig_tiefix<<<grid, 256, 0, ctx->stream>>>(sb.lo, b->d_sig_lo.as<unsigned long long>(), sb.val, scalars, sb.val2);
     ctx->launches++;

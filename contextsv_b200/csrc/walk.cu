@@ -57,6 +57,7 @@ struct WalkParams {
     const uint32_t* reg_tab;    // [tile_base (n_regions + 1) | len (n_regions) | beg (n_regions)], caller order
     uint32_t n_regions;
     uint32_t* bucket_cnt;       // signatures per depth tile
+    uint32_t sig_sub_mask;      // kSigSub - 1: slot counters in use (0: one counter, dense slots -- the radix order needs them dense)
 };
 
 
@@ -515,14 +516,16 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                         const bool beyond = pos1 >= m.y;
                         const uint32_t start = pos1, end = start + len - 1u;
                         if (!(op == 4 && beyond) && start <= end) {          // sv_caller.cpp:602-604, sv_object.cpp:25-28
-                            const uint32_t sl = atomicAdd(&P.scalars[SC_N_SIG], 1u);
-                            if (sl < P.sig_cap) {
+                            const uint32_t sub = blockIdx.x & P.sig_sub_mask;
+                            const uint32_t sl = atomicAdd(&P.scalars[SC_SIG_SUB0 + sub], 1u) * (P.sig_sub_mask + 1u) + sub;
+                            if (sl >= P.sig_cap) P.scalars[SC_SIG_DROPPED] = 1u;
+                            else {
                                 P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
                                 P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
                                 P.sig.k[sl] = k;
                                 const uint32_t kind = op == 1 ? 0u : (op == 2 ? 1u : 2u);
                                 P.sig.kind[sl] = (uint8_t)(kind | ((beyond || (int32_t)m.x < 0) ? 0x80u : 0u));
-                                atomicAdd(&P.reg_sig_cnt[m.w], 1u);
+                                if (P.sig_sub_mask == 0) atomicAdd(&P.reg_sig_cnt[m.w], 1u);   // (with the bucket order the counts per region fall out of the bucket scan: sigs.cu)
                                 // the ordering's bucket: the depth tile of the owner region the start falls into (clamped into
                                 // the region: monotone in start, which is all the bucket order needs)
                                 const uint32_t tb = P.reg_tab[m.w], nt = P.reg_tab[m.w + 1u] - tb, beg = P.reg_tab[2u * P.n_regions + 1u + m.w];
@@ -603,6 +606,7 @@ static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
     P.reg_tab = b->d_reg_tab.as<uint32_t>();
     P.n_regions = b->n_regions;
     P.bucket_cnt = b->d_bucket_cnt.as<uint32_t>();
+    P.sig_sub_mask = b->sig_sub_mask;
     P.sig_cap = (uint32_t)b->sig_cap;
     P.reg_sig_cnt = b->d_reg_sig_cnt.as<uint32_t>();
     P.span_rq = b->d_span_rq.as<uint2>();
