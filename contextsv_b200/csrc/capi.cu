@@ -329,7 +329,9 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         return regions[a].tid != regions[b].tid ? regions[a].tid < regions[b].tid : regions[a].beg < regions[b].beg;
     });
-    std::unique_ptr<csv_batch> b(new csv_batch);
+    // an error return below hands every buffer allocated so far back to the context's pool (out of memory is the likely one)
+    struct Releaser { csv_ctx* ctx; void operator()(csv_batch* x) const { if (x) { x->release(&ctx->pool); delete x; } } };
+    std::unique_ptr<csv_batch, Releaser> b(new csv_batch, Releaser{ctx});
     b->n_reads = r->n_reads; b->n_ops = r->n_ops; b->n_regions = n_regions; b->n_tids = (uint32_t)max_tid + 1;
     b->has_tid = r->tid != nullptr;
     b->regions.assign(regions, regions + n_regions);

@@ -639,6 +639,39 @@ def test_signature_pileup_at_one_start(ctx, oracle):
     b.free()
 
 
+def test_more_signatures_than_the_batch_reserved(ctx, oracle):
+    """A batch reserves room for max(2^20, ops / 16) signatures; clip- and insertion-heavy records can emit more (the
+    reference's vector has no limit).  4.8 M ops, every second one a 60-base insertion: 2.4 M signatures against room for
+    1.05 M, in a batch large enough for the 32 slot counters.  The pass must report the overflow with the size to reserve
+    (csv_sigs_fetch -> CSV_ERR_CAPACITY, csv_batch_reserve_sigs), the rescan (dense slots) must give the reference's vector
+    and the depth must be untouched by any of it."""
+    n, per = 300_000, 16
+    rng = np.random.default_rng(11)
+    pos0 = np.sort(rng.integers(0, 2_000_000, n)).astype(np.int32)
+    one = np.array([(60 << 4) | I, (10 << 4) | M] * (per // 2), np.uint32)
+    r = {"n_reads": n, "n_ops": n * per, "tid": np.zeros(n, np.int32), "pos0": pos0, "flag": np.zeros(n, np.uint16),
+         "mapq": np.full(n, 60, np.uint8), "cig_off": (np.arange(n + 1, dtype=np.uint64) * per), "cigar": np.tile(one, n)}
+    clen = [2_100_000]
+    assert r["n_ops"] >= (1 << 22)
+    b = run_batch(ctx, r, api.whole_contig_regions(clen))
+    out = {k: np.zeros(8, dt) for k, dt in (("start", np.uint32), ("end", np.uint32), ("kind", np.uint8), ("read_idx", np.uint32), ("op_idx", np.uint32), ("query_pos", np.uint32))}
+    sig = CsvSigs(*[ptr(out[k]) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")])
+    n_out = C.c_uint64(0)
+    rc = lib().csv_sigs_fetch(ctx.h, b.h, C.byref(sig), 8, C.byref(n_out), None)
+    assert rc == 3 and n_out.value > n * per // 2, "the overflow must be reported with what to reserve"      # CSV_ERR_CAPACITY
+    sg = b.sigs()                                            # reserves what was reported and scans again
+    assert len(sg["start"]) == n * per // 2
+    o = oracle.cigar_scan(r, 0, clen[0] + 1)
+    for f in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+        assert np.array_equal(sg[f], o[f]), f
+    d, s_, nz_ = oracle.depth(r, 0, clen[0] + 1)
+    sums, nzs = b.depth_stats()
+    assert np.array_equal(b.depth(0), d) and int(sums[0]) == s_ and int(nzs[0]) == nz_
+    lab = b.sigs_dbscan1d(100.0, 5)
+    assert np.array_equal(lab, oracle.dbscan1d(sg["start"].astype(np.int32), 100.0, 5, fast=True))       # one group: every signature is an insertion
+    b.free()
+
+
 def test_sv_rich_sweep_eps_minpts(ctx, oracle):
     """BASELINE config 5 in small: SV-rich reads with per-read breakpoint jitter, DBSCAN1D over the signature starts
     of every (contig, SVType) group for the whole eps x minPts grid."""
