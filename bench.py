@@ -744,11 +744,17 @@ def main_ours(args):
         dist.all_reduce(t)
         read_bases = [int(x) for x in t.tolist()]
 
+    step_s = []                 # wall time of every step of the last timed() call on this rank
+
     def timed(step, n_steps):
         barrier()
+        del step_s[:]
         t0 = time.perf_counter()
+        t_prev = t0
         for _ in range(n_steps):
             r = step()
+            t_now = time.perf_counter()                 # (every e2e step ends with its results in host memory)
+            step_s.append(t_now - t_prev); t_prev = t_now
         ctx.sync()
         dt = time.perf_counter() - t0
         barrier()
@@ -780,10 +786,18 @@ def main_ours(args):
         checksums = {"depth": hashlib.blake2b(per_contig.tobytes(), digest_size=8).hexdigest(), "depth_sum": int(tot_contig[0::2].sum()), "depth_nonzero": int(tot_contig[1::2].sum()), "signatures": dg[0], "dbscan1d_labels": dg[1], "depth_at_signature_start": dg[2],
                      "signatures_total": int(sum(len(m["start"]) for m in merged.values())), "contigs_refit_after_merge": n_split}
     if args.skip_e2e:        # profiling runs only (ncu): never used for a reported number
-        e2e_steps, dt_max, e2e_value = 0, 0.0, None
+        e2e_steps, dt_max, e2e_value, e2e_each, e2e_retimed = 0, 0.0, None, [], None
     else:
         step_e2e()
         dt_max, _ = timed(step_e2e, e2e_steps)
+        e2e_each = [round(1e3 * x, 3) for x in step_s]
+        # the same rule as for the device-timed steps: one step more than twice the median of the others means the run was
+        # disturbed from outside (the hosts of the pool are shared); measured once more, both reported
+        e2e_retimed = None
+        if e2e_steps >= 3 and max_over_ranks(1.0 if max(step_s) > 2.0 * float(np.median(step_s)) else 0.0) > 0.5:
+            e2e_retimed = {"first_ms_per_step": 1e3 * dt_max / e2e_steps, "first_ms_each_rank0": e2e_each}
+            dt_max, _ = timed(step_e2e, e2e_steps)
+            e2e_each = [round(1e3 * x, 3) for x in step_s]
         e2e_value = genome_reads * e2e_steps / dt_max
 
     # ---- sharded run: the single-device answer for the same genome, computed here and now on rank 0
@@ -871,7 +885,7 @@ def main_ours(args):
                        "ms_per_step_fastest_rank": ms_min / args.steps, "host_generation_s": round(t_gen, 2), "cpu_affinity_rank0": numa},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
+                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "ms_each_rank0": e2e_each, "retimed": e2e_retimed, "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
                     "result": "mean coverage inputs, signature vectors, DBSCAN1D labels, depth at every signature start in host memory; the per-base map stays in HBM" +
                               ("; contigs the plan cut are merged and re-fit by the rank that holds their first region (the other runs come through shared memory on the box)" if strong else "")},
             "e2e_full_map": full_map,

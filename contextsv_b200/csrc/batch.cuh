@@ -48,7 +48,7 @@ struct csv_batch {
     bool inputs_released = false;             // csv_batch_release_inputs: only the results are left (depth slabs, signature columns, labels)
 
     // input SoA (device)
-    csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar, d_n_gap, d_ref_len, d_ref_chk;
+    csv::DevBuf d_tid, d_pos0, d_flag, d_mapq, d_cig_off, d_cigar, d_n_gap, d_ref_len, d_ref_chk, d_ev_check;
     // derived per-read tables
     csv::DevBuf d_meta;      // uint4 {pos0, map_size | 0 (contig not requested), flag | mapq << 16, owner region | kNone} per non-empty read
     csv::DevBuf d_key;       // u64 (tid << 32 | pos0 + 1) per non-empty read: the batch's sort key
@@ -76,7 +76,7 @@ struct csv_batch {
     csv::DevBuf d_out_start, d_out_end, d_out_kind, d_out_read, d_out_op, d_out_qpos, d_out_seg, d_labels;
 
     void release(csv::DevPool* pool = nullptr) {
-        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_ref_len, &d_ref_chk, &d_span_rq, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
+        csv::DevBuf* all[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_ref_len, &d_ref_chk, &d_ev_check, &d_span_rq, &d_meta, &d_key, &d_ne_idx, &d_headbits, &d_scalars,
                               &d_regs, &d_tids, &d_reg_tab, &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds,
                               &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_depth, &d_sum, &d_nz, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r, &d_sig_hi, &d_sig_lo, &d_sig_k,
                               &d_sig_kind, &d_sig_payload, &d_sig_bucket, &d_sig_arrival, &d_bucket_cnt, &d_bucket_base, &d_out_start, &d_out_end, &d_out_kind, &d_out_read, &d_out_op,
@@ -85,7 +85,7 @@ struct csv_batch {
     }
     // everything a pass reads or writes on the way to the results; what stays serves the depth consumers and the fetches
     void release_inputs(csv::DevPool* pool) {
-        csv::DevBuf* in[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_ref_len, &d_ref_chk, &d_span_rq, &d_meta, &d_key, &d_ne_idx, &d_headbits,
+        csv::DevBuf* in[] = {&d_tid, &d_pos0, &d_flag, &d_mapq, &d_cig_off, &d_cigar, &d_n_gap, &d_ref_len, &d_ref_chk, &d_ev_check, &d_span_rq, &d_meta, &d_key, &d_ne_idx, &d_headbits,
                              &d_span_agg, &d_span_pre, &d_span_status, &d_scan_carry, &d_span_desc, &d_chunk_tid, &d_chunk_bounds,
                              &d_events, &d_ev_start, &d_ref_end, &d_pmax, &d_pmax_part, &d_tile_desc, &d_tile_ev, &d_tile_sum, &d_tile_nz, &d_wide_list, &d_tile_q, &d_tile_r,
                              &d_sig_hi, &d_sig_lo, &d_sig_k, &d_sig_kind, &d_sig_payload, &d_sig_bucket, &d_sig_arrival, &d_bucket_cnt, &d_bucket_base};
@@ -99,6 +99,7 @@ namespace csv {
 int launch_prep(csv_ctx* ctx, csv_batch* b, uint32_t min_mapq);
 int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int what = 3);
 int launch_claim_check(csv_ctx* ctx, csv_batch* b);
+int launch_ev_check(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p);
 int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1);
 int launch_chunk_bounds(csv_ctx* ctx, csv_batch* b);
 int launch_tile_hi(csv_ctx* ctx, csv_batch* b);

@@ -417,7 +417,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     if (b->has_tid) CSV_TRY(b->d_tid.ensure(nr * 4 + 16, &ctx->pool));
     CSV_TRY(b->d_pos0.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_flag.ensure(nr * 2 + 16, &ctx->pool)); CSV_TRY(b->d_mapq.ensure(nr + 16, &ctx->pool));
     CSV_TRY(b->d_cig_off.ensure((nr + 1) * 8, &ctx->pool)); CSV_TRY(b->d_cigar.ensure(no * 4 + 64, &ctx->pool));
-    if (b->rec_prepass) CSV_TRY(b->d_n_gap.ensure(nr * 4 + 16, &ctx->pool));
+    if (b->rec_prepass) { CSV_TRY(b->d_n_gap.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ev_check.ensure((nr + 2) * 4, &ctx->pool)); }
     if (b->claimed_ref) { CSV_TRY(b->d_ref_len.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_ref_chk.ensure(nr * 4 + 16, &ctx->pool)); }
     CSV_TRY(b->d_span_rq.ensure(((size_t)b->n_spans + 2) * 8, &ctx->pool));
     CSV_TRY(b->d_meta.ensure(nr * 16 + 16, &ctx->pool)); CSV_TRY(b->d_key.ensure(nr * 8 + 16, &ctx->pool)); CSV_TRY(b->d_ne_idx.ensure(nr * 4 + 16, &ctx->pool)); CSV_TRY(b->d_headbits.ensure(no / 8 + 512, &ctx->pool));   // the walk copies 272 bytes per span, also for the last one
@@ -582,7 +582,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
             // kernel: different tiles, nothing shared; the reductions wait for both
             CSV_CUDA(cudaEventRecord(ctx->ev_join, ctx->main_stream));
             CSV_CUDA(cudaStreamWaitEvent(ctx->tile_stream, ctx->ev_join, 0));
-            { TileScope ts(ctx); CSV_TRY(launch_depth_finish(ctx, b, 1)); }
+            { TileScope ts(ctx); CSV_TRY(launch_depth_finish(ctx, b, 1)); CSV_TRY(launch_ev_check(ctx, b, p)); }   // ... and so does the check of the caller's D/N counts
             CSV_CUDA(cudaEventRecord(ctx->ev_tile_join, ctx->tile_stream));
             ctx->tile_busy = false;
             StageTimer t(ctx, ST_DEPTH_TILES);
@@ -620,6 +620,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
     }
     }
     if (ranges_first) CSV_TRY(launch_claim_check(ctx, b));              // main stream, beside the tiles: only the fetches wait for it
+    if (nc > 1 || !p->want_depth) CSV_TRY(launch_ev_check(ctx, b, p));   // (single-chunk depth passes ran it beside the tiles)
     b->scanned = true; b->have_depth = p->want_depth != 0; b->have_sigs = p->want_sigs != 0; b->have_labels = false;
     return CSV_OK;
 }

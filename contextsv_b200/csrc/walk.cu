@@ -43,7 +43,8 @@ struct WalkParams {
     const uint32_t* n_gap;      // [n_reads] or null
     const unsigned long long* cig_off;
     const uint32_t* ne_idx;     // compact index -> record index
-    uint32_t ev_given;          // ev_start[] comes from the record scan (csv_reads::n_gap): the walk compares instead of writing
+    uint32_t ev_given;          // ev_start[] comes from the record scan (csv_reads::n_gap): the walk leaves what it finds in ev_check[]
+    uint32_t* ev_check;         // [n_nonempty + 1] event slot reached at the end of every record (k_ev_check compares after the walk)
     uint32_t* events;
     uint32_t ev_cap;
     uint32_t* ev_start;     // [n_nonempty + 1] first event slot of each record
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                         // CIGAR says: the event slots right here, the reference length by k_claim_check after the walk (then
                         // P.ref_end is the batch's check array); a wrong count voids the pass (CSV_ERR_ARG at the first fetch)
                         P.ref_end[kt] = re;
-                        if (P.ev_given) { if (P.ev_start[kt + 1u] != slot) P.scalars[SC_BAD_GAPS] = 1u; } else P.ev_start[kt + 1u] = slot;
+                        (P.ev_given ? P.ev_check : P.ev_start)[kt + 1u] = slot;   // a store, not a dependent load in the sparse loop: the claim is compared by k_ev_check
                     }
                     if (b < t.n_valid) {
                         klb++;
@@ -614,6 +615,7 @@ static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
     P.cig_off = b->d_cig_off.as<unsigned long long>();
     P.ne_idx = b->d_ne_idx.as<uint32_t>();
     P.ev_given = b->rec_prepass ? 1u : 0u;
+    P.ev_check = b->d_ev_check.as<uint32_t>();
     return P;
 }
 
@@ -655,6 +657,26 @@ int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, 
                 ctx->launches++;
             }
     }
+    CSV_CUDA(cudaGetLastError());
+    return CSV_OK;
+}
+
+// csv_reads::n_gap against the CIGARs: the event slot the record scan derived for the end of every record and the one the
+// walk reached there.  Beside the tiles; only the fetches wait for the verdict.
+__global__ void __launch_bounds__(256) k_ev_check(const uint32_t* __restrict__ ev_start, const uint32_t* __restrict__ ev_check, uint32_t* scalars)
+{
+    const uint32_t n = scalars[SC_N_NONEMPTY];
+    bool bad = false;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) bad |= ev_start[k + 1u] != ev_check[k + 1u];
+    if (bad) scalars[SC_BAD_GAPS] = 1u;
+}
+
+int launch_ev_check(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
+{
+    if (!b->rec_prepass || !p->want_depth || b->n_ops == 0) return CSV_OK;
+    const uint32_t grid = (b->n_reads + 255) / 256 < (uint32_t)ctx->sm_count * 2 ? (b->n_reads + 255) / 256 : (uint32_t)ctx->sm_count * 2;
+    k_ev_check<<<grid, 256, 0, ctx->stream>>>(b->d_ev_start.as<uint32_t>(), b->d_ev_check.as<uint32_t>(), b->d_scalars.as<uint32_t>());
+    ctx->launches++;
     CSV_CUDA(cudaGetLastError());
     return CSV_OK;
 }
