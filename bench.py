@@ -614,11 +614,7 @@ def main_ours(args):
     region_tid = np.array([t for (t, _, _, _) in regions], np.int32)
 
     phases = {}
-    holders = {}                 # contig -> ranks that hold a region of it, in genome order
-    for r_, regs_ in enumerate(plan if strong else []):
-        for (t_, _, _, _) in regs_:
-            if r_ not in holders.setdefault(t_, []):
-                holders[t_].append(r_)
+    holders = shard.contig_holders(plan) if strong else {}      # contig -> ranks that hold a region of it, in genome order
     my_cut_contigs = [t_ for t_, rs in sorted(holders.items()) if len(rs) > 1 and rs[0] == rank]
 
     def step_e2e(want_checksum=False):
@@ -917,7 +913,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N > 1: strong (default) = one genome region-sharded over the ranks [BASELINE configs[3]]; weak = one whole genome per rank")
     ap.add_argument("--seed", type=int, default=20261018 + 2)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--no-full-map", action="store_true", help="skip the extra e2e_full_map measurement")

@@ -64,6 +64,30 @@ def plan_regions(contig_len, n_shards, reads=None, op_cost=OP_COST):
     return shards
 
 
+def contig_holders(plan):
+    """plan (plan_regions): contig id -> the shards that hold a region of it, in genome order.  A contig with more than one
+    holder was cut; the FIRST holder finalises it (merges the holders' signature runs, re-fits its clusters)."""
+    holders = {}
+    for k, regs in enumerate(plan):
+        for (tid, _, _, _) in regs:
+            if k not in holders.setdefault(tid, []):
+                holders[tid].append(k)
+    return holders
+
+
+def contig_part(sigs, regions, base, tid, extra=()):
+    """The runs of one shard that belong to contig `tid`, as merge_signatures parts [(sigs restricted, [region], base), ...]."""
+    parts = []
+    for ri, g in enumerate(regions):
+        if g[0] != tid:
+            continue
+        lo, hi = int(sigs["region_off"][ri]), int(sigs["region_off"][ri + 1])
+        d = {k: sigs[k][lo:hi] for k in SIG_FIELDS + tuple(extra)}
+        d["region_off"] = np.array([0, hi - lo], np.uint64)
+        parts.append((d, [g], base))
+    return parts
+
+
 REF_MASK = (1 << 0) | (1 << 2) | (1 << 3) | (1 << 7) | (1 << 8)
 
 

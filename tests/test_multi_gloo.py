@@ -69,6 +69,58 @@ def worker(rank, world, port, seed, q):
     dist.destroy_process_group()
 
 
+def worker_owner_merge(rank, world, port, seed, q):
+    """The sharded bench's flow: no rank 0 bottleneck.  Every contig is finalised by the shard that holds its FIRST region:
+    contigs it holds whole are its own run; a contig the plan cut is merged there from the holders' runs."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    O = Oracle()
+    reads = synth.generate(CLEN, seed=seed, n_sv=90, coverage=15.0, threads=1)
+    plan = shard.plan_regions(CLEN, world, reads)                 # cost-balanced cuts
+    regions = plan[rank]
+    sub, base = shard.select_reads(reads, regions)
+    _, _, _, sg = scan_shard_with_oracle(O, sub, regions)
+    board = [None] * world                                        # what the shared-memory board of bench.py holds
+    dist.all_gather_object(board, (sg, base))
+    holders = shard.contig_holders(plan)
+    final = {}
+    for t, ranks in holders.items():
+        if ranks[0] != rank:
+            continue
+        parts = [p for r in ranks for p in shard.contig_part(board[r][0], plan[r], board[r][1], t)]
+        final[t] = shard.merge_signatures(parts)[t]
+    collected = [None] * world
+    dist.gather_object(final, collected if rank == 0 else None, dst=0)
+    if rank == 0:
+        ok = any(len(r) > 1 for r in holders.values())            # the plan must cut a contig, or the test shows nothing
+        owned = {}
+        for f in collected:
+            assert not (set(f) & set(owned))
+            owned.update(f)
+        for t in range(len(CLEN)):
+            o = O.cigar_scan(reads, t, CLEN[t] + 1)
+            ok &= t in owned
+            for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos"):
+                ok &= np.array_equal(np.asarray(owned[t][k]).astype(np.int64), o[k].astype(np.int64))
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_owner_finalises_cut_contigs_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker_owner_merge, args=(r, 2, port, 37, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
 def test_two_rank_region_sharding_gloo():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
