@@ -215,6 +215,7 @@ void csv_ctx_destroy(csv_ctx* ctx)
 int csv_ctx_sync(csv_ctx* ctx)
 {
     if (!ctx) { set_error("null context"); return CSV_ERR_ARG; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaStreamSynchronize(ctx->stream));
     return CSV_OK;
@@ -230,12 +231,14 @@ void csv_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int csv_timer_begin(csv_ctx* ctx)
 {
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     return CSV_OK;
 }
 int csv_timer_end(csv_ctx* ctx, float* ms_out)
 {
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     CSV_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -283,6 +286,7 @@ int csv_profile_read(csv_ctx* ctx, int max_stages, const char** names_out, doubl
 {
     static const char* kNames[ST_COUNT] = {"prep", "walk", "tile_ranges", "depth_tiles", "sig_sort", "dbscan1d", "k_depth_tiles16"};
     if (!ctx) { set_error("null context"); return -CSV_ERR_ARG; }
+    cudaSetDevice(ctx->device);
     if (side_join(ctx) != CSV_OK || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("csv_profile_read: stream synchronisation failed"); return -CSV_ERR_CUDA; }
     for (int s = 0; s < ST_COUNT; s++) {
         for (auto& e : ctx->stage_events[s]) {
@@ -519,6 +523,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
 {
     if (!ctx || !b || !p) { set_error("csv_scan_run: null argument"); return CSV_ERR_ARG; }
     if (!p->want_depth && !p->want_sigs) { set_error("csv_scan_run: nothing requested"); return CSV_ERR_ARG; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     if (b->inputs_released) { set_error("csv_scan_run: the batch's inputs were released (csv_batch_release_inputs): only its results are left"); return CSV_ERR_STATE; }
     CSV_TRY(side_join(ctx));            // the previous pass's signature work may still be reading this batch
     cudaStream_t st = ctx->stream;
@@ -629,6 +634,7 @@ int csv_depth_stats(csv_ctx* ctx, csv_batch* b, uint64_t* sum_out, uint32_t* non
 {
     if (!ctx || !b) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_stats: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     uint32_t sc[SC_COUNT];
     CSV_TRY(check_overflow(ctx, b, sc));
     if (sum_out) CSV_CUDA(cudaMemcpyAsync(sum_out, b->d_sum.p, b->n_regions * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -641,6 +647,7 @@ int csv_depth_fetch(csv_ctx* ctx, csv_batch* b, uint32_t region, uint32_t* depth
 {
     if (!ctx || !b || !depth_out) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_fetch: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     if (region >= b->n_regions) { set_error("region %u out of range", region); return CSV_ERR_ARG; }
     CSV_TRY(side_join(ctx));             // the tiles run on their own stream
     const size_t len = b->regions[region].end - b->regions[region].beg;
@@ -652,6 +659,7 @@ int csv_depth_fetch_all(csv_ctx* ctx, csv_batch* b, uint32_t* const* depth_out)
 {
     if (!ctx || !b || !depth_out) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_fetch_all: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));
     std::vector<FetchSeg> segs;
     for (uint32_t r = 0; r < b->n_regions; r++) {
@@ -664,6 +672,7 @@ int csv_depth_fetch_all(csv_ctx* ctx, csv_batch* b, uint32_t* const* depth_out)
 int csv_depth_device_ptr(csv_ctx* ctx, csv_batch* b, uint32_t region, const uint32_t** dptr_out)
 {
     if (!ctx || !b || !dptr_out || region >= b->n_regions) { set_error("bad argument"); return CSV_ERR_ARG; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));             // work the caller enqueues on the context's stream after this call sees the finished map
     *dptr_out = b->d_depth.as<uint32_t>() + (size_t)b->tile_base[region] * kTile;
     return CSV_OK;
@@ -673,6 +682,7 @@ int csv_sigs_count(csv_ctx* ctx, csv_batch* b, uint64_t* n_out)
 {
     if (!ctx || !b || !n_out) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_count: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     uint32_t sc[SC_COUNT];
     int s = check_overflow(ctx, b, sc);
     *n_out = sc[SC_N_SIG];
@@ -683,6 +693,7 @@ int csv_sigs_fetch(csv_ctx* ctx, csv_batch* b, csv_sigs* out, uint64_t cap, uint
 {
     if (!ctx || !b || !out || !n_out) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_fetch: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     uint32_t sc[SC_COUNT];
     sc[SC_N_SIG] = 0;
     const int ovf = check_overflow(ctx, b, sc);
@@ -715,6 +726,7 @@ int csv_sigs_dbscan1d(csv_ctx* ctx, csv_batch* b, double eps, int min_pts, int32
 {
     if (!ctx || !b) { set_error("null argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_sigs) { set_error("csv_sigs_dbscan1d: run csv_scan_run with want_sigs first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     if (ctx->side_busy) {               // the signature sort is still on the side stream: follow it there
         SideScope side(ctx);
         StageTimer t(ctx, ST_DBSCAN);

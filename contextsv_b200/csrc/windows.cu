@@ -94,6 +94,7 @@ extern "C" int csv_depth_at(csv_ctx* ctx, csv_batch* b, uint32_t region, uint64_
 {
     if (!ctx || !b || (n && (!positions || !depth_out))) { set_error("csv_depth_at: bad argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_at: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     if (region >= b->n_regions) { set_error("region %u out of range", region); return CSV_ERR_ARG; }
     const csv_region& g = b->regions[region];
     if (n == 0) return CSV_OK;
@@ -118,6 +119,7 @@ extern "C" int csv_window_sums(csv_ctx* ctx, csv_batch* b, uint32_t region, uint
 {
     if (!ctx || !b || !start_pos || !end_pos || !sum_out || !count_out || sample_size <= 0) { set_error("csv_window_sums: bad argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_window_sums: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     if (region >= b->n_regions) { set_error("region %u out of range", region); return CSV_ERR_ARG; }
     const csv_region& g = b->regions[region];
     if (n_sv == 0) return CSV_OK;
@@ -154,6 +156,7 @@ extern "C" int csv_depth_at_tid(csv_ctx* ctx, csv_batch* b, uint64_t n, const in
 {
     if (!ctx || !b || (n && (!tid || !positions || !depth_out))) { set_error("csv_depth_at_tid: bad argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_at_tid: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     if (n == 0) return CSV_OK;
     CSV_TRY(side_join(ctx));
     DevBuf& io = ctx->sort_tmp[4];
@@ -175,6 +178,7 @@ extern "C" int csv_sigs_depth(csv_ctx* ctx, csv_batch* b, uint32_t* depth_out, u
 {
     if (!ctx || !b || !depth_out) { set_error("csv_sigs_depth: bad argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth || !b->have_sigs) { set_error("csv_sigs_depth: run csv_scan_run with want_depth and want_sigs first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     uint64_t n = 0;
     CSV_TRY(csv_sigs_count(ctx, b, &n));                                   // joins the side and tile streams, checks the scan
     if (n > cap) { set_error("csv_sigs_depth: %llu signatures, caller capacity %llu", (unsigned long long)n, (unsigned long long)cap); return CSV_ERR_CAPACITY; }
@@ -199,6 +203,7 @@ extern "C" int csv_depth_checksum(csv_ctx* ctx, csv_batch* b, uint64_t* checksum
 {
     if (!ctx || !b || !checksum_out) { set_error("csv_depth_checksum: bad argument"); return CSV_ERR_ARG; }
     if (!b->scanned || !b->have_depth) { set_error("csv_depth_checksum: run csv_scan_run with want_depth first"); return CSV_ERR_STATE; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));
     DevBuf& out = ctx->sort_tmp[5];
     CSV_TRY(out.ensure((size_t)b->n_regions * 8));
@@ -220,6 +225,7 @@ extern "C" int csv_depth_checksum(csv_ctx* ctx, csv_batch* b, uint64_t* checksum
 extern "C" int csv_debug_fetch(csv_ctx* ctx, csv_batch* b, const char* name, uint64_t offset, uint64_t bytes, void* out, uint64_t* size_out)
 {
     if (!ctx || !b || !name) { set_error("csv_debug_fetch: bad argument"); return CSV_ERR_ARG; }
+    CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     const size_t nr = b->n_reads, nt = b->n_tiles;
     struct { const char* name; const DevBuf* buf; size_t bytes; } tab[] = {
         {"events", &b->d_events, (size_t)b->ev_cap * 4}, {"ev_start", &b->d_ev_start, (nr + 1) * 4}, {"ref_end", &b->d_ref_end, nr * 4},

@@ -45,6 +45,28 @@ def test_cli_vcf_identical(tmp_path, extra, max_ops):
     assert got == want
 
 
+def test_cli_vcf_identical_on_two_gpus(tmp_path):
+    """CONTEXTSV_GPUS=0,1: the depth pass hands contigs (and, with a small op budget, the shards of a contig) round-robin to
+    one worker per device; depth consumers ask the device that holds the shard.  Same VCF.  Needs two GPUs (skipped on the
+    single-GPU boxes of the regular run; `gpurun --gpus 2 -- python -m pytest tests/test_dropin_cli.py -m gpu`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ref_exe, gpu_exe = os.path.join(REF_DIR, "contextsv_ref"), os.path.join(REF_DIR, "contextsv_gpu")
+    if not (os.path.exists(ref_exe) and os.path.exists(gpu_exe)):
+        pytest.skip("oracle/_ref CLIs not built (make -C oracle ref dropin)")
+    d = str(tmp_path)
+    clen, names = [150000, 90000, 60000], ["chr20", "chr21", "chr22"]
+    r = synth.generate(clen, seed=13, n_sv=70, coverage=20.0, frac_len50=0.2)
+    bamio.write_bam(d + "/x.bam", r, names, clen, seed=1)
+    bamio.write_fasta(d + "/x.fa", names, clen)
+    open(d + "/snps.vcf", "w").write("##fileformat=VCFv4.2\n")
+    want = run_cli(ref_exe, d, d + "/out_ref")
+    assert len([l for l in want if not l.startswith("#")]) > 10
+    for k, env in enumerate(({"CONTEXTSV_GPUS": "0,1"}, {"CONTEXTSV_GPUS": "0,1", "CONTEXTSV_MAX_OPS": "3000"}, {"CONTEXTSV_GPUS": "1"})):
+        assert run_cli(gpu_exe, d, d + "/out_gpu%d" % k, env=env) == want, env
+
+
 def split_bam(d, seed=23):
     clen, names = [400000, 260000], ["chr21", "chr22"]
     r = synth.generate(clen, seed=seed, n_sv=40, coverage=12.0, frac_len50=0.2)
