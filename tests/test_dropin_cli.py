@@ -26,10 +26,11 @@ def run_cli(exe, d, out, extra=(), env=None):
         return [l for l in f if not l.startswith("##fileDate")]
 
 
-@pytest.mark.parametrize("extra,max_ops", [((), None), (("-c", "chr21"), None), ((), "3000"), (("-c", "chr21"), "1500")])
+@pytest.mark.parametrize("extra,max_ops", [((), None), (("-c", "chr21"), None), ((), "3000"), (("-c", "chr21"), "1500"), ((), "host_depth"), ((), "host_depth,2500")])
 def test_cli_vcf_identical(tmp_path, extra, max_ops):
     """max_ops: the host mirror streams each chromosome in shards of at most that many CIGAR ops (what it does on its own
-    once a chromosome holds more than a batch takes -- 60x ONT); the VCF must not change."""
+    once a chromosome holds more than a batch takes -- 60x ONT); the VCF must not change.  host_depth: CONTEXTSV_HOST_DEPTH=1,
+    the depth map is also brought into the caller's vectors (narrow fetch) and its consumers read it there, like the reference."""
     ref_exe, gpu_exe = os.path.join(REF_DIR, "contextsv_ref"), os.path.join(REF_DIR, "contextsv_gpu")
     if not (os.path.exists(ref_exe) and os.path.exists(gpu_exe)):
         pytest.skip("oracle/_ref CLIs not built (make -C oracle ref dropin)")
@@ -40,7 +41,13 @@ def test_cli_vcf_identical(tmp_path, extra, max_ops):
     bamio.write_fasta(d + "/x.fa", names, clen)
     open(d + "/snps.vcf", "w").write("##fileformat=VCFv4.2\n")
     want = run_cli(ref_exe, d, d + "/out_ref", extra)
-    got = run_cli(gpu_exe, d, d + "/out_gpu", extra, {"CONTEXTSV_MAX_OPS": max_ops} if max_ops else None)
+    env = {}
+    for item in (max_ops or "").split(","):
+        if item == "host_depth":
+            env["CONTEXTSV_HOST_DEPTH"] = "1"
+        elif item:
+            env["CONTEXTSV_MAX_OPS"] = item
+    got = run_cli(gpu_exe, d, d + "/out_gpu", extra, env or None)
     assert len([l for l in want if not l.startswith("#")]) > 10
     assert got == want
 
