@@ -145,9 +145,11 @@ void csv_batch_free(csv_ctx* ctx, csv_batch* b);
 int  csv_batch_release_inputs(csv_ctx* ctx, csv_batch* b);
 
 /* Signature capacity of a batch.  Upload reserves max(2^20, n_ops / 16) entries (never more than n_ops); a pass that
- * emits more fails with CSV_ERR_CAPACITY when its results are fetched (csv_sigs_count / csv_sigs_fetch report the
- * number emitted in *n_out all the same).  Reserve that many and run the pass again: the reference's vector has no
- * limit, so a caller must not drop calls.  csv_cigar_scan does this by itself. */
+ * emits more fails with CSV_ERR_CAPACITY when its results are fetched, and csv_sigs_count / csv_sigs_fetch then report
+ * in *n_out how many entries to RESERVE (the number emitted plus the slack the 32 slot counters of a large batch need,
+ * at least 1/8 more than the current capacity).  Reserve that many and run the pass again -- it deals dense slots and fits
+ * as soon as the capacity covers the count.  The reference's vector has no limit, so a caller must not drop calls.
+ * csv_cigar_scan does this by itself. */
 int csv_batch_reserve_sigs(csv_ctx* ctx, csv_batch* b, uint64_t n_sigs);
 
 typedef struct {
