@@ -627,7 +627,9 @@ def main_ours(args):
             board.flip()
             out = {k: board.view(rank, k) for k in ("start", "end", "kind", "read_idx", "op_idx", "query_pos")}
             out_label, out_depth = board.view(rank, "label"), board.view(rank, "depth")
+        ctx.set_pipeline_chunks(args.e2e_chunks)                                   # the CIGAR words go up chunk by chunk, the scan of chunk c runs beside the upload of c + 1
         bt = api.Batch(ctx, reads, regions)                                        # H2D of the packed SoA
+        ctx.set_pipeline_chunks(1)
         bt.scan(want_depth=True, want_sigs=True)
         check(lib().csv_sigs_dbscan1d(ctx.h, bt.h, float(DB_EPS), int(DB_MIN_PTS), ptr(out_label), len(out_label)))   # DBSCAN1D + D2H labels
         n = bt.sigs_count()
@@ -881,7 +883,7 @@ def main_ours(args):
                        "ms_per_step_fastest_rank": ms_min / args.steps, "host_generation_s": round(t_gen, 2), "cpu_affinity_rank0": numa},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "ms_each_rank0": e2e_each, "retimed": e2e_retimed, "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
+                    "ms_per_step": 1e3 * dt_max / max(e2e_steps, 1), "pipeline_chunks": args.e2e_chunks, "ms_each_rank0": e2e_each, "retimed": e2e_retimed, "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
                     "result": "mean coverage inputs, signature vectors, DBSCAN1D labels, depth at every signature start in host memory; the per-base map stays in HBM" +
                               ("; contigs the plan cut are merged and re-fit by the rank that holds their first region (the other runs come through shared memory on the box)" if strong else "")},
             "e2e_full_map": full_map,
@@ -914,6 +916,7 @@ def main():
                     help="N > 1: strong (default) = one genome region-sharded over the ranks [BASELINE configs[3]]; weak = one whole genome per rank")
     ap.add_argument("--seed", type=int, default=20261018 + 2)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="pipeline chunks of the e2e batches (csv_ctx_set_pipeline_chunks): upload and scan overlap chunk by chunk; 1 = upload, then scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--no-full-map", action="store_true", help="skip the extra e2e_full_map measurement")

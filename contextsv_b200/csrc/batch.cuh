@@ -45,6 +45,7 @@ struct csv_batch {
     bool scanned = false, have_depth = false, have_sigs = false, have_labels = false;
     bool rec_prepass = false;                 // the caller supplied n_gap[] and records are short: record-level pre-pass (walk.cu)
     bool claimed_ref = false;                 // ... and csv_reads::ref_len: the tile ranges are ready before the walk ends (depth_tiles.cu)
+    bool split_upload = false;                // the CIGAR words went up chunk by chunk on the upload stream (csv_ctx::ev_upload): the walk of chunk c only waits for its own
     bool inputs_released = false;             // csv_batch_release_inputs: only the results are left (depth slabs, signature columns, labels)
 
     // input SoA (device)
@@ -97,7 +98,8 @@ struct csv_batch {
 namespace csv {
 // kernels' host launchers (each enqueues on ctx->stream and bumps ctx->launches)
 int launch_prep(csv_ctx* ctx, csv_batch* b, uint32_t min_mapq);
-int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int what = 3);
+int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int what = 3, uint32_t span_from = 0, uint32_t span_to = 0xffffffffu);
+int wait_upload(csv_ctx* ctx, csv_batch* b, uint32_t chunk_or_all);   // main stream waits for the CIGAR words of a chunk (0xffffffff: of all)
 int launch_claim_check(csv_ctx* ctx, csv_batch* b);
 int launch_ev_check(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p);
 int launch_walk(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, uint32_t span0, uint32_t span1);

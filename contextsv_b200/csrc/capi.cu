@@ -134,6 +134,14 @@ static int alloc_sig_buffers(csv_ctx* ctx, csv_batch* b)
     return CSV_OK;
 }
 
+int wait_upload(csv_ctx* ctx, csv_batch* b, uint32_t chunk_or_all)
+{
+    if (!b->split_upload) return CSV_OK;
+    const uint32_t c = chunk_or_all == 0xffffffffu ? (uint32_t)b->chunks.size() - 1u : chunk_or_all;   // one stream, in order: the last event covers all
+    CSV_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_upload[c], 0));
+    return CSV_OK;
+}
+
 }  // namespace csv
 
 using namespace csv;
@@ -169,6 +177,7 @@ int csv_ctx_create(int device, csv_ctx** out)
     if (getenv("CSV_SIDE_PRIO") && atoi(getenv("CSV_SIDE_PRIO")) == 0) prio_hi = prio_lo;     // tuning knob: side stream at normal priority
     CSV_CUDA(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
     CSV_CUDA(cudaStreamCreateWithFlags(&ctx->tile_stream, cudaStreamNonBlocking));
+    CSV_CUDA(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->main_stream;
     CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -194,7 +203,10 @@ void csv_ctx_destroy(csv_ctx* ctx)
     cudaStreamSynchronize(ctx->main_stream);
     ctx->pool.trim();
     fetch_release(ctx);
+    cudaStreamSynchronize(ctx->upload_stream);
     for (auto e : ctx->ev_chunk) cudaEventDestroy(e);
+    for (auto e : ctx->ev_upload) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->upload_stream);
     cudaEventDestroy(ctx->ev_tile_join);
     cudaStreamDestroy(ctx->tile_stream);
     for (auto& v : ctx->stage_events) for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -218,6 +230,7 @@ int csv_ctx_sync(csv_ctx* ctx)
     CSV_CUDA(cudaSetDevice(ctx->device));       // the caller may be a thread that last used another device (CONTEXTSV_GPUS)
     CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaStreamSynchronize(ctx->stream));
+    CSV_CUDA(cudaStreamSynchronize(ctx->upload_stream));     // uploads in flight from pinned host arrays
     return CSV_OK;
 }
 
@@ -458,7 +471,22 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
     } else {
         CSV_CUDA(cudaMemsetAsync(b->d_cig_off.p, 0, 8, st));
     }
-    if (no) CSV_CUDA(cudaMemcpyAsync(b->d_cigar.p, r->cigar, no * 4, cudaMemcpyHostToDevice, st));
+    // The CIGAR words are nine tenths of the upload.  A batch that will be scanned in pipeline chunks gets them chunk by
+    // chunk on the upload stream, an event behind each: the walk of chunk c waits for its own words only, and the scan
+    // of the first chunks runs while the last ones are still crossing PCIe (csv_scan_run).
+    b->split_upload = no != 0 && b->chunks.size() > 1;
+    if (b->split_upload) {
+        while (ctx->ev_upload.size() < b->chunks.size()) {
+            cudaEvent_t e = nullptr;
+            CSV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_upload.push_back(e);
+        }
+        for (size_t c = 0; c < b->chunks.size(); c++) {
+            const size_t o0 = (size_t)b->chunks[c].span0 * kWalkSpan, o1 = std::min<size_t>((size_t)b->chunks[c].span1 * kWalkSpan, no);
+            if (o1 > o0) CSV_CUDA(cudaMemcpyAsync(b->d_cigar.as<uint32_t>() + o0, r->cigar + o0, (o1 - o0) * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+            CSV_CUDA(cudaEventRecord(ctx->ev_upload[c], ctx->upload_stream));
+        }
+    } else if (no) CSV_CUDA(cudaMemcpyAsync(b->d_cigar.p, r->cigar, no * 4, cudaMemcpyHostToDevice, st));
     // table copies come from temporaries: make them synchronous with respect to the host
     CSV_CUDA(cudaMemcpyAsync(b->d_regs.p, regs.data(), regs.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, st));
     CSV_CUDA(cudaMemcpyAsync(b->d_tids.p, tids.data(), tids.size() * sizeof(TidDev), cudaMemcpyHostToDevice, st));
@@ -488,7 +516,7 @@ int csv_batch_upload(csv_ctx* ctx, const csv_reads* r, uint32_t n_regions, const
 void csv_batch_free(csv_ctx* ctx, csv_batch* b)
 {
     if (!b) return;
-    if (ctx) { cudaSetDevice(ctx->device); side_join(ctx); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); side_join(ctx); cudaStreamSynchronize(ctx->stream); if (b->split_upload) cudaStreamSynchronize(ctx->upload_stream); }
     b->release(ctx ? &ctx->pool : nullptr);
     delete b;
 }
@@ -500,6 +528,7 @@ int csv_batch_release_inputs(csv_ctx* ctx, csv_batch* b)
     CSV_CUDA(cudaSetDevice(ctx->device));
     CSV_TRY(side_join(ctx));
     CSV_CUDA(cudaStreamSynchronize(ctx->stream));            // the pass may still be reading them
+    if (b->split_upload) CSV_CUDA(cudaStreamSynchronize(ctx->upload_stream));
     b->release_inputs(&ctx->pool);
     return CSV_OK;
 }
@@ -563,7 +592,7 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         StageTimer t(ctx, ST_TILE_RANGES);
         CSV_TRY(launch_tile_ranges(ctx, b, 0, 2));
     }
-    { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p, 2)); }
+    if (nc == 1) { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_record_prepass(ctx, b, p, 2)); }
     if (nc == 1) {
         // One chunk: the whole critical chain stays on the main stream (walk -> prefix max -> range searches -> tiles ->
         // reductions; no cross-stream hop in it).  The signature side stream forks right behind the walk; what the tile
@@ -597,7 +626,13 @@ int csv_scan_run(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p)
         }
     } else {
     for (uint32_t c = 0; c < nc; c++) {
-        { StageTimer t(ctx, ST_WALK); CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1)); }
+        CSV_TRY(wait_upload(ctx, b, c));                               // this chunk's CIGAR words (no-op unless they came up in pieces)
+        {
+            StageTimer t(ctx, ST_WALK);
+            // the span starts of (span0, span1]: each exactly once over the chunks; the walk of chunk c reads the descriptors of span0 .. span1
+            CSV_TRY(launch_record_prepass(ctx, b, p, 2, b->chunks[c].span0, b->chunks[c].span1));
+            CSV_TRY(launch_walk(ctx, b, p, b->chunks[c].span0, b->chunks[c].span1));
+        }
         CSV_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->main_stream));
         if (p->want_depth && c >= 1) {
             const uint32_t tc = c - 1;                                   // its records are complete now

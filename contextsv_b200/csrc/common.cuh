@@ -138,6 +138,8 @@ struct csv_ctx {
     cudaStream_t main_stream = nullptr; // depth pipeline, copies, timers
     cudaStream_t side_stream = nullptr; // signature sort + DBSCAN1D: only depend on the walk, run beside the depth tiles
     cudaStream_t tile_stream = nullptr; // tile ranges + depth tiles of chunk c, beside the walk of chunks c + 2, c + 3, ...
+    cudaStream_t upload_stream = nullptr; // CIGAR words of a batch that is scanned in pipeline chunks: chunk by chunk, an event each
+    std::vector<cudaEvent_t> ev_upload; // chunk c's CIGAR words have arrived (upload stream)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tile_join = nullptr;
     std::vector<cudaEvent_t> ev_chunk;  // walk of chunk c finished (main stream)
     bool side_busy = false, tile_busy = false;

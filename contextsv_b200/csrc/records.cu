@@ -60,6 +60,7 @@ extern "C" int csv_record_summary(csv_ctx* ctx, csv_batch* b, int32_t* endpos_ou
     if (n == 0 || (!endpos_out && !query_start_out && !query_end_out)) return CSV_OK;
     CSV_CUDA(cudaSetDevice(ctx->device));
     CSV_TRY(side_join(ctx));
+    CSV_TRY(wait_upload(ctx, b, 0xffffffffu));
     DevBuf& out = ctx->sort_tmp[5];
     CSV_TRY(out.ensure((size_t)n * 12));
     int32_t* d_e = out.as<int32_t>(); int32_t* d_s = d_e + n; int32_t* d_q = d_s + n;

@@ -283,11 +283,11 @@ __global__ void __launch_bounds__(256) k_span_finalize(const WalkParams P)
 // gather.  A record far longer than a span pays O(ops) per span start it crosses: the batch-level test in
 // csv_batch_upload keeps such batches (ONT) on the op-level pre-pass.
 constexpr uint32_t kCarryLanes = 8;
-__global__ void __launch_bounds__(256) k_span_carry(const WalkParams P, uint32_t n_carry)
+__global__ void __launch_bounds__(256) k_span_carry(const WalkParams P, uint32_t s_first, uint32_t s_last)   // span starts s_first .. s_last (inclusive)
 {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / kCarryLanes, gl = threadIdx.x % kCarryLanes;
-    const uint32_t s = g + 1u;
-    const bool live = s <= n_carry;
+    const uint32_t s = g + s_first;
+    const bool live = s <= s_last;
     uint4 d = make_uint4(0u, 0u, 0u, 0u);
     if (live) d = P.span_desc[s];
     const uint32_t B = s * (uint32_t)kWalkSpan;
@@ -621,7 +621,9 @@ static WalkParams walk_params(csv_batch* b, const csv_scan_params* p)
 
 // Record-level pre-pass of a batch whose caller counted the D / N ops per record: once per pass, before the walk.
 // what: 1 = the record scan (event slots, span starts parked), 2 = the span carry, 3 = both
-int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int what)
+// span_from / span_to (what & 2): only the span starts in (span_from, span_to] -- the pipeline chunks of a batch whose CIGAR
+// words arrive chunk by chunk; every span start must be done exactly once (the kernel rewrites the parked entry)
+int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, int what, uint32_t span_from, uint32_t span_to)
 {
     if (!b->rec_prepass || b->n_ops == 0) return CSV_OK;
     const WalkParams P = walk_params(b, p);
@@ -651,9 +653,10 @@ int launch_record_prepass(csv_ctx* ctx, csv_batch* b, const csv_scan_params* p, 
     }
     if (what & 2) {
             const uint32_t n_carry = (uint32_t)(b->n_ops / kWalkSpan);               // span starts B = s * kWalkSpan, 1 <= s <= n_carry
-            if (n_carry) {
-                const uint32_t per_cta = 256 / kCarryLanes;
-                k_span_carry<<<(n_carry + per_cta - 1) / per_cta, 256, 0, ctx->stream>>>(P, n_carry);
+            const uint32_t s_first = span_from + 1u, s_last = span_to < n_carry ? span_to : n_carry;
+            if (s_first <= s_last) {
+                const uint32_t per_cta = 256 / kCarryLanes, n = s_last - s_first + 1u;
+                k_span_carry<<<(n + per_cta - 1) / per_cta, 256, 0, ctx->stream>>>(P, s_first, s_last);
                 ctx->launches++;
             }
     }
