@@ -518,8 +518,9 @@ __global__ void __launch_bounds__(kWalkThreads, MINB * 256 / kWalkThreads) k_wal
                         const uint32_t start = pos1, end = start + len - 1u;
                         if (!(op == 4 && beyond) && start <= end) {          // sv_caller.cpp:602-604, sv_object.cpp:25-28
                             const uint32_t sub = blockIdx.x & P.sig_sub_mask;
-                            const uint32_t sl = atomicAdd(&P.scalars[SC_SIG_SUB0 + sub], 1u) * (P.sig_sub_mask + 1u) + sub;
-                            if (sl >= P.sig_cap) P.scalars[SC_SIG_DROPPED] = 1u;
+                            const unsigned long long sl64 = (unsigned long long)atomicAdd(&P.scalars[SC_SIG_SUB0 + sub], 1u) * (P.sig_sub_mask + 1u) + sub;   // (64 bits: a counter that ran far beyond the capacity must not wrap into it)
+                            const uint32_t sl = (uint32_t)sl64;
+                            if (sl64 >= P.sig_cap) P.scalars[SC_SIG_DROPPED] = 1u;
                             else {
                                 P.sig.key_hi[sl] = ((unsigned long long)m.w << 32) | start;
                                 P.sig.key_lo[sl] = ((unsigned long long)end << 32) | (0xffffffffu - (g0 + j));
